@@ -1,0 +1,149 @@
+"""Pins oracle/vq_oracle.py (numpy, fp64 + fp32) and oracle/torch_port.py against vectors produced
+by the unmodified reference modules (oracle/gen_golden.py -> tests/golden/*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import L2_CASES, SEP_CASES, ST_ONEHOT, load_golden, rel_err
+from oracle import vq_oracle as O
+from oracle import torch_port as TP
+
+# The reference computes in fp32; its own distance to the fp64 truth is ~1e-6 norm-wise on outputs and
+# ~1e-5 on p_code-derived gradients (exp(-d) with d~128 amplifies fp32 rounding of d, SURVEY hard part 4).
+TOL_OUT = 2e-6
+TOL_GRAD = 5e-5
+
+
+def _table(g, dtype):
+    if "sd.learnable_table" in g:
+        lt = g["sd.learnable_table"]
+    else:
+        lt = g["sd.embedding.weight"]
+    if "sd.phn_attr.weight" in g:
+        return O.assemble_table(lt, g["sd.phn_attr.weight"], g["sd.proj_attr.weight"], g["sd.proj_attr.bias"], dtype)
+    return O.assemble_table(lt, dtype=dtype)
+
+
+@pytest.mark.parametrize("name", L2_CASES)
+def test_l2_oracle_fp64_vs_reference(name):
+    g = load_golden(name)
+    E = _table(g, np.float64)
+    stop_grad = name not in ST_ONEHOT
+    skip = name == "l2_attr_skip_train"
+    temp = float(g["sd.temp"][0])
+    f = O.l2_forward(g["x"], E, temp, stop_grad=stop_grad, skip=skip)
+    rep = O.index_mismatch_report(f["idx"], g["idx"], f["dist"])
+    assert rep["hard_mismatches"] == 0, rep
+    assert rel_err(f["p_code"], g["p_code"]) < 2e-5
+    assert rel_err(f["new_latent"], g["new_latent"]) < TOL_OUT
+    B, S, D = g["x"].shape
+    n_real = int(g["first_n_real_mel"]) * S
+    b = O.l2_backward(g["x"], E, temp, f["p_code"], g["idx"], g.get("g_p"), g.get("g_q"),
+                      stop_grad=stop_grad, first_n_real_rows=n_real, skip=skip)
+    assert rel_err(b["dx"], g["dx"]) < TOL_GRAD
+    tb = O.table_backward(b["dtable"], g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"))
+    assert rel_err(tb["d_learnable"], g["grad.learnable_table"]) < TOL_GRAD
+    if "grad.proj_attr.weight" in g:
+        assert rel_err(tb["d_proj_w"], g["grad.proj_attr.weight"]) < TOL_GRAD
+        assert rel_err(tb["d_proj_b"], g["grad.proj_attr.bias"]) < TOL_GRAD
+    if "grad.temp" in g:
+        assert abs(b["dtemp"] - g["grad.temp"][0]) <= TOL_GRAD * max(1.0, abs(g["grad.temp"][0]))
+
+
+@pytest.mark.parametrize("name", ["l2_attr_stopgrad", "l2_config1_16x200", "l2_noattr_k300_d128"])
+def test_l2_oracle_fp32_indices_and_ulp(name):
+    """fp32 restatement in the reference's evaluation order: indices identical outside near-ties,
+    new_latent bit-identical wherever the index agrees ((x + c) - x is deterministic)."""
+    g = load_golden(name)
+    E32 = _table(g, np.float32)
+    f = O.l2_forward(g["x"], E32, float(g["sd.temp"][0]), dtype=np.float32)
+    d64 = O.l2_forward(g["x"], _table(g, np.float64), float(g["sd.temp"][0]))["dist"]
+    rep = O.index_mismatch_report(f["idx"], g["idx"], d64)
+    assert rep["hard_mismatches"] == 0, rep
+    same = (f["idx"] == g["idx"])
+    assert rel_err(f["new_latent"][same], g["new_latent"][same]) < 2e-7
+
+
+@pytest.mark.parametrize("name", SEP_CASES)
+def test_separate_oracle_fp64_vs_reference(name):
+    g = load_golden(name)
+    E = _table(g, np.float64)
+    stop_grad = name not in ST_ONEHOT
+    f = O.separate_forward(g["x"], E, g["sd.asr_final_layer.weight"], g["sd.asr_final_layer.bias"],
+                           stop_grad=stop_grad, phn_attr=g.get("sd.phn_attr.weight"),
+                           proj_w=g.get("sd.proj_attr.weight"), proj_b=g.get("sd.proj_attr.bias"),
+                           emb_weight=g["sd.embedding.weight"])
+    assert np.array_equal(f["idx"], g["idx"]) or \
+        O.index_mismatch_report(f["idx"], g["idx"], -f["logits"])["hard_mismatches"] == 0
+    assert rel_err(f["p_code"], g["p_code"]) < 2e-6
+    assert rel_err(f["new_latent"], g["new_latent"]) < TOL_OUT
+    b = O.separate_backward(g["x"], E, g["sd.asr_final_layer.weight"], f["p_code"], g["idx"],
+                            g.get("g_p"), g.get("g_q"), stop_grad=stop_grad)
+    assert rel_err(b["dx"], g["dx"]) < TOL_GRAD
+    assert rel_err(b["d_asr_w"], g["grad.asr_final_layer.weight"]) < TOL_GRAD
+    assert rel_err(b["d_asr_b"], g["grad.asr_final_layer.bias"]) < TOL_GRAD
+    tb = O.table_backward(b["dtable"], g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"))
+    assert rel_err(tb["d_learnable"], g["grad.embedding.weight"]) < TOL_GRAD
+    if "grad.proj_attr.weight" in g:
+        assert rel_err(tb["d_proj_w"], g["grad.proj_attr.weight"]) < TOL_GRAD
+        assert rel_err(tb["d_proj_b"], g["grad.proj_attr.bias"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("name", ["inference_l2", "inference_sep"])
+def test_inference_oracle(name):
+    g = load_golden(name)
+    E = _table(g, np.float32)
+    assert rel_err(O.inference(g["txt"], E), g["out"]) < 1e-7
+    if "table" in g:
+        assert rel_err(E, g["table"]) < 1e-7
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_mean_forward_oracle(tag):
+    g = load_golden("mean_forward_" + tag)
+    out, lens = O.mean_forward(g["idx"], g["latent"], int(g["max_frames_per_phn"]))
+    assert np.array_equal(lens, g["lens"])
+    assert out.shape == g["out"].shape
+    assert rel_err(out, g["out"]) < 1e-6
+
+
+def test_mean_forward_all_blank_returns_none():
+    idx = np.zeros((2, 9), np.int64)
+    idx[0, 3] = 1
+    assert O.mean_forward(idx, np.random.randn(2, 9, 4), 8) is None
+
+
+def test_usage_histogram_semantics():
+    """src/util.py:139-143: cnts[i] = data.count(i)/len(data), cnts[0] = 0."""
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 7, size=500).tolist()
+    expect = [data.count(i) / len(data) for i in range(7)]
+    expect[0] = 0
+    got = O.usage_bar(O.usage_counts(np.asarray(data), 7))
+    assert np.allclose(got, expect, rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["l2_attr_stopgrad", "l2_attr_first_n", "l2_attr_st_onehot_first_n",
+                                  "l2_attr_learn_temp", "l2_attr_skip_train"])
+def test_torch_port_matches_reference(name):
+    """The fp32 ATen-op port used as the CPU baseline reproduces the reference's numbers."""
+    g = load_golden(name)
+    t = lambda k: None if k not in g else torch.from_numpy(g[k].copy())
+    x = t("x").requires_grad_(True)
+    lt = t("sd.learnable_table").requires_grad_(True)
+    pw, pb = t("sd.proj_attr.weight").requires_grad_(True), t("sd.proj_attr.bias").requires_grad_(True)
+    temp = t("sd.temp")
+    if "grad.temp" in g:
+        temp.requires_grad_(True)
+    table = TP.assemble_table(lt, t("sd.phn_attr.weight"), pw, pb)
+    p, q, idx = TP.l2_forward(x, table, temp, stop_grad=name not in ST_ONEHOT,
+                              first_n_real_mel=int(g["first_n_real_mel"]), skip=name == "l2_attr_skip_train")
+    torch.autograd.backward([p, q], [t("g_p"), t("g_q")])
+    assert np.array_equal(idx.numpy(), g["idx"])
+    assert rel_err(p.detach().numpy(), g["p_code"]) < 1e-6
+    assert rel_err(q.detach().numpy(), g["new_latent"]) < 1e-7
+    assert rel_err(x.grad.numpy(), g["dx"]) < 1e-6
+    assert rel_err(lt.grad.numpy(), g["grad.learnable_table"]) < 1e-6
+    assert rel_err(pw.grad.numpy(), g["grad.proj_attr.weight"]) < 1e-6
+    if "grad.temp" in g:
+        assert abs(temp.grad.item() - g["grad.temp"][0]) < 1e-4 * max(1, abs(g["grad.temp"][0]))
