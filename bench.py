@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- VQ bottleneck fwd+bwd frames/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 ...            # the reference's CPU op sequence (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+A "step" is one forward + backward of the quantizer over one batch of synthetic encoder frames
+(BASELINE.json configs[1]: 64 x 800 frames, K=43, D=64, phoneme-attribute codebook of
+config/semi-multi-spkr-paired-data.yaml), with upstream gradients for BOTH outputs (g_p for p_code, g_q for
+new_latent), as bin/train_vqvae.py drives it.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+B, S, K, D, DA, A = 64, 800, 43, 64, 16, 31
+N_ROWS = B * S
+RING = 8             # distinct input/output sets cycled through so that no step finds its inputs in L2
+WORKLOAD = "semi-tts L2 quantizer fwd+bwd, batch 64 x 800 frames, K=43 D=64 (config/semi-multi-spkr-paired-data.yaml codebook)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _phn_attr_tsv():
+    from helpers import phn_attr_tsv
+    return phn_attr_tsv()
+
+
+def _codebook_kwargs():
+    return dict(softmax="normal", latent_dim=D, commit_weight=0, vq_weight=0, temp=1, skip_prob=0,
+                stop_grad=True, phn_attr_pth=_phn_attr_tsv(), proj_attr=DA)
+
+
+def _inputs(seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, S, D, generator=g)
+    gp = torch.randn(B, S, K, generator=g)
+    gq = torch.randn(B, S, D, generator=g)
+    if pin:
+        x, gp, gq = x.pin_memory(), gp.pin_memory(), gq.pin_memory()
+    return [t.to(device) for t in (x, gp, gq)] if device != "cpu" else [x, gp, gq]
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's op sequence on the host cores (oracle/torch_port.py)
+# --------------------------------------------------------------------------------------------------
+def _cpu_state(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    tab = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "phn_attr_table.npy")))
+    lt = torch.randn(K, D - DA, generator=g).requires_grad_(True)
+    bound = 1.0 / np.sqrt(A)
+    pw = ((torch.rand(DA, A, generator=g) * 2 - 1) * bound).requires_grad_(True)
+    pb = ((torch.rand(DA, generator=g) * 2 - 1) * bound).requires_grad_(True)
+    return lt, tab.float(), pw, pb, torch.ones(1)
+
+
+def cpu_fwd_bwd_rate(steps, warmup, budget_s=None):
+    """frames/s of the reference op sequence (fwd + autograd bwd, both upstream grads) on all host threads."""
+    from oracle import torch_port as TP
+    torch.set_num_threads(os.cpu_count() or 1)
+    lt, tab, pw, pb, temp = _cpu_state()
+    x, gp, gq = _inputs(1)
+    x.requires_grad_(True)
+    for _ in range(warmup):
+        TP.l2_step(x, lt, tab, pw, pb, temp, gp, gq)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        TP.l2_step(x, lt, tab, pw, pb, temp, gp, gq)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return N_ROWS * done / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rate, ms, done, cores = cpu_fwd_bwd_rate(args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": "vq_fwd_bwd_frames_per_sec", "value": rate, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_step": N_ROWS, "grads": "g_p+g_q"},
+            "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d full steps of the same workload (oracle/torch_port.py: the reference's ATen op "
+                                       "sequence, src/embed.py:105-147, with torch autograd backward)" % done},
+            "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def _time_kernels(V, m, sets, iters=24):
+    """CUDA-event time of the two dominant kernels launched alone through the C ABI (ring-rotated inputs)."""
+    import ctypes
+    from semi_tts_b200 import functional as VF, _lib
+    attr, pw, pb = m.phn_attr.weight, m.proj_attr.weight, m.proj_attr.bias
+    table, enorm, _ = VF.assemble_table(m.learnable_table, attr, pw, pb)
+    flags = _lib.SCORE_L2 | _lib.STOP_GRAD
+    outs = [VF._run_forward(flags, s[0].view(N_ROWS, D), table, enorm, table, m.temp, True, None, False) for s in sets]
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    fwd_ms, bwd_ms = [], []
+    lib = _lib.load()
+    # pre-build argument structs so only the launch is inside the events
+    fa, ba, keep = [], [], []
+    for s, o in zip(sets, outs):
+        p_code, idx, q, _ = o
+        a = _lib.FwdArgs(); a.struct_size = ctypes.sizeof(_lib.FwdArgs); a.flags = flags
+        a.n_rows, a.dim, a.n_codes = N_ROWS, D, K
+        a.x, a.score_w, a.score_b, a.gather_table = s[0].data_ptr(), table.data_ptr(), enorm.data_ptr(), table.data_ptr()
+        a.temp, a.p_code, a.idx, a.new_latent = m.temp.data_ptr(), p_code.data_ptr(), idx.data_ptr(), q.data_ptr()
+        fa.append(a)
+        dx = torch.empty(N_ROWS, D, device="cuda"); dw = torch.zeros(K, D, device="cuda"); cs = torch.zeros(K, device="cuda")
+        b = _lib.BwdArgs(); b.struct_size = ctypes.sizeof(_lib.BwdArgs); b.flags = flags
+        b.n_rows, b.dim, b.n_codes, b.n_real_rows = N_ROWS, D, K, 0
+        b.x, b.score_w, b.score_b, b.gather_table, b.temp = s[0].data_ptr(), table.data_ptr(), enorm.data_ptr(), table.data_ptr(), m.temp.data_ptr()
+        b.p_code, b.idx, b.g_p, b.g_q = p_code.data_ptr(), idx.data_ptr(), s[1].data_ptr(), s[2].data_ptr()
+        b.dx, b.d_score_w, b.colsum = dx.data_ptr(), dw.data_ptr(), cs.data_ptr()
+        ba.append(b); keep.append((dx, dw, cs))
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    for i in range(iters + 4):
+        j = i % len(sets)
+        ev[0].record(stream)
+        _lib.check(lib.vqb_forward(ctypes.byref(fa[j]), sp))
+        ev[1].record(stream)
+        _lib.check(lib.vqb_backward(ctypes.byref(ba[j]), sp))
+        ev[2].record(stream)
+        torch.cuda.synchronize()
+        if i >= 4:
+            fwd_ms.append(ev[0].elapsed_time(ev[1])); bwd_ms.append(ev[1].elapsed_time(ev[2]))
+    return statistics.mean(fwd_ms), statistics.mean(bwd_ms)
+
+
+def run_ours(args, rank, world, local_rank):
+    import semi_tts_b200 as V
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (GPU arm) needs a B200; there is no CPU fallback -- use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    m = V.L2Embedding(K, False, **_codebook_kwargs()).to(dev)
+    m.train()
+    # ring of distinct device-resident input sets (weak scaling: every rank owns RING x 64 x 800 frames)
+    sets = [_inputs(1000 * rank + i, dev) for i in range(RING)]
+    for s in sets:
+        s[0].requires_grad_(True)
+
+    def step(s):
+        p, q, _, _ = m(s[0])
+        torch.autograd.backward([p, q], [s[1], s[2]])
+        if dist_on:
+            V.dist.allreduce_codebook_grads(m)
+
+    # ---- value: device-resident inputs, whole step (fwd + bwd [+ all-reduce]) captured in CUDA graphs ------
+    for p_ in m.parameters():
+        p_.grad = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s in sets[:3]:
+            step(s)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs, use_graph = [], True
+    try:
+        pool = None
+        for s in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                step(s)
+            pool = g.pool()
+            graphs.append(g)
+    except Exception as e:           # noqa: BLE001 -- report and fall back to eager launches of the same kernels
+        use_graph = False
+        graphs = []
+        torch.cuda.synchronize()
+        if rank == 0:
+            print("bench: CUDA-graph capture failed (%s); timing eager launches" % str(e).splitlines()[0], file=sys.stderr)
+
+    def run_steps(n, first=0):
+        for i in range(n):
+            if use_graph:
+                graphs[(first + i) % RING].replay()
+            else:
+                step(sets[(first + i) % RING])
+
+    def barrier():
+        if dist_on:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    run_steps(max(args.warmup, 3))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_steps(args.steps, first=args.warmup)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms_total], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = N_ROWS * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: public module API, HOST (pinned) inputs, H2D + D2H inside the timed region ---------------------
+    host_sets = [_inputs(5000 + 1000 * rank + i, "cpu", pin=True) for i in range(4)]
+    n_grad = sum(p_.numel() for p_ in m.parameters() if p_.requires_grad)
+    h_idx = torch.empty(B, S, dtype=torch.int64).pin_memory()
+    h_grad = torch.empty(n_grad + K, dtype=torch.float32).pin_memory()
+
+    def e2e_step(hs):
+        x = hs[0].to(dev, non_blocking=True).requires_grad_(True)
+        gp = hs[1].to(dev, non_blocking=True)
+        gq = hs[2].to(dev, non_blocking=True)
+        for p_ in m.parameters():
+            p_.grad = None
+        p, q, _, _ = m(x)
+        torch.autograd.backward([p, q], [gp, gq])
+        if dist_on:
+            V.dist.allreduce_codebook_grads(m)
+        h_idx.copy_(m.last_idx, non_blocking=True)
+        flat = torch.cat([p_.grad.reshape(-1) for p_ in m.parameters() if p_.requires_grad] + [m.usage.counts.float()])
+        h_grad.copy_(flat, non_blocking=True)
+        return float(h_grad[0]) if False else None
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        e2e_step(host_sets[i % 4])
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(host_sets[i % 4])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([e2e_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = N_ROWS * world * e2e_steps / (e2e_ms * 1e-3)
+    h2d = 4 * (B * S * D * 2 + B * S * K)
+    d2h = 8 * B * S + 4 * (n_grad + K)
+
+    if rank == 0:
+        fwd_ms, bwd_ms = _time_kernels(V, m, sets)
+        peak, peak_src = _peaks()
+        fwd_bytes = N_ROWS * (8 * D + 8 + 4 * K)                      # read x, write new_latent, idx(int64), p_code
+        bwd_bytes = N_ROWS * (12 * D + 8 * K + 8)                     # read x, g_q, p_code, g_p, idx; write dx
+        dom = ("vqb_bwd_simt_kernel", bwd_ms, bwd_bytes) if bwd_ms >= fwd_ms else ("vqb_fwd_simt_small_kernel", fwd_ms, fwd_bytes)
+        achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+        cpu_rate, cpu_ms, cpu_done, cores = cpu_fwd_bwd_rate(400, 3, budget_s=12.0)
+        line = {"metric": "vq_fwd_bwd_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rows_per_step_per_gpu": N_ROWS, "grads": "g_p+g_q",
+                           "launch": "cuda_graph" if use_graph else "eager",
+                           "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
+                               RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
+                           "parallelism": "dp%d (frames sharded by batch, codebook replicated%s)" % (
+                               world, ", one NCCL all-reduce of dE + histogram per step" if dist_on else "")},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "gpu_launches": 4 * args.steps,
+                "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": {"vqb_fwd_simt_small_kernel": fwd_ms, "vqb_bwd_simt_kernel": bwd_ms},
+                             "algorithmic_bytes": {"fwd": fwd_bytes, "bwd": bwd_bytes}},
+                "cpu_baseline": {"value": cpu_rate, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": "%d full steps of the same workload on the host (oracle/torch_port.py)" % cpu_done},
+                "clocks": clocks}
+        print(json.dumps(line))
+    if dist_on:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

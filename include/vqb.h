@@ -1,0 +1,169 @@
+/*
+ * vqb.h -- C ABI of libvqb200.so: the semi-tts vector-quantisation bottleneck on B200 (sm_100a).
+ *
+ * The reference (ttaoREtw/semi-tts) has no FFI: its quantizer is the Python nn.Module surface of
+ * src/embed.py (L2Embedding :57-147, SeperateEmbedding :150-205, neg_batch_l2 :208-213), bound by
+ * name at src/vqvae.py:8 and src/tts.py:5.  This header is what a torch.autograd.Function binds
+ * (through ctypes) to replace the ATen op sequence of those methods; INTEGRATION.md shows the
+ * reference-side stub.  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer owned by the caller (the PyTorch caching allocator);
+ *    the library keeps no persistent device allocations;
+ *  - all tensors are contiguous row-major fp32, indices are int64, histogram counts are int64;
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the host;
+ *  - return value 0 = success, otherwise a VQB_ERR_* code and vqb_last_error() (thread-local) holds
+ *    the message; CUDA out-of-memory keeps the substring "out of memory" (bin/train_vqvae.py:321);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Notation: N rows (= B*S encoder frames), D = latent_dim, K = vocab_size (codebook size),
+ *           A = phoneme attributes (31), D_a = proj_attr (16), D_l = D - D_a.
+ */
+#ifndef VQB_H_
+#define VQB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VQB_API __attribute__((visibility("default")))
+#else
+#define VQB_API
+#endif
+
+/* error codes */
+#define VQB_OK              0
+#define VQB_ERR_INVALID     1   /* bad argument / unsupported shape */
+#define VQB_ERR_CUDA        2   /* a CUDA runtime call failed */
+#define VQB_ERR_WORKSPACE   3   /* workspace too small */
+#define VQB_ERR_NO_DEVICE   4   /* no sm_100 device visible */
+
+/* flags (vqb_fwd_args.flags / vqb_bwd_args.flags) */
+#define VQB_SCORE_L2        0x0001u  /* score = -relu(temp) * ((|x|^2 + |e|^2) - 2 x.e)   src/embed.py:115-124,208-213 */
+#define VQB_SCORE_LINEAR    0x0002u  /* score = x.W^T + b                                 src/embed.py:190 */
+#define VQB_STOP_GRAD       0x0004u  /* gather route is F.embedding (:134 / :194-197); clear = ST-onehot (:137-138 / :199-203) */
+#define VQB_SKIP            0x0008u  /* skip connection drawn this step: new_latent = x   src/embed.py:140-142 */
+#define VQB_TEMP_GRAD       0x0010u  /* temp is an nn.Parameter: also produce d temp      src/embed.py:33-34 */
+#define VQB_SEARCH_TENSOR   0x0020u  /* fused mode only: tcgen05 bf16 search + exact fp32 re-rank (p_code must be NULL) */
+
+VQB_API int vqb_abi_version(void);
+VQB_API const char* vqb_last_error(void);
+/* number of sm_100 devices usable by this library (0 if none); never fails */
+VQB_API int vqb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Codebook table assembly  (replaces src/embed.py:109-112, the same expression in :87-94)
+ *   table[K,D] = cat([learnable[K,D_l], phn_attr[K,A] @ proj_w[D_a,A]^T + proj_b[D_a]], -1)
+ *   enorm[K]   = sum_d table[k,d]^2                      (the |e|^2 term of src/embed.py:211)
+ * phn_attr / proj_w / proj_b may be NULL (n_attr = dim_attr = 0): table = learnable.
+ * table_bf16 (optional, may be NULL): bf16 copy [K, D] for the tensor-core search.
+ * ------------------------------------------------------------------------------------------- */
+VQB_API int vqb_assemble_table(const float* learnable, const float* phn_attr, const float* proj_w,
+                       const float* proj_b, int64_t n_codes, int64_t dim, int64_t n_attr,
+                       int64_t dim_attr, float* table, float* enorm, void* table_bf16, void* stream);
+
+/* Backward of the assembly (autograd of src/embed.py:109-112):
+ *   dtable[k,:] += 2 * table[k,:] * colsum[k]     if colsum != NULL (the |e|^2 term of the L2 route)
+ *   d_learnable[K,D_l] = dtable[:, :D_l]
+ *   d_proj_w[D_a,A]    = dtable[:, D_l:]^T @ phn_attr ;  d_proj_b[D_a] = colsum_k dtable[:, D_l:]
+ * d_learnable may alias nothing; all outputs are overwritten (not accumulated). */
+VQB_API int vqb_table_backward(const float* dtable, const float* table, const float* colsum,
+                       const float* phn_attr, int64_t n_codes, int64_t dim, int64_t n_attr,
+                       int64_t dim_attr, float* d_learnable, float* d_proj_w, float* d_proj_b,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Forward  (replaces L2Embedding.forward src/embed.py:105-147 / SeperateEmbedding.forward :187-205)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vqb_fwd_args {
+    uint32_t struct_size;        /* sizeof(vqb_fwd_args) */
+    uint32_t flags;
+    int64_t n_rows, dim, n_codes;
+    const float* x;              /* [N,D]   enc_embs flattened (src/embed.py:209)                      */
+    const float* score_w;        /* [K,D]   L2: assembled table E; LINEAR: asr_final_layer.weight      */
+    const float* score_b;        /* [K]     L2: enorm |e|^2;       LINEAR: asr_final_layer.bias        */
+    const void*  score_w_bf16;   /* [K,D]   bf16 copy of score_w (only for VQB_SEARCH_TENSOR)          */
+    const float* gather_table;   /* [K,D]   codewords gathered into new_latent (L2: == score_w)        */
+    const float* temp;           /* [1]     device scalar; tau = relu(temp) (src/embed.py:115)         */
+    float*   p_code;             /* [N,K]   softmax over codes (src/embed.py:127); NULL = fused mode   */
+    int64_t* idx;                /* [N]     argmax(p_code) (src/embed.py:130)                          */
+    float*   new_latent;         /* [N,D]   L2: (x + E[idx]) - x (:145) or x if VQB_SKIP; LINEAR: T[idx] */
+    int64_t* hist;               /* [K]     += per-code usage counts of this call, or NULL
+                                            (bin/train_vqvae.py:256-261; src/util.py:139)              */
+    double*  sq_err_sum;         /* [1]     += sum (x - E[idx])^2 (numerator of the loss extensions), or NULL */
+    void*    workspace;          /* vqb_forward_workspace() bytes, or NULL if that is 0                 */
+    size_t   workspace_bytes;
+} vqb_fwd_args;
+
+VQB_API int vqb_forward_workspace(const vqb_fwd_args* args, size_t* bytes);
+VQB_API int vqb_forward(const vqb_fwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward (autograd of the above, entered from src/solver.py:144; algebra in DESIGN.md)
+ *   G   = g_p (+ g_q @ T^T when !STOP_GRAD);  Gs = P * (G - rowsum(G*P))
+ *   L2:     Gd = -tau*Gs;  dx = g_q + 2 x rowsum(Gd) - 2 Gd@E
+ *           d_score_w = -2 Gd*^T @ x + scatter_add(idx, g_q) ; colsum = colsum(Gd*)   (Gd* = rows < n_real_rows)
+ *           d_temp = sum Gs * (-dist) * [temp > 0]
+ *   LINEAR: dx = Gs@W;  d_score_w = Gs^T @ x;  colsum = colsum(Gs);  d_gather = scatter_add(idx, g_q)
+ * All outputs are ACCUMULATED into (+=): the caller zeroes d_score_w, colsum, d_gather, d_temp first.
+ * dx is overwritten.  If g_p == NULL, STOP_GRAD and L2, only the scatter route runs and dx may be
+ * NULL (the caller aliases dx = g_q: the straight-through identity costs zero bytes).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vqb_bwd_args {
+    uint32_t struct_size;
+    uint32_t flags;
+    int64_t n_rows, dim, n_codes;
+    int64_t n_real_rows;         /* first_n_real_mel * S; rows >= this do not reach the table through
+                                    the distance route (src/embed.py:115-122); <= 0 means all rows do */
+    const float* x;              /* [N,D] */
+    const float* score_w;        /* [K,D] */
+    const float* score_b;        /* [K]   (L2: enorm, needed only with VQB_TEMP_GRAD) */
+    const float* gather_table;   /* [K,D] */
+    const float* temp;           /* [1]   */
+    const float* p_code;         /* [N,K] saved forward output; NULL if g_p == NULL and STOP_GRAD */
+    const int64_t* idx;          /* [N]   */
+    const float* g_p;            /* [N,K] upstream grad of p_code, or NULL */
+    const float* g_q;            /* [N,D] upstream grad of new_latent, or NULL */
+    float* dx;                   /* [N,D] */
+    float* d_score_w;            /* [K,D] += */
+    float* colsum;               /* [K]   += */
+    float* d_gather;             /* [K,D] += (LINEAR only; L2 accumulates the scatter into d_score_w) */
+    float* d_temp;               /* [1]   += (only with VQB_TEMP_GRAD) */
+    void*  workspace;
+    size_t workspace_bytes;
+} vqb_bwd_args;
+
+VQB_API int vqb_backward_workspace(const vqb_bwd_args* args, size_t* bytes);
+VQB_API int vqb_backward(const vqb_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gather-only paths
+ * ------------------------------------------------------------------------------------------- */
+/* out[m,:] = table[txt[m],:]  (replaces L2Embedding.inference src/embed.py:96-103 and
+ * SeperateEmbedding.inference :180-185 on the assembled table).  Returns VQB_ERR_INVALID through a
+ * device-side flag only in debug builds; indices are clamped to [0,K) like a bounds-checked gather. */
+VQB_API int vqb_inference_gather(const int64_t* txt, int64_t n_tokens, const float* table, int64_t n_codes,
+                         int64_t dim, float* out, void* stream);
+
+/* dtable[txt[m],:] += g[m,:]  (autograd of the gather; F.embedding backward) */
+VQB_API int vqb_scatter_add(const int64_t* txt, int64_t n_tokens, const float* g, int64_t n_codes,
+                    int64_t dim, float* dtable, int64_t* hist, void* stream);
+
+/* Loss extensions (NO reference arithmetic; van den Oord et al. 2017): backward of
+ *   vq_loss = commit_loss = mean((x - E[idx])^2):
+ *   dx[n,:] (+)= g_commit * 2 (x - c) / (N D);  dtable[idx[n],:] += g_vq * 2 (c - x) / (N D)
+ * g_vq / g_commit are device scalars (may be NULL = 0). dx_accumulate != 0 adds into dx. */
+VQB_API int vqb_loss_backward(const float* x, const float* table, const int64_t* idx, int64_t n_rows,
+                      int64_t dim, int64_t n_codes, const float* g_vq, const float* g_commit,
+                      float* dx, int dx_accumulate, float* dtable, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB_H_ */

@@ -1,0 +1,188 @@
+// C-ABI entry points of libvqb200.so (declared in include/vqb.h): argument validation, kernel
+// selection, thread-local error string.  No CPU fallback exists anywhere in this library.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "vqb_common.cuh"
+
+namespace vqb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int invalid(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return VQB_ERR_INVALID;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    // keep torch's wording for OOM so the reference's substring check still matches
+    // (bin/train_vqvae.py:321 looks for 'out of memory')
+    if (e == cudaErrorMemoryAllocation)
+        set_error("CUDA out of memory in libvqb200 (%s)", what);
+    else
+        set_error("CUDA error in libvqb200: %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+    cudaGetLastError();   // clear the sticky-free error state
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? VQB_ERR_NO_DEVICE : VQB_ERR_CUDA;
+}
+
+struct DevInfo { int sms; int smem; int major; };
+static DevInfo dev_info() {
+    static thread_local int cached_dev = -1;
+    static thread_local DevInfo info = {148, 227 * 1024, 10};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return info;
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&info.smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&info.major, cudaDevAttrComputeCapabilityMajor, dev);
+        cached_dev = dev;
+    }
+    return info;
+}
+int sm_count() { return dev_info().sms; }
+int max_optin_smem() { return dev_info().smem; }
+
+static int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("libvqb200: no CUDA device visible (this library has no CPU fallback)");
+        return VQB_ERR_NO_DEVICE;
+    }
+    if (dev_info().major != 10) {
+        set_error("libvqb200: built for sm_100a only; current device has compute capability %d.x", dev_info().major);
+        return VQB_ERR_NO_DEVICE;
+    }
+    return VQB_OK;
+}
+
+static int check_common(const char* fn, int64_t N, int64_t D, int64_t K) {
+    if (N < 0 || D <= 0 || K <= 0) return invalid("%s: bad shape N=%lld D=%lld K=%lld", fn, (long long)N, (long long)D, (long long)K);
+    if (N >= (1ll << 31) || K >= (1ll << 24)) return invalid("%s: N must be < 2^31 and K < 2^24", fn);
+    if (D % 4 != 0 || D > 512) return invalid("%s: D must be a multiple of 4 and <= 512 (got %lld)", fn, (long long)D);
+    return VQB_OK;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
+extern "C" const char* vqb_last_error(void) { return g_err; }
+
+extern "C" int vqb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+static int validate_fwd(const vqb_fwd_args* a) {
+    if (!a || a->struct_size != sizeof(vqb_fwd_args)) return invalid("vqb_forward: struct_size mismatch (ABI %d)", VQB_ABI_VERSION);
+    const bool l2 = a->flags & VQB_SCORE_L2, lin = a->flags & VQB_SCORE_LINEAR;
+    if (l2 == lin) return invalid("vqb_forward: exactly one of VQB_SCORE_L2 / VQB_SCORE_LINEAR must be set");
+    int rc = check_common("vqb_forward", a->n_rows, a->dim, a->n_codes);
+    if (rc) return rc;
+    if (a->n_rows == 0) return VQB_OK;
+    if (!a->x || !a->score_w || !a->score_b || !a->gather_table || !a->idx || !a->new_latent)
+        return invalid("vqb_forward: x, score_w, score_b, gather_table, idx and new_latent are required");
+    if (l2 && !a->temp) return invalid("vqb_forward: temp is required for the L2 score");
+    if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->new_latent) ||
+        (a->p_code && !aligned16(a->p_code)))
+        return invalid("vqb_forward: tensor pointers must be 16-byte aligned");
+    if ((a->flags & VQB_SEARCH_TENSOR) && (a->p_code || !l2 || !a->score_w_bf16))
+        return invalid("vqb_forward: VQB_SEARCH_TENSOR needs the L2 score, p_code == NULL and score_w_bf16");
+    return VQB_OK;
+}
+
+extern "C" int vqb_forward_workspace(const vqb_fwd_args* a, size_t* bytes) {
+    if (!bytes) return invalid("vqb_forward_workspace: bytes is NULL");
+    *bytes = 0;
+    int rc = validate_fwd(a);
+    if (rc) return rc;
+    if (a->flags & VQB_SEARCH_TENSOR) return forward_tensor_workspace(a, bytes);
+    return VQB_OK;
+}
+
+extern "C" int vqb_forward(const vqb_fwd_args* a, void* stream) {
+    int rc = validate_fwd(a);
+    if (rc) return rc;
+    if ((rc = require_device())) return rc;
+    if (a->dim > 256 && !(a->flags & VQB_SEARCH_TENSOR))
+        return invalid("vqb_forward: the exact-fp32 path supports D <= 256 (got %lld)", (long long)a->dim);
+    if (a->flags & VQB_SEARCH_TENSOR) return launch_forward_tensor(a, (cudaStream_t)stream);
+    return launch_forward_simt(a, (cudaStream_t)stream);
+}
+
+static int validate_bwd(const vqb_bwd_args* a) {
+    if (!a || a->struct_size != sizeof(vqb_bwd_args)) return invalid("vqb_backward: struct_size mismatch (ABI %d)", VQB_ABI_VERSION);
+    const bool l2 = a->flags & VQB_SCORE_L2, lin = a->flags & VQB_SCORE_LINEAR;
+    if (l2 == lin) return invalid("vqb_backward: exactly one of VQB_SCORE_L2 / VQB_SCORE_LINEAR must be set");
+    int rc = check_common("vqb_backward", a->n_rows, a->dim, a->n_codes);
+    if (rc) return rc;
+    if (a->n_rows == 0) return VQB_OK;
+    if (!a->idx) return invalid("vqb_backward: idx is required");
+    if (!a->g_p && !a->g_q) return invalid("vqb_backward: at least one of g_p / g_q is required");
+    return VQB_OK;
+}
+
+extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
+    if (!bytes) return invalid("vqb_backward_workspace: bytes is NULL");
+    *bytes = 0;
+    return validate_bwd(a);
+}
+
+extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
+    int rc = validate_bwd(a);
+    if (rc) return rc;
+    if ((rc = require_device())) return rc;
+    if (a->n_rows == 0) return VQB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool l2 = a->flags & VQB_SCORE_L2;
+    const bool stop_grad = a->flags & VQB_STOP_GRAD;
+    const bool skip = a->flags & VQB_SKIP;
+    const size_t nd_bytes = (size_t)a->n_rows * a->dim * sizeof(float);
+
+    if (!a->g_p && stop_grad) {
+        // scatter-only backward: nothing reaches the softmax route.
+        //   L2:     dx = g_q (straight-through identity; zero bytes when the caller aliases it)
+        //   LINEAR: dx = 0   (no path from new_latent to x with stop_grad, src/embed.py:194-197)
+        if (a->dx) {
+            if (l2) {
+                if (a->dx != a->g_q) VQB_CUDA(cudaMemcpyAsync(a->dx, a->g_q, nd_bytes, cudaMemcpyDeviceToDevice, s));
+            } else {
+                VQB_CUDA(cudaMemsetAsync(a->dx, 0, nd_bytes, s));
+            }
+        }
+        if (skip && l2) return VQB_OK;
+        float* dst = l2 ? a->d_score_w : a->d_gather;
+        if (!dst) return invalid("vqb_backward: the scatter destination (d_score_w for L2, d_gather for LINEAR) is NULL");
+        if (!aligned16(a->g_q) || !aligned16(dst)) return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
+        return launch_scatter_add(a->idx, a->n_rows, a->g_q, a->n_codes, a->dim, dst, nullptr, s);
+    }
+
+    if (!a->x || !a->score_w || !a->gather_table || !a->p_code || !a->dx || !a->d_score_w || !a->colsum)
+        return invalid("vqb_backward: x, score_w, gather_table, p_code, dx, d_score_w and colsum are required for the p_code route");
+    if (l2 && !a->temp) return invalid("vqb_backward: temp is required for the L2 score");
+    if ((a->flags & VQB_TEMP_GRAD) && (!a->d_temp || !a->score_b)) return invalid("vqb_backward: VQB_TEMP_GRAD needs d_temp and score_b");
+    if (!l2 && a->g_q && !a->d_gather) return invalid("vqb_backward: d_gather is required for the LINEAR score when g_q is given");
+    if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->dx) ||
+        !aligned16(a->d_score_w) || (a->g_q && !aligned16(a->g_q)) || (a->d_gather && !aligned16(a->d_gather)))
+        return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
+    return launch_backward_simt(a, s);
+}

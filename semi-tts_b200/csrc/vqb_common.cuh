@@ -1,0 +1,64 @@
+// Shared helpers for libvqb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "vqb.h"
+
+namespace vqb {
+
+// thread-local error string behind vqb_last_error()
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int invalid(const char* fmt, ...);
+
+#define VQB_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return ::vqb::cuda_fail(e_, #call);  \
+    } while (0)
+
+#define VQB_CHECK_LAUNCH(name)                                      \
+    do {                                                            \
+        cudaError_t e_ = cudaGetLastError();                        \
+        if (e_ != cudaSuccess) return ::vqb::cuda_fail(e_, name);   \
+    } while (0)
+
+int sm_count();                       // SMs of the current device (148 on B200)
+int max_optin_smem();                 // bytes of dynamic smem a CTA may opt in to (227 KB)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming (read-once) 128-bit load: do not allocate in L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg4_stream(float* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// entry points implemented in the individual .cu files (host side, return VQB_* codes)
+int launch_forward_simt(const vqb_fwd_args* a, cudaStream_t s);
+int launch_backward_simt(const vqb_bwd_args* a, cudaStream_t s);
+int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K, int64_t D,
+                       float* dtable, int64_t* hist, cudaStream_t s);
+int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
+int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
+
+}  // namespace vqb

@@ -1,0 +1,331 @@
+"""torch.autograd.Function wrappers over the C ABI (include/vqb.h).
+
+Each Function replaces the ATen op sequence of one reference method and its autograd backward:
+  vq_l2           L2Embedding.forward         src/embed.py:105-147 (+ neg_batch_l2 :208-213)
+  vq_linear       SeperateEmbedding.forward   src/embed.py:187-205
+  codebook_lookup *.inference                 src/embed.py:96-103, :180-185
+PyTorch only supplies device memory, the current stream and the autograd graph; all arithmetic is in
+libvqb200.so.  CPU tensors are rejected: there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+
+def _require(t, name, dtype=torch.float32):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError("semi-tts_b200: `%s` must be a CUDA tensor -- this package has no CPU path" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("semi-tts_b200: `%s` must be %s (got %s)" % (name, dtype, t.dtype))
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw (non-differentiable) table assembly: src/embed.py:109-112
+# ------------------------------------------------------------------------------------------------
+def assemble_table(learnable, phn_attr=None, proj_w=None, proj_b=None, want_bf16=False):
+    """Returns (table[K,D], enorm[K], table_bf16 or None).  No autograd."""
+    lib = _lib.load()
+    _require(learnable, "learnable_table")
+    learnable = _c(learnable.detach())
+    K, Dl = learnable.shape
+    A = Da = 0
+    if phn_attr is not None:
+        _require(phn_attr, "phn_attr"); _require(proj_w, "proj_attr.weight"); _require(proj_b, "proj_attr.bias")
+        phn_attr, proj_w, proj_b = _c(phn_attr.detach()), _c(proj_w.detach()), _c(proj_b.detach())
+        A, Da = phn_attr.shape[1], proj_w.shape[0]
+    D = Dl + Da
+    table = torch.empty(K, D, device=learnable.device, dtype=torch.float32)
+    enorm = torch.empty(K, device=learnable.device, dtype=torch.float32)
+    tbf = torch.empty(K, D, device=learnable.device, dtype=torch.bfloat16) if want_bf16 else None
+    with torch.cuda.device(learnable.device):
+        _lib.check(lib.vqb_assemble_table(ptr(learnable), ptr(phn_attr), ptr(proj_w), ptr(proj_b), K, D, A, Da,
+                                          ptr(table), ptr(enorm), ptr(tbf), _stream(learnable)))
+    return table, enorm, tbf
+
+
+def _table_backward(dtable, table, colsum, phn_attr, Da):
+    """Returns (d_learnable, d_proj_w, d_proj_b) from the accumulated dtable (+ the |e|^2 term)."""
+    lib = _lib.load()
+    K, D = dtable.shape
+    A = phn_attr.shape[1] if phn_attr is not None else 0
+    if phn_attr is None:
+        Da = 0
+    d_learn = torch.empty(K, D - Da, device=dtable.device, dtype=torch.float32)
+    d_w = torch.empty(Da, A, device=dtable.device, dtype=torch.float32) if Da else None
+    d_b = torch.empty(Da, device=dtable.device, dtype=torch.float32) if Da else None
+    with torch.cuda.device(dtable.device):
+        _lib.check(lib.vqb_table_backward(ptr(dtable), ptr(table), ptr(colsum), ptr(phn_attr), K, D, A, Da,
+                                          ptr(d_learn), ptr(d_w), ptr(d_b), _stream(dtable)))
+    return d_learn, d_w, d_b
+
+
+def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, hist, want_sqerr,
+                 score_w_bf16=None):
+    lib = _lib.load()
+    N, D = x2d.shape
+    K = score_w.shape[0]
+    dev = x2d.device
+    p_code = torch.empty(N, K, device=dev, dtype=torch.float32) if want_pcode else None
+    idx = torch.empty(N, device=dev, dtype=torch.int64)
+    q = torch.empty(N, D, device=dev, dtype=torch.float32)
+    sq = torch.zeros(1, device=dev, dtype=torch.float64) if want_sqerr else None
+    a = _lib.FwdArgs()
+    a.struct_size = ctypes.sizeof(_lib.FwdArgs)
+    a.flags = flags
+    a.n_rows, a.dim, a.n_codes = N, D, K
+    a.x, a.score_w, a.score_b, a.gather_table = ptr(x2d), ptr(score_w), ptr(score_b), ptr(gather_table)
+    a.score_w_bf16 = ptr(score_w_bf16)
+    a.temp, a.p_code, a.idx, a.new_latent = ptr(temp), ptr(p_code), ptr(idx), ptr(q)
+    a.hist, a.sq_err_sum = ptr(hist), ptr(sq)
+    with torch.cuda.device(dev):
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
+        ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8) if nbytes.value else None
+        a.workspace, a.workspace_bytes = ptr(ws), nbytes.value
+        _lib.check(lib.vqb_forward(ctypes.byref(a), _stream(x2d)))
+    return p_code, idx, q, sq
+
+
+def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp, p_code, idx, g_p, g_q,
+                  want_dx_buffer, separate_gather):
+    """Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None)."""
+    lib = _lib.load()
+    N, D = x2d.shape
+    K = score_w.shape[0]
+    dev = x2d.device
+    d_w = torch.zeros(K, D, device=dev, dtype=torch.float32)
+    colsum = torch.zeros(K, device=dev, dtype=torch.float32)
+    d_gather = torch.zeros(K, D, device=dev, dtype=torch.float32) if separate_gather else None
+    d_temp = torch.zeros(1, device=dev, dtype=torch.float32) if flags & _lib.TEMP_GRAD else None
+    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if want_dx_buffer else None
+    a = _lib.BwdArgs()
+    a.struct_size = ctypes.sizeof(_lib.BwdArgs)
+    a.flags = flags
+    a.n_rows, a.dim, a.n_codes, a.n_real_rows = N, D, K, n_real_rows
+    a.x, a.score_w, a.score_b, a.gather_table, a.temp = ptr(x2d), ptr(score_w), ptr(score_b), ptr(gather_table), ptr(temp)
+    a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
+    a.dx, a.d_score_w, a.colsum, a.d_gather, a.d_temp = ptr(dx), ptr(d_w), ptr(colsum), ptr(d_gather), ptr(d_temp)
+    with torch.cuda.device(dev):
+        _lib.check(lib.vqb_backward(ctypes.byref(a), _stream(x2d)))
+    return dx, d_w, colsum, d_gather, d_temp
+
+
+def _loss_backward(x2d, table, idx, g_vq, g_commit, dx, dx_accumulate, dtable):
+    lib = _lib.load()
+    N, D = x2d.shape
+    with torch.cuda.device(x2d.device):
+        _lib.check(lib.vqb_loss_backward(ptr(x2d), ptr(table), ptr(idx), N, D, table.shape[0], ptr(g_vq),
+                                         ptr(g_commit), ptr(dx), 1 if dx_accumulate else 0, ptr(dtable),
+                                         _stream(x2d)))
+
+
+class _Cfg:
+    """Per-call options (plain Python, not a tensor)."""
+    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "search_tensor")
+
+    def __init__(self, stop_grad=True, skip=False, n_real_rows=0, want_pcode=True, hist=None,
+                 want_losses=False, search_tensor=False):
+        self.stop_grad, self.skip, self.n_real_rows = bool(stop_grad), bool(skip), int(n_real_rows)
+        self.want_pcode, self.hist, self.want_losses = bool(want_pcode), hist, bool(want_losses)
+        self.search_tensor = bool(search_tensor)
+
+
+def _g32(t):
+    return None if t is None else _c(t.to(torch.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# L2 quantizer
+# ------------------------------------------------------------------------------------------------
+def _fwd_flags(score, cfg):
+    return score | (_lib.STOP_GRAD if cfg.stop_grad else 0) | (_lib.SKIP if cfg.skip else 0)
+
+
+class _VQL2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, learnable, phn_attr, proj_w, proj_b, temp, cfg):
+        _require(x, "enc_embs"); _require(temp, "temp")
+        if x.dim() != 3:
+            raise RuntimeError("semi-tts_b200: enc_embs must be [B, S, D]")
+        B, S, D = x.shape
+        x2d = _c(x.detach()).view(B * S, D)
+        table, enorm, tbf = assemble_table(learnable, phn_attr, proj_w, proj_b, want_bf16=cfg.search_tensor)
+        K = table.shape[0]
+        if table.shape[1] != D:
+            raise RuntimeError("semi-tts_b200: enc_embs has D=%d but the codebook has D=%d" % (D, table.shape[1]))
+        if not cfg.want_pcode and not cfg.stop_grad:
+            raise RuntimeError("semi-tts_b200: the ST-onehot variant (stop_grad=False) needs p_code")
+        flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.SEARCH_TENSOR if cfg.search_tensor else 0)
+        temp_c = _c(temp.detach())
+        p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
+                                          cfg.want_losses, tbf)
+        ctx.cfg, ctx.shape = cfg, (B, S, D, K)
+        ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
+        ctx.temp_grad = bool(temp.requires_grad)
+        ctx.save_for_backward(x2d, table, enorm, temp_c, p_code, idx, phn_attr)
+        idx3 = idx.view(B, S)
+        ctx.mark_non_differentiable(idx3)
+        vq = commit = None
+        if cfg.want_losses:
+            vq = (sq / float(max(B * S * D, 1))).to(torch.float32).view(())
+            commit = vq.clone()
+        return (p_code.view(B, S, K) if p_code is not None else None), q.view(B, S, D), idx3, vq, commit
+
+    @staticmethod
+    def backward(ctx, g_p, g_q, _g_idx, g_vq, g_commit):
+        x2d, table, enorm, temp, p_code, idx, phn_attr = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, S, D, K = ctx.shape
+        N = B * S
+        have_loss = g_vq is not None or g_commit is not None
+        if (g_p is None and g_q is None and not have_loss) or N == 0:
+            return (None,) * 7
+        dev = x2d.device
+        g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
+        g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
+        flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TEMP_GRAD if ctx.temp_grad else 0)
+        d_temp = colsum = None
+        if g_p2 is None and g_q2 is None:
+            dx, d_w = None, torch.zeros(K, D, device=dev, dtype=torch.float32)
+        elif g_p2 is None and cfg.stop_grad:
+            # scatter-only: dx = g_q, the straight-through identity, returned as the same tensor (zero bytes)
+            _, d_w, _, _, _ = _run_backward(flags & ~_lib.TEMP_GRAD, cfg.n_real_rows, x2d, table, enorm, table, temp,
+                                            None, idx, None, g_q2, False, False)
+            dx = g_q2
+        else:
+            dx, d_w, colsum, _, d_temp = _run_backward(flags, cfg.n_real_rows, x2d, table, enorm, table, temp,
+                                                       p_code, idx, g_p2, g_q2, True, False)
+        if have_loss:
+            if dx is None:
+                dx, acc = torch.empty(N, D, device=dev, dtype=torch.float32), False
+            elif dx is g_q2:
+                dx, acc = g_q2.clone(), True
+            else:
+                acc = True
+            _loss_backward(x2d, table, idx, _g32(g_vq), _g32(g_commit), dx, acc, d_w)
+        d_learn, d_pw, d_pb = _table_backward(d_w, table, colsum, phn_attr, ctx.Da)
+        if ctx.temp_grad and d_temp is None:
+            d_temp = torch.zeros(1, device=dev, dtype=torch.float32)
+        return (dx.view(B, S, D) if dx is not None else None), d_learn, None, d_pw, d_pb, \
+            (d_temp if ctx.temp_grad else None), None
+
+
+def vq_l2(x, learnable_table, phn_attr, proj_w, proj_b, temp, stop_grad=True, skip=False, n_real_rows=0,
+          want_pcode=True, hist=None, want_losses=False, search_tensor=False):
+    """L2 quantizer (src/embed.py:105-147).
+    Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S] int64, vq_loss or None, commit_loss or None)."""
+    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, search_tensor)
+    return _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
+
+
+def vq_search(x, table, temp=None, hist=None, search_tensor=True):
+    """Fused-mode forward on a ready-made table (no p_code, no autograd): nearest-codeword search +
+    gather + straight-through.  x[N,D] or [B,S,D], table[K,D] -> (idx int64, new_latent)."""
+    _require(x, "x"); _require(table, "table")
+    shape = x.shape
+    x2d = _c(x.detach()).view(-1, shape[-1])
+    table = _c(table.detach())
+    if temp is None:
+        temp = torch.ones(1, device=x.device, dtype=torch.float32)
+    tab, enorm, tbf = assemble_table(table, want_bf16=search_tensor)
+    flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SEARCH_TENSOR if search_tensor else 0)
+    _, idx, q, _ = _run_forward(flags, x2d, tab, enorm, tab, temp, False, hist, False, tbf)
+    return idx.view(shape[:-1]), q.view(shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# "separate" quantizer
+# ------------------------------------------------------------------------------------------------
+class _VQLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, cfg):
+        _require(x, "enc_embs"); _require(asr_w, "asr_final_layer.weight"); _require(asr_b, "asr_final_layer.bias")
+        if x.dim() != 3:
+            raise RuntimeError("semi-tts_b200: enc_embs must be [B, S, D]")
+        B, S, D = x.shape
+        x2d = _c(x.detach()).view(B * S, D)
+        table, _, _ = assemble_table(emb_w, phn_attr, proj_w, proj_b)
+        K = asr_w.shape[0]
+        if table.shape != (K, D) or asr_w.shape[1] != D:
+            raise RuntimeError("semi-tts_b200: shape mismatch between enc_embs, asr_final_layer and the embedding table")
+        w, b = _c(asr_w.detach()), _c(asr_b.detach())
+        p_code, idx, q, _ = _run_forward(_fwd_flags(_lib.SCORE_LINEAR, cfg), x2d, w, b, table, None, True,
+                                         cfg.hist, False)
+        ctx.cfg, ctx.shape = cfg, (B, S, D, K)
+        ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
+        ctx.save_for_backward(x2d, w, table, p_code, idx, phn_attr)
+        idx3 = idx.view(B, S)
+        ctx.mark_non_differentiable(idx3)
+        return p_code.view(B, S, K), q.view(B, S, D), idx3
+
+    @staticmethod
+    def backward(ctx, g_p, g_q, _g_idx):
+        x2d, w, table, p_code, idx, phn_attr = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, S, D, K = ctx.shape
+        N = B * S
+        if (g_p is None and g_q is None) or N == 0:
+            return (None,) * 8
+        g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
+        g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
+        flags = _fwd_flags(_lib.SCORE_LINEAR, cfg)
+        dx, d_w, colsum, d_tab, _ = _run_backward(flags, 0, x2d, w, None, table, None, p_code, idx, g_p2, g_q2,
+                                                  True, True)
+        d_emb, d_pw, d_pb = _table_backward(d_tab, None, None, phn_attr, ctx.Da)
+        return dx.view(B, S, D), d_w, colsum, d_emb, None, d_pw, d_pb, None
+
+
+def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None):
+    """Separate quantizer (src/embed.py:187-205). Returns (p_code, new_latent, idx)."""
+    cfg = _Cfg(stop_grad=stop_grad, hist=hist)
+    return _VQLinear.apply(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# gather-only inference path
+# ------------------------------------------------------------------------------------------------
+class _Lookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, txt, learnable, phn_attr, proj_w, proj_b):
+        _require(txt, "txt", torch.int64)
+        lib = _lib.load()
+        table, _, _ = assemble_table(learnable, phn_attr, proj_w, proj_b)
+        K, D = table.shape
+        t = _c(txt)
+        out = torch.empty(*t.shape, D, device=t.device, dtype=torch.float32)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.vqb_inference_gather(ptr(t), t.numel(), ptr(table), K, D, ptr(out), _stream(t)))
+        ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
+        ctx.save_for_backward(t, table, phn_attr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        t, table, phn_attr = ctx.saved_tensors
+        lib = _lib.load()
+        K, D = table.shape
+        g2 = _g32(g).view(-1, D)
+        dtab = torch.zeros(K, D, device=g2.device, dtype=torch.float32)
+        with torch.cuda.device(g2.device):
+            _lib.check(lib.vqb_scatter_add(ptr(t), t.numel(), ptr(g2), K, D, ptr(dtab), None, _stream(g2)))
+        d_learn, d_pw, d_pb = _table_backward(dtab, None, None, phn_attr, ctx.Da)
+        return None, d_learn, None, d_pw, d_pb
+
+
+def codebook_lookup(txt, learnable_table, phn_attr=None, proj_w=None, proj_b=None):
+    """inference(txt): table[txt] on the assembled table (src/embed.py:96-103, :180-185), differentiable
+    w.r.t. learnable_table / proj_attr (the text->speech branch trains the codebook through it)."""
+    return _Lookup.apply(txt, learnable_table, phn_attr, proj_w, proj_b)

@@ -1,0 +1,39 @@
+"""Device-side code-usage histogram.
+
+The reference appends `unpair_prob.argmax(-1).cpu().flatten().tolist()` to a Python list every other
+step (bin/train_vqvae.py:256-261) and, every 500 steps, computes `data.count(i)/len(data)` per code with
+entry 0 forced to zero (src/util.py:139-143) before resetting the list (:310).  Here the counts are
+accumulated by the forward kernel itself into an int64 [K] buffer; `bar()` returns the same numbers
+without a per-step device->host sync.
+"""
+import torch
+
+
+class UsageHistogram:
+    def __init__(self, n_codes):
+        self.n_codes = n_codes
+        self.counts = None            # int64 [K] on the device of the first forward
+
+    def buffer_for(self, ref):
+        if self.counts is None or self.counts.device != ref.device:
+            self.counts = torch.zeros(self.n_codes, dtype=torch.int64, device=ref.device)
+        return self.counts
+
+    def reset(self):
+        if self.counts is not None:
+            self.counts.zero_()
+
+    def total(self):
+        return 0 if self.counts is None else int(self.counts.sum().item())
+
+    def bar(self, zero_pad_tok=True):
+        """`cnts` of src/util.py:139-143 as a list of K floats (one host sync, at plot time only)."""
+        if self.counts is None:
+            return [0.0] * self.n_codes
+        c = self.counts.to(torch.float64)
+        tot = c.sum()
+        out = (c / tot) if tot > 0 else c
+        if zero_pad_tok:
+            out = out.clone()
+            out[0] = 0
+        return out.cpu().tolist()

@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the drop-in nn.Modules -> autograd.Function -> C ABI) against
+(1) golden vectors produced by the unmodified reference and (2) the fp64 oracle.
+
+Tolerances (BASELINE.json north_star): code indices bit-exact except rows whose top-2 distance gap is
+below 1e-6 relative (count reported); p_code, new_latent, losses and gradients within 1e-5 relative
+(norm-wise, in fp32) of the fp64 oracle.  The reference's own fp32 outputs sit ~1e-6 from the fp64 oracle
+(tests/test_oracle_golden.py), so agreement with the golden vectors is asserted at 2e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import L2_CASES, SEP_CASES, ST_ONEHOT, load_golden, rel_err
+from helpers import build_module
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5          # vs fp64 oracle
+TOL_REF = 2e-5      # vs the reference's fp32 outputs
+
+
+def _cuda(a):
+    return None if a is None else torch.from_numpy(np.asarray(a).copy()).cuda()
+
+
+def _table64(g, key="sd.learnable_table"):
+    return O.assemble_table(g[key], g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"), g.get("sd.proj_attr.bias"))
+
+
+def _grad(p):
+    return None if p.grad is None else p.grad.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", L2_CASES)
+def test_l2_module_vs_reference_and_oracle(name):
+    g = load_golden(name)
+    stop_grad = name not in ST_ONEHOT
+    learn_temp = "grad.temp" in g
+    skip_case = name == "l2_attr_skip_train"
+    m = build_module(g, "l2", stop_grad=stop_grad, learn_temp=learn_temp, skip_prob=1.0 if skip_case else 0)
+    m.train(bool(g["train"]))
+    x = _cuda(g["x"]).requires_grad_(True)
+    B, S, D = x.shape
+    p_code, new_latent, vq, commit = m(x, int(g["first_n_real_mel"]))
+    assert vq == 0 and commit == 0 and isinstance(vq, int)              # src/embed.py:147
+    assert p_code.shape == g["p_code"].shape and new_latent.shape == g["new_latent"].shape
+    idx = m.last_idx.cpu().numpy()
+    assert idx.dtype == np.int64
+
+    E64 = _table64(g)
+    temp = float(g["sd.temp"][0])
+    f64 = O.l2_forward(g["x"], E64, temp, stop_grad=stop_grad, skip=skip_case)
+    rep = O.index_mismatch_report(idx, g["idx"], f64["dist"])
+    assert rep["hard_mismatches"] == 0, rep
+    assert np.array_equal(idx, p_code.argmax(-1).cpu().numpy())         # idx is argmax over p_code (:130)
+    assert rel_err(p_code.detach().cpu().numpy(), f64["p_code"]) < TOL
+    assert rel_err(p_code.detach().cpu().numpy(), g["p_code"]) < TOL_REF
+    same = idx == g["idx"]
+    assert rel_err(new_latent.detach().cpu().numpy()[same], g["new_latent"][same]) < 1e-6
+    assert rel_err(new_latent.detach().cpu().numpy()[same], f64["new_latent"][same]) < TOL
+
+    outs, grads = [], []
+    if "g_p" in g:
+        outs.append(p_code); grads.append(_cuda(g["g_p"]))
+    if "g_q" in g:
+        outs.append(new_latent); grads.append(_cuda(g["g_q"]))
+    torch.autograd.backward(outs, grads)
+    b64 = O.l2_backward(g["x"], E64, temp, f64["p_code"], idx, g.get("g_p"), g.get("g_q"), stop_grad=stop_grad,
+                        first_n_real_rows=int(g["first_n_real_mel"]) * S, skip=skip_case)
+    t64 = O.table_backward(b64["dtable"], g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"))
+    exact = bool(same.all())
+    dx = x.grad.cpu().numpy()
+    assert rel_err(dx, b64["dx"]) < TOL
+    assert rel_err(_grad(m.learnable_table), t64["d_learnable"]) < TOL
+    if exact:
+        assert rel_err(dx, g["dx"]) < TOL_REF
+        assert rel_err(_grad(m.learnable_table), g["grad.learnable_table"]) < TOL_REF
+    if "grad.proj_attr.weight" in g:
+        assert rel_err(_grad(m.proj_attr.weight), t64["d_proj_w"]) < TOL
+        assert rel_err(_grad(m.proj_attr.bias), t64["d_proj_b"]) < TOL
+        if exact:
+            assert rel_err(_grad(m.proj_attr.weight), g["grad.proj_attr.weight"]) < TOL_REF
+            assert rel_err(_grad(m.proj_attr.bias), g["grad.proj_attr.bias"]) < TOL_REF
+    if learn_temp:
+        got = float(m.temp.grad.item())
+        assert abs(got - float(b64["dtemp"])) <= 2e-5 * max(1.0, abs(float(b64["dtemp"])))
+        assert abs(got - float(g["grad.temp"][0])) <= 1e-4 * max(1.0, abs(float(g["grad.temp"][0])))
+    # frozen tables never receive gradients (freeze=True, src/embed.py:29,80)
+    assert m.onehot.weight.grad is None
+    if m.phn_attr is not None:
+        assert m.phn_attr.weight.grad is None
+    # usage histogram fused into the forward == bincount of the picked indices
+    assert np.array_equal(m.usage.counts.cpu().numpy(), O.usage_counts(idx, m.vocab_size))
+
+
+@pytest.mark.parametrize("name", SEP_CASES)
+def test_separate_module_vs_reference_and_oracle(name):
+    g = load_golden(name)
+    stop_grad = name not in ST_ONEHOT
+    m = build_module(g, "sep", stop_grad=stop_grad)
+    m.eval()
+    x = _cuda(g["x"]).requires_grad_(True)
+    p_code, new_latent, vq, commit = m(x)
+    assert vq == 0 and commit == 0
+    idx = m.last_idx.cpu().numpy()
+    E64 = _table64(g, "sd.embedding.weight")
+    f64 = O.separate_forward(g["x"], E64, g["sd.asr_final_layer.weight"], g["sd.asr_final_layer.bias"],
+                             stop_grad=stop_grad, phn_attr=g.get("sd.phn_attr.weight"),
+                             proj_w=g.get("sd.proj_attr.weight"), proj_b=g.get("sd.proj_attr.bias"),
+                             emb_weight=g["sd.embedding.weight"])
+    rep = O.index_mismatch_report(idx, g["idx"], -f64["logits"])
+    assert rep["hard_mismatches"] == 0, rep
+    assert rel_err(p_code.detach().cpu().numpy(), f64["p_code"]) < TOL
+    assert rel_err(p_code.detach().cpu().numpy(), g["p_code"]) < TOL_REF
+    same = idx == g["idx"]
+    assert rel_err(new_latent.detach().cpu().numpy()[same], g["new_latent"][same]) < 1e-6
+    outs, grads = [p_code], [_cuda(g["g_p"])]
+    if new_latent.requires_grad:
+        outs.append(new_latent); grads.append(_cuda(g["g_q"]))
+    torch.autograd.backward(outs, grads)
+    b64 = O.separate_backward(g["x"], E64, g["sd.asr_final_layer.weight"], f64["p_code"], idx, g["g_p"], g["g_q"],
+                              stop_grad=stop_grad)
+    t64 = O.table_backward(b64["dtable"], g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"))
+    assert rel_err(x.grad.cpu().numpy(), b64["dx"]) < TOL
+    assert rel_err(_grad(m.asr_final_layer.weight), b64["d_asr_w"]) < TOL
+    assert rel_err(_grad(m.asr_final_layer.bias), b64["d_asr_b"]) < TOL
+    assert rel_err(_grad(m.embedding.weight), t64["d_learnable"]) < TOL
+    if bool(same.all()):
+        assert rel_err(x.grad.cpu().numpy(), g["dx"]) < TOL_REF
+        assert rel_err(_grad(m.asr_final_layer.weight), g["grad.asr_final_layer.weight"]) < TOL_REF
+        assert rel_err(_grad(m.embedding.weight), g["grad.embedding.weight"]) < TOL_REF
+    if "grad.proj_attr.weight" in g:
+        assert rel_err(_grad(m.proj_attr.weight), t64["d_proj_w"]) < TOL
+        assert rel_err(_grad(m.proj_attr.bias), t64["d_proj_b"]) < TOL
+
+
+@pytest.mark.parametrize("name,bone", [("inference_l2", "l2"), ("inference_sep", "sep")])
+def test_inference_gather_and_its_backward(name, bone):
+    g = load_golden(name)
+    m = build_module(g, bone)
+    txt = _cuda(g["txt"])
+    out = m.inference(txt)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < 1e-6
+    if bone == "l2":
+        assert rel_err(m.embedding.weight.data.cpu().numpy(), g["table"]) < 1e-6       # bin/train_vqvae.py:425
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    out.backward(go)
+    K, D = m.vocab_size, m.latent_dim
+    dtab = np.zeros((K, D))
+    np.add.at(dtab, g["txt"].reshape(-1), go.cpu().numpy().astype(np.float64).reshape(-1, D))
+    t64 = O.table_backward(dtab, g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"))
+    lt = m.learnable_table if bone == "l2" else m.embedding.weight
+    assert rel_err(_grad(lt), t64["d_learnable"]) < TOL
+    assert rel_err(_grad(m.proj_attr.weight), t64["d_proj_w"]) < TOL
+    assert rel_err(_grad(m.proj_attr.bias), t64["d_proj_b"]) < TOL
+
+
+def test_no_grad_forward_and_skip_rng_parity():
+    """validate() runs the module under torch.no_grad() (bin/train_vqvae.py:343); the skip branch draws
+    np.random.rand() only when training and skip_prob > 0 (src/embed.py:140)."""
+    g = load_golden("l2_attr_stopgrad")
+    m = build_module(g, "l2", skip_prob=0.5)
+    x = _cuda(g["x"])
+    m.eval()
+    state = np.random.get_state()
+    with torch.no_grad():
+        p, q, _, _ = m(x)
+    assert not p.requires_grad and not q.requires_grad
+    assert np.array_equal(np.random.get_state()[1], state[1])            # eval: RNG untouched
+    m.train()
+    np.random.seed(123)
+    draws = np.random.rand(6)
+    np.random.seed(123)
+    for i in range(6):
+        _, q, _, _ = m(x)
+        skipped = torch.equal(q, x)
+        assert skipped == bool(draws[i] < 0.5)
+
+
+def test_fused_mode_matches_parity_mode_and_scatter_only_backward():
+    g = load_golden("l2_config1_16x200")
+    m = build_module(g, "l2")
+    x = _cuda(g["x"]).requires_grad_(True)
+    p, q, _, _ = m(x)
+    idx_parity = m.last_idx.clone()
+    gq = _cuda(g["g_q"])
+    q.backward(gq)
+    ref_dx, ref_dlt = x.grad.clone(), m.learnable_table.grad.clone()
+    ref_dpw = m.proj_attr.weight.grad.clone()
+    assert torch.equal(ref_dx, gq)                                       # straight-through identity
+    # same thing without ever materialising p_code (exact-fp32 SIMT search)
+    import semi_tts_b200 as V
+    pf, qf, idxf, _, _ = V.vq_l2(x, m.learnable_table, m.phn_attr.weight, m.proj_attr.weight, m.proj_attr.bias,
+                                 m.temp, want_pcode=False)
+    assert pf is None
+    assert torch.equal(idxf, idx_parity) and torch.equal(qf, q)
+    # scatter-only backward vs oracle
+    E64 = _table64(g)
+    dtab = np.zeros_like(E64)
+    np.add.at(dtab, idx_parity.cpu().numpy().reshape(-1), g["g_q"].astype(np.float64).reshape(-1, E64.shape[1]))
+    t64 = O.table_backward(dtab, g["sd.phn_attr.weight"], g["sd.proj_attr.weight"])
+    assert rel_err(ref_dlt.cpu().numpy(), t64["d_learnable"]) < TOL
+    assert rel_err(ref_dpw.cpu().numpy(), t64["d_proj_w"]) < TOL
+
+
+def test_generic_large_k_forward_and_unsupported_backward_is_loud():
+    g = load_golden("l2_noattr_k300_d128")
+    m = build_module(g, "l2")
+    x = _cuda(g["x"]).requires_grad_(True)
+    p, q, _, _ = m(x)
+    q.backward(_cuda(g["g_q"]))                                          # scatter route works for any K
+    E64 = g["sd.learnable_table"].astype(np.float64)
+    dtab = np.zeros_like(E64)
+    np.add.at(dtab, m.last_idx.cpu().numpy().reshape(-1), g["g_q"].astype(np.float64).reshape(-1, 128))
+    assert rel_err(m.learnable_table.grad.cpu().numpy(), dtab) < TOL
+
+
+def test_loss_extensions_vs_oracle():
+    """commit / codebook loss: no reference arithmetic (parity UNPINNED) -- checked against the oracle's
+    restatement of van den Oord et al. 2017."""
+    import semi_tts_b200 as V
+    g = load_golden("l2_attr_stopgrad")
+    m = build_module(g, "l2")
+    m.vq_weight, m.commit_weight = 1.0, 0.25
+    x = _cuda(g["x"]).requires_grad_(True)
+    p, q, vq, commit = m(x)
+    idx = m.last_idx.cpu().numpy()
+    E64 = _table64(g)
+    code = E64[idx]
+    want = O.vq_losses(g["x"], code)
+    assert abs(float(vq) - want["vq_loss"]) < 1e-5 * want["vq_loss"]
+    assert abs(float(commit) - want["commit_loss"]) < 1e-5 * want["commit_loss"]
+    (m.vq_weight * vq + m.commit_weight * commit).backward()
+    b = O.vq_losses_backward(g["x"], code, idx, E64.shape[0], g_vq=1.0, g_commit=0.25)
+    t64 = O.table_backward(b["dtable"], g["sd.phn_attr.weight"], g["sd.proj_attr.weight"])
+    assert rel_err(x.grad.cpu().numpy(), b["dx"]) < TOL
+    assert rel_err(_grad(m.learnable_table), t64["d_learnable"]) < TOL
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    g = load_golden("l2_attr_stopgrad")
+    m = build_module(g, "l2", device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.from_numpy(g["x"]))
+
+
+def test_config2_size_against_cpu_port_and_properties():
+    """BASELINE config 2 (64 x 800 frames, K=43, D=64): CUDA vs the fp32 CPU port on the same seeded inputs;
+    then size-independent properties."""
+    from oracle import torch_port as TP
+    g = load_golden("l2_config1_16x200")
+    m = build_module(g, "l2")
+    gen = torch.Generator().manual_seed(0)
+    x_cpu = torch.randn(64, 800, 64, generator=gen)
+    gp_cpu = torch.randn(64, 800, 43, generator=gen)
+    gq_cpu = torch.randn(64, 800, 64, generator=gen)
+    # CPU port
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    xc = x_cpu.clone().requires_grad_(True)
+    lt = sd["learnable_table"].clone().requires_grad_(True)
+    pw, pb = sd["proj_attr.weight"].clone().requires_grad_(True), sd["proj_attr.bias"].clone().requires_grad_(True)
+    pc, qc, ic = TP.l2_step(xc, lt, sd["phn_attr.weight"], pw, pb, sd["temp"], gp_cpu, gq_cpu)
+    # CUDA
+    x = x_cpu.cuda().requires_grad_(True)
+    p, q, _, _ = m(x)
+    torch.autograd.backward([p, q], [gp_cpu.cuda(), gq_cpu.cuda()])
+    idx = m.last_idx.cpu()
+    E64 = O.assemble_table(sd["learnable_table"].numpy(), sd["phn_attr.weight"].numpy(), pw.detach().numpy(), pb.detach().numpy())
+    d64 = O.l2_distance(x_cpu.numpy().reshape(-1, 64), E64)
+    rep = O.index_mismatch_report(idx.numpy(), ic.numpy(), d64)
+    print("config2 index report:", rep)
+    assert rep["hard_mismatches"] == 0, rep
+    same = (idx == ic).numpy()
+    assert rel_err(p.detach().cpu().numpy(), pc.detach().numpy()) < TOL_REF
+    assert torch.equal(q.detach().cpu()[torch.from_numpy(same)][:, :48], qc.detach()[torch.from_numpy(same)][:, :48])
+    if same.all():
+        assert rel_err(x.grad.cpu().numpy(), xc.grad.numpy()) < TOL_REF
+        assert rel_err(m.learnable_table.grad.cpu().numpy(), lt.grad.numpy()) < TOL_REF
+        assert rel_err(m.proj_attr.weight.grad.cpu().numpy(), pw.grad.numpy()) < TOL_REF
+    # properties: rows of p_code sum to 1; histogram sums to N; quantising the output is idempotent
+    assert torch.allclose(p.sum(-1), torch.ones_like(p.sum(-1)), atol=1e-5)
+    assert int(m.usage.counts.sum().item()) == 64 * 800
+    with torch.no_grad():
+        tab = m.embedding.weight.data
+        _, q2, _, _ = m(tab[m.last_idx])
+        assert torch.equal(m.last_idx.cpu(), idx)
