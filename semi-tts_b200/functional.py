@@ -172,6 +172,7 @@ class _VQL2(torch.autograd.Function):
         temp_c = _c(temp.detach())
         p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
                                           cfg.want_losses, tbf)
+        ctx.set_materialize_grads(False)                    # an unused output must arrive as None, not zeros
         ctx.cfg, ctx.shape = cfg, (B, S, D, K)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
         ctx.temp_grad = bool(temp.requires_grad)
@@ -264,6 +265,7 @@ class _VQLinear(torch.autograd.Function):
         w, b = _c(asr_w.detach()), _c(asr_b.detach())
         p_code, idx, q, _ = _run_forward(_fwd_flags(_lib.SCORE_LINEAR, cfg), x2d, w, b, table, None, True,
                                          cfg.hist, False)
+        ctx.set_materialize_grads(False)
         ctx.cfg, ctx.shape = cfg, (B, S, D, K)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
         ctx.save_for_backward(x2d, w, table, p_code, idx, phn_attr)
@@ -308,12 +310,15 @@ class _Lookup(torch.autograd.Function):
         out = torch.empty(*t.shape, D, device=t.device, dtype=torch.float32)
         with torch.cuda.device(t.device):
             _lib.check(lib.vqb_inference_gather(ptr(t), t.numel(), ptr(table), K, D, ptr(out), _stream(t)))
+        ctx.set_materialize_grads(False)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
         ctx.save_for_backward(t, table, phn_attr)
         return out
 
     @staticmethod
     def backward(ctx, g):
+        if g is None:
+            return (None,) * 5
         t, table, phn_attr = ctx.saved_tensors
         lib = _lib.load()
         K, D = table.shape
