@@ -50,7 +50,7 @@ extern "C" {
 #define VQB_STOP_GRAD       0x0004u  /* gather route is F.embedding (:134 / :194-197); clear = ST-onehot (:137-138 / :199-203) */
 #define VQB_SKIP            0x0008u  /* skip connection drawn this step: new_latent = x   src/embed.py:140-142 */
 #define VQB_TEMP_GRAD       0x0010u  /* temp is an nn.Parameter: also produce d temp      src/embed.py:33-34 */
-#define VQB_SEARCH_TENSOR   0x0020u  /* fused mode only: tcgen05 bf16 search + exact fp32 re-rank (p_code must be NULL) */
+#define VQB_SEARCH_TENSOR   0x0020u  /* fused mode only: tcgen05 tf32 search + exact fp32 re-rank (p_code must be NULL) */
 
 VQB_API int vqb_abi_version(void);
 VQB_API const char* vqb_last_error(void);
@@ -88,7 +88,7 @@ typedef struct vqb_fwd_args {
     const float* x;              /* [N,D]   enc_embs flattened (src/embed.py:209)                      */
     const float* score_w;        /* [K,D]   L2: assembled table E; LINEAR: asr_final_layer.weight      */
     const float* score_b;        /* [K]     L2: enorm |e|^2;       LINEAR: asr_final_layer.bias        */
-    const void*  score_w_bf16;   /* [K,D]   bf16 copy of score_w (only for VQB_SEARCH_TENSOR)          */
+    const void*  score_w_bf16;   /* [K,D]   optional bf16 copy of score_w (reserved for a bf16 search)  */
     const float* gather_table;   /* [K,D]   codewords gathered into new_latent (L2: == score_w)        */
     const float* temp;           /* [1]     device scalar; tau = relu(temp) (src/embed.py:115)         */
     float*   p_code;             /* [N,K]   softmax over codes (src/embed.py:127); NULL = fused mode   */
@@ -97,6 +97,8 @@ typedef struct vqb_fwd_args {
     int64_t* hist;               /* [K]     += per-code usage counts of this call, or NULL
                                             (bin/train_vqvae.py:256-261; src/util.py:139)              */
     double*  sq_err_sum;         /* [1]     += sum (x - E[idx])^2 (numerator of the loss extensions), or NULL */
+    uint32_t* search_stats;      /* [2]     VQB_SEARCH_TENSOR only, or NULL: += rows re-ranked in exact fp32,
+                                            += rows that needed the full exact scan                      */
     void*    workspace;          /* vqb_forward_workspace() bytes, or NULL if that is 0                 */
     size_t   workspace_bytes;
 } vqb_fwd_args;

@@ -23,7 +23,7 @@ class FwdArgs(ctypes.Structure):
                 ("n_rows", ctypes.c_int64), ("dim", ctypes.c_int64), ("n_codes", ctypes.c_int64),
                 ("x", _p), ("score_w", _p), ("score_b", _p), ("score_w_bf16", _p), ("gather_table", _p),
                 ("temp", _p), ("p_code", _p), ("idx", _p), ("new_latent", _p), ("hist", _p),
-                ("sq_err_sum", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
+                ("sq_err_sum", _p), ("search_stats", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
 
 
 class BwdArgs(ctypes.Structure):

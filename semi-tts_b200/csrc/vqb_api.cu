@@ -105,8 +105,8 @@ static int validate_fwd(const vqb_fwd_args* a) {
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->new_latent) ||
         (a->p_code && !aligned16(a->p_code)))
         return invalid("vqb_forward: tensor pointers must be 16-byte aligned");
-    if ((a->flags & VQB_SEARCH_TENSOR) && (a->p_code || !l2 || !a->score_w_bf16))
-        return invalid("vqb_forward: VQB_SEARCH_TENSOR needs the L2 score, p_code == NULL and score_w_bf16");
+    if ((a->flags & VQB_SEARCH_TENSOR) && (a->p_code || !l2))
+        return invalid("vqb_forward: VQB_SEARCH_TENSOR needs the L2 score and p_code == NULL");
     return VQB_OK;
 }
 

@@ -73,7 +73,7 @@ def _table_backward(dtable, table, colsum, phn_attr, Da):
 
 
 def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, hist, want_sqerr,
-                 score_w_bf16=None):
+                 score_w_bf16=None, search_stats=None):
     lib = _lib.load()
     N, D = x2d.shape
     K = score_w.shape[0]
@@ -89,7 +89,7 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
     a.x, a.score_w, a.score_b, a.gather_table = ptr(x2d), ptr(score_w), ptr(score_b), ptr(gather_table)
     a.score_w_bf16 = ptr(score_w_bf16)
     a.temp, a.p_code, a.idx, a.new_latent = ptr(temp), ptr(p_code), ptr(idx), ptr(q)
-    a.hist, a.sq_err_sum = ptr(hist), ptr(sq)
+    a.hist, a.sq_err_sum, a.search_stats = ptr(hist), ptr(sq), ptr(search_stats)
     with torch.cuda.device(dev):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
@@ -162,7 +162,7 @@ class _VQL2(torch.autograd.Function):
             raise RuntimeError("semi-tts_b200: enc_embs must be [B, S, D]")
         B, S, D = x.shape
         x2d = _c(x.detach()).view(B * S, D)
-        table, enorm, tbf = assemble_table(learnable, phn_attr, proj_w, proj_b, want_bf16=cfg.search_tensor)
+        table, enorm, tbf = assemble_table(learnable, phn_attr, proj_w, proj_b)
         K = table.shape[0]
         if table.shape[1] != D:
             raise RuntimeError("semi-tts_b200: enc_embs has D=%d but the codebook has D=%d" % (D, table.shape[1]))
@@ -232,7 +232,7 @@ def vq_l2(x, learnable_table, phn_attr, proj_w, proj_b, temp, stop_grad=True, sk
     return _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
 
 
-def vq_search(x, table, temp=None, hist=None, search_tensor=True):
+def vq_search(x, table, temp=None, hist=None, search_tensor=True, stats=None):
     """Fused-mode forward on a ready-made table (no p_code, no autograd): nearest-codeword search +
     gather + straight-through.  x[N,D] or [B,S,D], table[K,D] -> (idx int64, new_latent)."""
     _require(x, "x"); _require(table, "table")
@@ -241,9 +241,11 @@ def vq_search(x, table, temp=None, hist=None, search_tensor=True):
     table = _c(table.detach())
     if temp is None:
         temp = torch.ones(1, device=x.device, dtype=torch.float32)
-    tab, enorm, tbf = assemble_table(table, want_bf16=search_tensor)
+    tab, enorm, _ = assemble_table(table)
     flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SEARCH_TENSOR if search_tensor else 0)
-    _, idx, q, _ = _run_forward(flags, x2d, tab, enorm, tab, temp, False, hist, False, tbf)
+    if stats is not None and (stats.dtype != torch.int32 or stats.numel() < 2 or not stats.is_cuda):
+        raise RuntimeError("semi-tts_b200: `stats` must be a CUDA int32 tensor with 2 elements")
+    _, idx, q, _ = _run_forward(flags, x2d, tab, enorm, tab, temp, False, hist, False, None, stats)
     return idx.view(shape[:-1]), q.view(shape)
 
 
