@@ -50,7 +50,10 @@ extern "C" {
 #define VQB_STOP_GRAD       0x0004u  /* gather route is F.embedding (:134 / :194-197); clear = ST-onehot (:137-138 / :199-203) */
 #define VQB_SKIP            0x0008u  /* skip connection drawn this step: new_latent = x   src/embed.py:140-142 */
 #define VQB_TEMP_GRAD       0x0010u  /* temp is an nn.Parameter: also produce d temp      src/embed.py:33-34 */
-#define VQB_SEARCH_TENSOR   0x0020u  /* fused mode only: tcgen05 tf32 search + exact fp32 re-rank (p_code must be NULL) */
+#define VQB_TENSOR_CORES    0x0020u  /* run the forward on the tcgen05 kernel where the shape allows it (p_code mode:
+                                        K <= 64, D in {32,64}; fused mode: L2 score, D in {32,64,128,256}); other
+                                        shapes, or a cleared flag, take the exact-fp32 CUDA-core kernel */
+#define VQB_SEARCH_TENSOR   VQB_TENSOR_CORES
 
 VQB_API int vqb_abi_version(void);
 VQB_API const char* vqb_last_error(void);
@@ -97,7 +100,7 @@ typedef struct vqb_fwd_args {
     int64_t* hist;               /* [K]     += per-code usage counts of this call, or NULL
                                             (bin/train_vqvae.py:256-261; src/util.py:139)              */
     double*  sq_err_sum;         /* [1]     += sum (x - E[idx])^2 (numerator of the loss extensions), or NULL */
-    uint32_t* search_stats;      /* [2]     VQB_SEARCH_TENSOR only, or NULL: += rows re-ranked in exact fp32,
+    uint32_t* search_stats;      /* [2]     tensor-core fused mode only, or NULL: += rows re-ranked in exact fp32,
                                             += rows that needed the full exact scan                      */
     void*    workspace;          /* vqb_forward_workspace() bytes, or NULL if that is 0                 */
     size_t   workspace_bytes;

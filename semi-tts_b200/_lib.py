@@ -13,7 +13,8 @@ SCORE_LINEAR = 0x0002
 STOP_GRAD = 0x0004
 SKIP = 0x0008
 TEMP_GRAD = 0x0010
-SEARCH_TENSOR = 0x0020
+TENSOR_CORES = 0x0020
+SEARCH_TENSOR = TENSOR_CORES
 
 _p = ctypes.c_void_p
 

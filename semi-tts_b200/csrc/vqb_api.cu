@@ -105,8 +105,6 @@ static int validate_fwd(const vqb_fwd_args* a) {
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->new_latent) ||
         (a->p_code && !aligned16(a->p_code)))
         return invalid("vqb_forward: tensor pointers must be 16-byte aligned");
-    if ((a->flags & VQB_SEARCH_TENSOR) && (a->p_code || !l2))
-        return invalid("vqb_forward: VQB_SEARCH_TENSOR needs the L2 score and p_code == NULL");
     return VQB_OK;
 }
 
@@ -115,7 +113,7 @@ extern "C" int vqb_forward_workspace(const vqb_fwd_args* a, size_t* bytes) {
     *bytes = 0;
     int rc = validate_fwd(a);
     if (rc) return rc;
-    if (a->flags & VQB_SEARCH_TENSOR) return forward_tensor_workspace(a, bytes);
+    if ((a->flags & VQB_TENSOR_CORES) && a->n_rows > 0) return forward_tensor_workspace(a, bytes);
     return VQB_OK;
 }
 
@@ -123,9 +121,9 @@ extern "C" int vqb_forward(const vqb_fwd_args* a, void* stream) {
     int rc = validate_fwd(a);
     if (rc) return rc;
     if ((rc = require_device())) return rc;
-    if (a->dim > 256 && !(a->flags & VQB_SEARCH_TENSOR))
-        return invalid("vqb_forward: the exact-fp32 path supports D <= 256 (got %lld)", (long long)a->dim);
-    if (a->flags & VQB_SEARCH_TENSOR) return launch_forward_tensor(a, (cudaStream_t)stream);
+    if (a->n_rows == 0) return VQB_OK;
+    if ((a->flags & VQB_TENSOR_CORES) && forward_tensor_supported(a)) return launch_forward_tensor(a, (cudaStream_t)stream);
+    if (a->dim > 256) return invalid("vqb_forward: the exact-fp32 path supports D <= 256 (got %lld)", (long long)a->dim);
     return launch_forward_simt(a, (cudaStream_t)stream);
 }
 

@@ -58,6 +58,7 @@ int launch_forward_simt(const vqb_fwd_args* a, cudaStream_t s);
 int launch_backward_simt(const vqb_bwd_args* a, cudaStream_t s);
 int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K, int64_t D,
                        float* dtable, int64_t* hist, cudaStream_t s);
+bool forward_tensor_supported(const vqb_fwd_args* a);
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
 int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
 

@@ -1,0 +1,641 @@
+// Forward of the quantizer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), two epilogues:
+//
+//   SEARCH  (fused mode, no p_code)   nearest-codeword search + exact re-rank + gather + straight-through;
+//           the N x K distance matrix never leaves TMEM.  Replaces neg_batch_l2 + argmax + F.embedding +
+//           straight-through of src/embed.py:208-213, :130, :134, :145.
+//   PCODE   (parity mode, K <= 64)    scores -> softmax -> p_code, argmax over p_code, gather, straight-through,
+//           usage histogram: the whole of L2Embedding.forward (src/embed.py:105-147) or
+//           SeperateEmbedding.forward (:187-205, LINEAR score) in one kernel.
+//
+// Anatomy (one persistent CTA per SM, 6 warps, warp-specialised):
+//   warp 0  TMA producer   x tile [128 rows][D] fp32 (double-buffered when it fits); codebook K-blocks
+//                          [BN codes][32 floats]: resident in shared memory when the codebook is one chunk,
+//                          otherwise streamed through a ring
+//   warp 1  MMA issuer     tcgen05.mma kind::tf32, M=128, N=BN, K=8; accumulators double-buffered in TMEM
+//   warps 2-5 epilogue     tcgen05.ld 32x32b: thread = row, so soft-max / arg-max / top-k are thread-local
+//
+// Precision.  kind::tf32 reads the top 19 bits of each fp32 operand.  PASSES = 3 ("3xTF32") adds the two
+// cross terms with the operands' low parts: x = x_hi + x_lo (x_hi = hardware truncation of the raw tile, x_lo
+// written by the epilogue warps into a second tile), e = e_hi + e_lo (split once per call by the prep kernel),
+// acc = x.e_hi + x.e_lo + x_lo.e_hi, which restores fp32-level accuracy (error <= 3 * 2^-20 |x||e|).
+// PASSES = 1 is used where the MMA is the bound (large codebooks); its error 1.5 * 2^-10 |x||e| is covered by a
+// provable candidate window + exact fp32 re-rank (top-8 candidates, full exact scan if the window overflows).
+// The bias (|e|^2 for L2, b for LINEAR) is folded into the GEMM as one extra K-step: A = [1,1,1,0,..],
+// B = the bias split into three tf32-exact words, so the accumulator is directly |e|^2 - 2 x.e (or x.w + b).
+#include <cudaTypedefs.h>
+#include <math.h>
+#include "vqb_common.cuh"
+#include "vqb_tc.cuh"
+
+namespace vqb {
+using namespace tc;
+
+constexpr int BM = 128;                 // rows per tile (UMMA M)
+constexpr int XBLK = BM * 128;          // one x K-block: [128 rows][32 fp32] = 16 KB
+constexpr int TC_THREADS = 192;
+
+struct TcP {
+    const float* table;        // [K][D] fp32 score table (exact re-rank)
+    const float* gtab;         // [K][D] fp32 gather table
+    const float* bias;         // [K]    |e|^2 (L2) or b (LINEAR)
+    const float* temp;         // [1]
+    const float* emax;         // [1]    max_k |e_k|
+    float* pcode;
+    long long* idx;
+    float* q;
+    unsigned long long* hist;
+    double* sqerr;
+    unsigned int* stats;       // [0] rows re-ranked, [1] rows that needed the full exact scan
+    int N, K, D, num_tiles, num_chunks;
+    unsigned flags;
+};
+
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// hi[k] = [tf32_rn(scale * w_k) (D floats) | bias_k as three tf32-exact words | 0 x 29]   ([K][D+32])
+// lo[k] = scale * w_k - hi[k]                                                              ([K][D])
+// emax  = max_k |w_k|
+__global__ void __launch_bounds__(128)
+build_operands_kernel(const float* __restrict__ w, const float* __restrict__ bias, int K, int D, float scale,
+                      float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ emax) {
+    const int k = blockIdx.x;
+    float* hrow = hi + (size_t)k * (D + 32);
+    float sq = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float raw = w[(size_t)k * D + d];
+        const float v = scale * raw;
+        const float h = tf32_rn(v);
+        hrow[d] = h;
+        if (lo) lo[(size_t)k * D + d] = v - h;
+        sq = fmaf(raw, raw, sq);
+    }
+    if (threadIdx.x < 32) {
+        const float b = bias[k];
+        const float b0 = tf32_trunc(b);
+        const float r1 = b - b0;
+        const float b1 = tf32_trunc(r1);
+        const float b2 = r1 - b1;
+        const int j = threadIdx.x;
+        hrow[D + j] = j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : 0.f));
+    }
+    __shared__ float red[4];
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(red[0] + red[1] + red[2] + red[3])));
+}
+
+// exact score of code k for the row held (swizzled) in shared memory -- same expression and fmaf order as
+// the exact SIMT kernel (vqb_fwd_simt.cu: dot_chunk + score_of)
+template <int KB>
+__device__ __forceinline__ float exact_score(const uint8_t* sXt, int r, float xx, const float* __restrict__ table,
+                                             const float* __restrict__ enorm, int k, float tau) {
+    const float* e = table + (size_t)k * (KB * 32);
+    float dot = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 xv = *reinterpret_cast<const float4*>(sXt + kb * XBLK + sw128_offset(r, c));
+            const float4 w = ldg4(e + kb * 32 + c * 4);
+            dot = fmaf(xv.x, w.x, dot); dot = fmaf(xv.y, w.y, dot);
+            dot = fmaf(xv.z, w.z, dot); dot = fmaf(xv.w, w.w, dot);
+        }
+    }
+    const float dist = __fsub_rn(__fadd_rn(xx, __ldg(enorm + k)), 2.f * dot);
+    return tau * (-dist);
+}
+
+template <int NC>
+struct TopK {
+    float v[NC];
+    int i[NC];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) { v[j] = INFINITY; i[j] = 0; }
+    }
+    // ascending by value; among equal values the earlier (lower) index stays first
+    __device__ __forceinline__ void insert(float val, int col) {
+        v[NC - 1] = val; i[NC - 1] = col;
+#pragma unroll
+        for (int j = NC - 1; j > 0; --j) {
+            if (v[j] < v[j - 1]) {
+                const float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
+                const int ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
+            }
+        }
+    }
+};
+
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+                  const __grid_constant__ CUtensorMap tm_lo, TcP p) {
+    constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
+    constexpr int PIECES = PASSES == 3 ? 2 * KB + 1 : KB + 1;     // per chunk: hi/lo per K-block + the bias block
+    constexpr int TMEM_COLS = 2 * BN;
+    constexpr int NCAND = PASSES == 3 ? 4 : 8;
+    static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
+    static_assert(!PCODE || BN == 64, "the p_code epilogue keeps one 64-column accumulator in registers");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sX = smem;                                                        // [XS][KB][16 KB]
+    uint8_t* sXlo = sX + (size_t)XS * KB * XBLK;                               // [XS][KB][16 KB]  (PASSES == 3)
+    uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0);         // [16 KB] A block [1,1,1,0,...]
+    uint8_t* sB = sAug + XBLK;                                                 // [BS][PIECE]
+    float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65]        (PCODE)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? BM * 65 * 4 : 0));
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = x_full + XS;
+    uint64_t* xlo_full = x_empty + XS;
+    uint64_t* b_full = xlo_full + XS;
+    uint64_t* b_empty = b_full + BS;
+    uint64_t* t_full = b_empty + BS;
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time setup ----------------------------------------------------------------------------------
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_hi);
+        if (PASSES == 3) tma_prefetch_desc(&tm_lo);
+        for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
+        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+    for (int i = threadIdx.x; i < XBLK / 16; i += TC_THREADS)
+        reinterpret_cast<float4*>(sAug)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (threadIdx.x < BM)
+        *reinterpret_cast<float4*>(sAug + sw128_offset(threadIdx.x, 0)) = make_float4(1.f, 1.f, 1.f, 0.f);
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t IDESC = umma_idesc(2u, BM, BN);
+
+    if (warp == 0) {
+        // =============================== TMA producer =====================================================
+        if (lane == 0) {
+            uint32_t x_it = 0, b_it = 0;
+            bool resident_loaded = false;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
+                mbar_wait(&x_empty[xs], xph ^ 1);
+                mbar_arrive_expect_tx(&x_full[xs], KB * XBLK);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sX + ((size_t)xs * KB + kb) * XBLK, &tm_x, kb * 32, tile * BM, &x_full[xs]);
+                ++x_it;
+                if (RESIDENT && resident_loaded) continue;
+                resident_loaded = true;
+                for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
+                    for (int j = 0; j < PIECES; ++j) {
+                        const uint32_t bs = b_it % BS, bph = (b_it / BS) & 1;
+                        if (!RESIDENT) mbar_wait(&b_empty[bs], bph ^ 1);
+                        mbar_arrive_expect_tx(&b_full[bs], PIECE);
+                        const bool is_lo = PASSES == 3 && j < 2 * KB && (j & 1);
+                        const int kb = PASSES == 3 ? (j >> 1) : j;                 // the bias block has kb == KB
+                        tma_load_2d(sB + (size_t)bs * PIECE, is_lo ? &tm_lo : &tm_hi, kb * 32, chunk * BN, &b_full[bs]);
+                        ++b_it;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer =======================================================
+        if (lane == 0) {
+            uint32_t x_it = 0, b_it = 0, c_it = 0;
+            bool resident_ready = false;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
+                const uint8_t* xt = sX + (size_t)xs * KB * XBLK;
+                const uint8_t* xlt = sXlo + (size_t)xs * KB * XBLK;
+                mbar_wait(&x_full[xs], xph);
+                if (PASSES == 3 && !RESIDENT) mbar_wait(&xlo_full[xs], xph);
+                tcgen05_fence_after();
+                for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
+                    const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                    mbar_wait(&t_empty[buf], tph ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    if (RESIDENT) {
+                        if (!resident_ready) {
+                            for (int j = 0; j < PIECES; ++j) mbar_wait(&b_full[j], 0);
+                            tcgen05_fence_after();
+                            resident_ready = true;
+                        }
+                        // group A: x . e_hi (+ bias);  group B: x . e_lo;  group C (needs x_lo): x_lo . e_hi
+#pragma unroll
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const uint64_t a = umma_desc_sw128(xt + kb * XBLK);
+                            const uint64_t b = umma_desc_sw128(sB + (size_t)(PASSES == 3 ? 2 * kb : kb) * PIECE);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, (kb | k) != 0);
+                        }
+                        umma_tf32(d_tmem, umma_desc_sw128(sAug), umma_desc_sw128(sB + (size_t)(PIECES - 1) * PIECE), IDESC, true);
+                        if (PASSES == 3) {
+#pragma unroll
+                            for (int kb = 0; kb < KB; ++kb) {
+                                const uint64_t a = umma_desc_sw128(xt + kb * XBLK);
+                                const uint64_t b = umma_desc_sw128(sB + (size_t)(2 * kb + 1) * PIECE);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, true);
+                            }
+                            mbar_wait(&xlo_full[xs], xph);
+                            tcgen05_fence_after();
+#pragma unroll
+                            for (int kb = 0; kb < KB; ++kb) {
+                                const uint64_t a = umma_desc_sw128(xlt + kb * XBLK);
+                                const uint64_t b = umma_desc_sw128(sB + (size_t)(2 * kb) * PIECE);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, true);
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < PIECES; ++j) {
+                            const uint32_t bs = b_it % BS, bph = (b_it / BS) & 1;
+                            mbar_wait(&b_full[bs], bph);
+                            tcgen05_fence_after();
+                            const uint64_t b = umma_desc_sw128(sB + (size_t)bs * PIECE);
+                            const bool is_aug = j == PIECES - 1;
+                            const bool is_lo = PASSES == 3 && !is_aug && (j & 1);
+                            const int kb = PASSES == 3 ? (j >> 1) : j;
+                            if (is_aug) {
+                                umma_tf32(d_tmem, umma_desc_sw128(sAug), b, IDESC, true);
+                            } else {
+                                const uint64_t a = umma_desc_sw128(xt + kb * XBLK);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, (j | k) != 0);
+                                if (PASSES == 3 && !is_lo) {
+                                    const uint64_t al = umma_desc_sw128(xlt + kb * XBLK);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + 2 * k, b + 2 * k, IDESC, true);
+                                }
+                            }
+                            umma_commit(&b_empty[bs]);              // frees the ring slot when these MMAs retire
+                            ++b_it;
+                        }
+                    }
+                    umma_commit(&t_full[buf]);                      // accumulator of this chunk is complete
+                    ++c_it;
+                }
+                ++x_it;
+            }
+        }
+    } else {
+        // =============================== epilogue (thread = row) ==========================================
+        const int q4 = warp & 3;                                    // TMEM lane quadrant this warp may read
+        const int r = q4 * 32 + lane;                               // row within the tile == TMEM lane
+        const int et = (warp - 2) * 32 + lane;                      // 0..127 among the epilogue threads
+        const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
+        const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
+        const float emax = __ldg(p.emax);
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        uint32_t x_it = 0, c_it = 0;
+        float se_acc = 0.f;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
+            uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
+            uint8_t* sXl = sXlo + (size_t)xs * KB * XBLK;
+            mbar_wait(&x_full[xs], xph);
+            const int row0 = tile * BM;
+            const int rows = min(BM, p.N - row0);
+            const bool valid = r < rows;
+            // |x|^2 in the exact kernel's fmaf order; x_lo = x - trunc_tf32(x) for the third MMA pass
+            float xx = 0.f;
+#pragma unroll 1
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t off = kb * XBLK + sw128_offset(r, c);
+                    const float4 xv = *reinterpret_cast<const float4*>(sXt + off);
+                    xx = fmaf(xv.x, xv.x, xx); xx = fmaf(xv.y, xv.y, xx);
+                    xx = fmaf(xv.z, xv.z, xx); xx = fmaf(xv.w, xv.w, xx);
+                    if (PASSES == 3) {
+                        float4 lo;
+                        lo.x = xv.x - tf32_trunc(xv.x); lo.y = xv.y - tf32_trunc(xv.y);
+                        lo.z = xv.z - tf32_trunc(xv.z); lo.w = xv.w - tf32_trunc(xv.w);
+                        *reinterpret_cast<float4*>(sXl + off) = lo;
+                    }
+                }
+            }
+            if (PASSES == 3) {
+                fence_proxy_async_smem();                           // generic writes -> tcgen05.mma operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xlo_full[xs]);
+            }
+
+            int best = 0;
+            if (PCODE) {
+                // ---------------- scores -> softmax -> p_code, argmax over p_code ----------------------------
+                const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                mbar_wait(&t_full[buf], tph);
+                tcgen05_fence_after();
+                float v[64];
+                {
+                    float t[32];
+                    tmem_ld_32x32(tmem_base + lane_addr + buf * BN, t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = t[j];
+                    tmem_ld_32x32(tmem_base + lane_addr + buf * BN + 32, t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[32 + j] = t[j];
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[buf]);          // TMEM buffer free: next tile's MMA may start
+                ++c_it;
+                float m = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) {
+                    // L2: acc = |e|^2 - 2 x.e, score = relu(temp) * -(|x|^2 + acc)   (:115, :208-213)
+                    float s = linear ? v[k] : tau * (-(xx + v[k]));
+                    if (k >= p.K) s = -INFINITY;
+                    v[k] = s;
+                    m = fmaxf(m, s);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) {
+                    const float e = (k < p.K) ? expf(v[k] - m) : 0.f;
+                    v[k] = e;
+                    sum += e;
+                }
+                float bv = -1.f;
+                const int KP = p.K | 1;                             // odd row stride: conflict-free thread-per-row stores
+#pragma unroll
+                for (int k = 0; k < 64; ++k) {
+                    const float pk = v[k] / sum;                    // softmax (:127)
+                    if (k < p.K) {
+                        sP[r * KP + k] = pk;
+                        if (pk > bv) { bv = pk; best = k; }         // argmax over p_code, first max (:130)
+                    }
+                }
+            } else {
+                // ---------------- running top-k over the codebook chunks -------------------------------------
+                TopK<NCAND> top;
+                top.init();
+                for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
+                    const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                    mbar_wait(&t_full[buf], tph);
+                    tcgen05_fence_after();
+                    const bool full_chunk = (chunk + 1) * BN <= p.K;
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        float v[32];
+                        tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
+                        const int col0 = chunk * BN + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float val = (full_chunk || col0 + j < p.K) ? v[j] : INFINITY;
+                            if (val < top.v[NCAND - 1]) top.insert(val, col0 + j);
+                        }
+                    }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[buf]);
+                    ++c_it;
+                }
+                // provable candidate window: |approx - exact| <= eps for every code of this row
+                const float rel = PASSES == 3 ? 6.0f * 9.5367431640625e-7f : 3.0f * 9.765625e-4f;   // 6*2^-20 | 3*2^-10
+                const float eps = 1.02f * rel * sqrtf(xx) * emax + 2e-6f * (fabsf(top.v[0]) + xx);
+                const float window = top.v[0] + 2.f * eps;
+                int ncand = 1;
+#pragma unroll
+                for (int j = 1; j < NCAND; ++j) ncand += (top.v[j] <= window);
+                const bool full_scan = valid && ncand == NCAND && p.K > NCAND;
+                const bool rerank = valid && ncand > 1;
+                best = top.i[0];
+                if (full_scan) {
+                    float bs_ = -INFINITY;
+                    for (int k = 0; k < p.K; ++k) {
+                        const float s = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
+                        if (s > bs_) { bs_ = s; best = k; }
+                    }
+                } else if (rerank) {
+                    float bs_ = exact_score<KB>(sXt, r, xx, p.table, p.bias, top.i[0], tau);
+#pragma unroll
+                    for (int j = 1; j < NCAND; ++j) {
+                        if (j < ncand) {
+                            const float s = exact_score<KB>(sXt, r, xx, p.table, p.bias, top.i[j], tau);
+                            if (s > bs_ || (s == bs_ && top.i[j] < best)) { bs_ = s; best = top.i[j]; }
+                        }
+                    }
+                }
+                if (p.stats) {
+                    const unsigned m1 = __ballot_sync(0xffffffffu, rerank), m2 = __ballot_sync(0xffffffffu, full_scan);
+                    if (lane == 0) {
+                        if (m1) atomicAdd(p.stats, (unsigned)__popc(m1));
+                        if (m2) atomicAdd(p.stats + 1, (unsigned)__popc(m2));
+                    }
+                }
+            }
+
+            // ---- gather + straight-through, staged in place over the x tile ----------------------------------
+            if (valid) {
+                const float* crow = p.gtab + (size_t)best * p.D;
+                const bool skip = (p.flags & VQB_SKIP) != 0;
+#pragma unroll 1
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4* xp = reinterpret_cast<float4*>(sXt + kb * XBLK + sw128_offset(r, c));
+                        const float4 xv = *xp;
+                        const float4 cv = ldg4(crow + kb * 32 + c * 4);
+                        float4 o;
+                        if (linear) {
+                            o = cv;                                                         // (:194-197)
+                        } else {
+                            // new_latent = enc_embs + picked_code - enc_embs.detach()  (:145)
+                            o.x = __fsub_rn(__fadd_rn(xv.x, cv.x), xv.x); o.y = __fsub_rn(__fadd_rn(xv.y, cv.y), xv.y);
+                            o.z = __fsub_rn(__fadd_rn(xv.z, cv.z), xv.z); o.w = __fsub_rn(__fadd_rn(xv.w, cv.w), xv.w);
+                            if (skip) o = xv;                                               // (:142)
+                        }
+                        const float d0 = xv.x - cv.x, d1 = xv.y - cv.y, d2 = xv.z - cv.z, d3 = xv.w - cv.w;
+                        se_acc = fmaf(d0, d0, se_acc); se_acc = fmaf(d1, d1, se_acc);
+                        se_acc = fmaf(d2, d2, se_acc); se_acc = fmaf(d3, d3, se_acc);
+                        *xp = o;
+                    }
+                }
+                p.idx[row0 + r] = best;
+            }
+            if (p.hist) {
+                // warp-aggregated histogram: one atomic per distinct code per warp
+                const unsigned peers = __match_any_sync(0xffffffffu, valid ? best : -1);
+                if (valid && lane == (__ffs(peers) - 1)) atomicAdd(p.hist + best, (unsigned long long)__popc(peers));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // epilogue warps only
+            constexpr int D4 = KB * 8;
+            for (int i = et; i < rows * D4; i += 128) {
+                const int rr = i / D4, c = i % D4;
+                const float4 o = *reinterpret_cast<const float4*>(sXt + (c >> 3) * XBLK + sw128_offset(rr, c & 7));
+                stg4_stream(p.q + (size_t)(row0 + rr) * p.D + 4 * c, o);
+            }
+            if (PCODE) {
+                const int KP = p.K | 1;
+                float* dst = p.pcode + (size_t)row0 * p.K;
+                const int n = rows * p.K;
+                int rr = et / p.K, k = et - rr * p.K;               // running (row, code) of element i
+                const int step_r = 128 / p.K, step_k = 128 - step_r * p.K;
+                for (int i = et; i < n; i += 128) {
+                    __stcs(dst + i, sP[rr * KP + k]);
+                    rr += step_r; k += step_k;
+                    if (k >= p.K) { k -= p.K; ++rr; }
+                }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // sP / x tile fully drained before reuse
+            if (lane == 0) mbar_arrive(&x_empty[xs]);               // the x slot may be refilled by TMA
+            ++x_it;
+        }
+        if (p.sqerr) {
+            se_acc = warp_sum(se_acc);
+            if (lane == 0) atomicAdd(p.sqerr, (double)se_acc);
+        }
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------------------
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// host side
+// -----------------------------------------------------------------------------------------------------------
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                     uint32_t box_rows) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            set_error("libvqb200: cuTensorMapEncodeTiled is not available from the driver");
+            return VQB_ERR_CUDA;
+        }
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_elems * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("libvqb200: cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols);
+        return VQB_ERR_CUDA;
+    }
+    return VQB_OK;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t hi_bytes(int64_t K, int64_t D) { return align256((size_t)K * (D + 32) * 4); }
+static size_t lo_bytes(int64_t K, int64_t D) { return align256((size_t)K * D * 4); }
+
+// which kernel configuration serves this call (0 = none: use the exact SIMT path)
+enum TcMode { TC_NONE = 0, TC_PCODE, TC_SEARCH3, TC_SEARCH1 };
+static TcMode tc_mode(const vqb_fwd_args* a) {
+    const int64_t K = a->n_codes, D = a->dim;
+    if (a->p_code) return (K <= 64 && (D == 32 || D == 64)) ? TC_PCODE : TC_NONE;
+    if (!(a->flags & VQB_SCORE_L2)) return TC_NONE;
+    if (D != 32 && D != 64 && D != 128 && D != 256) return TC_NONE;
+    if (K <= 1024 && D <= 128) return TC_SEARCH3;
+    return TC_SEARCH1;
+}
+
+bool forward_tensor_supported(const vqb_fwd_args* a) { return tc_mode(a) != TC_NONE; }
+
+int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
+    *bytes = tc_mode(a) == TC_NONE ? 0 : hi_bytes(a->n_codes, a->dim) + lo_bytes(a->n_codes, a->dim) + 256;
+    return VQB_OK;
+}
+
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
+static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const TcP& p, cudaStream_t s) {
+    const size_t smem = (size_t)XS * KB * XBLK * (PASSES == 3 ? 2 : 1) + XBLK + (size_t)BS * BN * 128 +
+                        (PCODE ? BM * 65 * 4 : 0) + 1024 + 256;
+    if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE>;
+    VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    kern<<<grid, TC_THREADS, smem, s>>>(tx, th, tl, p);
+    VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
+    return VQB_OK;
+}
+
+int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
+    const int64_t N = a->n_rows, K = a->n_codes, D = a->dim;
+    if (N == 0) return VQB_OK;
+    const TcMode mode = tc_mode(a);
+    if (mode == TC_NONE) return invalid("vqb_forward: shape not supported by the tensor-core path");
+    const size_t need = hi_bytes(K, D) + lo_bytes(K, D) + 256;
+    if (!a->workspace || a->workspace_bytes < need) {
+        set_error("vqb_forward: workspace too small (%zu < %zu bytes)", a->workspace_bytes, need);
+        return VQB_ERR_WORKSPACE;
+    }
+    const bool linear = !(a->flags & VQB_SCORE_L2);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+    float* hi = reinterpret_cast<float*>(ws);
+    float* lo = reinterpret_cast<float*>(ws + hi_bytes(K, D));
+    uint8_t* tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
+    float* emax = reinterpret_cast<float*>(tail);
+    unsigned int* stats = a->search_stats ? a->search_stats : reinterpret_cast<unsigned int*>(tail + 16);
+    VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));
+    build_operands_kernel<<<(unsigned)K, 128, 0, s>>>(a->score_w, a->score_b, (int)K, (int)D, linear ? 1.f : -2.f,
+                                                      hi, mode == TC_SEARCH1 ? nullptr : lo, emax);
+    VQB_CHECK_LAUNCH("build_operands_kernel");
+
+    const int BN = mode == TC_PCODE ? 64 : 128;
+    CUtensorMap tx, th, tl;
+    int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM);
+    if (rc) return rc;
+    if ((rc = make_tmap_2d_f32(&th, hi, (uint64_t)K, (uint64_t)(D + 32), (uint64_t)(D + 32), BN))) return rc;
+    if ((rc = make_tmap_2d_f32(&tl, lo, (uint64_t)K, (uint64_t)D, (uint64_t)D, BN))) return rc;
+
+    TcP p;
+    p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.emax = emax;
+    p.pcode = a->p_code; p.idx = (long long*)a->idx; p.q = a->new_latent;
+    p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum; p.stats = stats;
+    p.N = (int)N; p.K = (int)K; p.D = (int)D;
+    p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
+    p.flags = a->flags;
+
+    //                      KB  BN  XS BS PASSES RESIDENT PCODE
+    if (mode == TC_PCODE) {
+        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true>(tx, th, tl, p, s);
+        return launch_tc<2, 64, 2, 5, 3, true, true>(tx, th, tl, p, s);
+    }
+    if (mode == TC_SEARCH3) {
+        if (K <= 128) {                                            // whole codebook resident in shared memory
+            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, p, s);
+            if (D == 64) return launch_tc<2, 128, 2, 5, 3, true, false>(tx, th, tl, p, s);
+        }
+        if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, p, s);
+        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, p, s);
+        return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, p, s);
+    }
+    switch (D) {
+        case 32:  return launch_tc<1, 128, 2, 4, 1, false, false>(tx, th, tl, p, s);
+        case 64:  return launch_tc<2, 128, 2, 4, 1, false, false>(tx, th, tl, p, s);
+        case 128: return launch_tc<4, 128, 1, 4, 1, false, false>(tx, th, tl, p, s);
+        default:  return launch_tc<8, 128, 1, 4, 1, false, false>(tx, th, tl, p, s);
+    }
+}
+
+}  // namespace vqb

@@ -69,6 +69,8 @@ class _QuantizerBase(nn.Module):
         # device-side usage histogram (replaces the host list of bin/train_vqvae.py:256-261)
         self.usage = UsageHistogram(vocab_size)
         self.track_usage = True
+        # forward on the tcgen05 kernel where the shape allows it (False: exact-fp32 CUDA-core kernel)
+        self.tensor_cores = True
         self.last_idx = None
 
     def _init_attr(self, latent_dim, phn_attr_pth, proj_attr):
@@ -125,7 +127,7 @@ class L2Embedding(_QuantizerBase):
         self.stop_grad = stop_grad
         d_attr = self._init_attr(latent_dim, phn_attr_pth, proj_attr)
         self.learnable_table = nn.Parameter(torch.randn((vocab_size, latent_dim - d_attr)))
-        # large-codebook option: search with the tcgen05 kernel and do not materialise p_code
+        # large-codebook option: do not materialise p_code (slot 1 of the return tuple is None)
         self.fused_search = False
 
     @property
@@ -146,7 +148,7 @@ class L2Embedding(_QuantizerBase):
             enc_embs, self.learnable_table, attr, pw, pb, self.temp, stop_grad=self.stop_grad, skip=skip,
             n_real_rows=first_n_real_mel * S if first_n_real_mel > 0 else 0,
             want_pcode=not self.fused_search, hist=self._hist(enc_embs), want_losses=want_losses,
-            search_tensor=self.fused_search)
+            tensor_cores=self.tensor_cores)
         self.last_idx = idx
         return (p_code, new_latent) + self._losses(vq, commit)
 
@@ -175,6 +177,6 @@ class SeperateEmbedding(_QuantizerBase):
         attr, pw, pb = self._attr_params()
         p_code, new_latent, idx = VF.vq_linear(
             enc_embs, self.asr_final_layer.weight, self.asr_final_layer.bias, self.embedding.weight,
-            attr, pw, pb, stop_grad=self.stop_grad, hist=self._hist(enc_embs))
+            attr, pw, pb, stop_grad=self.stop_grad, hist=self._hist(enc_embs), tensor_cores=self.tensor_cores)
         self.last_idx = idx
         return p_code, new_latent, 0, 0

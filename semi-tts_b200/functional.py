@@ -134,13 +134,13 @@ def _loss_backward(x2d, table, idx, g_vq, g_commit, dx, dx_accumulate, dtable):
 
 class _Cfg:
     """Per-call options (plain Python, not a tensor)."""
-    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "search_tensor")
+    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores")
 
     def __init__(self, stop_grad=True, skip=False, n_real_rows=0, want_pcode=True, hist=None,
-                 want_losses=False, search_tensor=False):
+                 want_losses=False, tensor_cores=True):
         self.stop_grad, self.skip, self.n_real_rows = bool(stop_grad), bool(skip), int(n_real_rows)
         self.want_pcode, self.hist, self.want_losses = bool(want_pcode), hist, bool(want_losses)
-        self.search_tensor = bool(search_tensor)
+        self.tensor_cores = bool(tensor_cores)
 
 
 def _g32(t):
@@ -168,7 +168,7 @@ class _VQL2(torch.autograd.Function):
             raise RuntimeError("semi-tts_b200: enc_embs has D=%d but the codebook has D=%d" % (D, table.shape[1]))
         if not cfg.want_pcode and not cfg.stop_grad:
             raise RuntimeError("semi-tts_b200: the ST-onehot variant (stop_grad=False) needs p_code")
-        flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.SEARCH_TENSOR if cfg.search_tensor else 0)
+        flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         temp_c = _c(temp.detach())
         p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
                                           cfg.want_losses, tbf)
@@ -225,10 +225,10 @@ class _VQL2(torch.autograd.Function):
 
 
 def vq_l2(x, learnable_table, phn_attr, proj_w, proj_b, temp, stop_grad=True, skip=False, n_real_rows=0,
-          want_pcode=True, hist=None, want_losses=False, search_tensor=False):
+          want_pcode=True, hist=None, want_losses=False, tensor_cores=True):
     """L2 quantizer (src/embed.py:105-147).
     Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S] int64, vq_loss or None, commit_loss or None)."""
-    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, search_tensor)
+    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores)
     return _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
 
 
@@ -265,8 +265,8 @@ class _VQLinear(torch.autograd.Function):
         if table.shape != (K, D) or asr_w.shape[1] != D:
             raise RuntimeError("semi-tts_b200: shape mismatch between enc_embs, asr_final_layer and the embedding table")
         w, b = _c(asr_w.detach()), _c(asr_b.detach())
-        p_code, idx, q, _ = _run_forward(_fwd_flags(_lib.SCORE_LINEAR, cfg), x2d, w, b, table, None, True,
-                                         cfg.hist, False)
+        flags = _fwd_flags(_lib.SCORE_LINEAR, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
+        p_code, idx, q, _ = _run_forward(flags, x2d, w, b, table, None, True, cfg.hist, False)
         ctx.set_materialize_grads(False)
         ctx.cfg, ctx.shape = cfg, (B, S, D, K)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
@@ -292,9 +292,9 @@ class _VQLinear(torch.autograd.Function):
         return dx.view(B, S, D), d_w, colsum, d_emb, None, d_pw, d_pb, None
 
 
-def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None):
+def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None, tensor_cores=True):
     """Separate quantizer (src/embed.py:187-205). Returns (p_code, new_latent, idx)."""
-    cfg = _Cfg(stop_grad=stop_grad, hist=hist)
+    cfg = _Cfg(stop_grad=stop_grad, hist=hist, tensor_cores=tensor_cores)
     return _VQLinear.apply(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, cfg)
 
 
