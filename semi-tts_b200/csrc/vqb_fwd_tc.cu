@@ -19,7 +19,7 @@
 // written by the epilogue warps into a second tile), e = e_hi + e_lo (split once per call by the prep kernel),
 // acc = x.e_hi + x.e_lo + x_lo.e_hi, which restores fp32-level accuracy (error <= 3 * 2^-20 |x||e|).
 // PASSES = 1 is used where the MMA is the bound (large codebooks); its error 1.5 * 2^-10 |x||e| is covered by a
-// provable candidate window + exact fp32 re-rank (top-8 candidates, full exact scan if the window overflows).
+// provable candidate window + exact fp32 re-rank (per-row candidate list; full exact scan if it overflows).
 // The bias (|e|^2 for L2, b for LINEAR) is folded into the GEMM as one extra K-step: A = [1,1,1,0,..],
 // B = the bias split into three tf32-exact words, so the accumulator is directly |e|^2 - 2 x.e (or x.w + b).
 #include <cudaTypedefs.h>
@@ -112,27 +112,6 @@ __device__ __forceinline__ float exact_score(const uint8_t* sXt, int r, float xx
     return tau * (-dist);
 }
 
-template <int NC>
-struct TopK {
-    float v[NC];
-    int i[NC];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int j = 0; j < NC; ++j) { v[j] = INFINITY; i[j] = 0; }
-    }
-    // ascending by value; among equal values the earlier (lower) index stays first
-    __device__ __forceinline__ void insert(float val, int col) {
-        v[NC - 1] = val; i[NC - 1] = col;
-#pragma unroll
-        for (int j = NC - 1; j > 0; --j) {
-            if (v[j] < v[j - 1]) {
-                const float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
-                const int ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
-            }
-        }
-    }
-};
-
 template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
@@ -140,7 +119,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
     constexpr int PIECES = PASSES == 3 ? 2 * KB + 1 : KB + 1;     // per chunk: hi/lo per K-block + the bias block
     constexpr int TMEM_COLS = 2 * BN;
-    constexpr int NCAND = PASSES == 3 ? 4 : 8;
+    constexpr int CAP = 16;                                       // per-row candidate list capacity (SEARCH)
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
     static_assert(!PCODE || BN == 64, "the p_code epilogue keeps one 64-column accumulator in registers");
 
@@ -150,8 +129,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sXlo = sX + (size_t)XS * KB * XBLK;                               // [XS][KB][16 KB]  (PASSES == 3)
     uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0);         // [16 KB] A block [1,1,1,0,...]
     uint8_t* sB = sAug + XBLK;                                                 // [BS][PIECE]
-    float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65]        (PCODE)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? BM * 65 * 4 : 0));
+    float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65] p_code staging (PCODE)
+    uint2* sCand = reinterpret_cast<uint2*>(sP);                               // [CAP][128] (value, code)  (SEARCH)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? BM * 65 * 4 : CAP * BM * 8));
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
     uint64_t* xlo_full = x_empty + XS;
@@ -357,36 +337,51 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);          // TMEM buffer free: next tile's MMA may start
                 ++c_it;
+                // scores in the log2 domain: s2 = log2(e) * score, so that exp(score - max) = ex2(s2 - max2)
+                //   L2:     score = relu(temp) * -(|x|^2 + acc),  acc = |e|^2 - 2 x.e     (:115, :208-213)
+                //   LINEAR: score = acc = x.w + b                                          (:190)
+                const float LOG2E = 1.4426950408889634f;
+                const float mul = linear ? LOG2E : -tau * LOG2E;
+                const float add = linear ? 0.f : xx;
                 float m = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < 64; ++k) {
-                    // L2: acc = |e|^2 - 2 x.e, score = relu(temp) * -(|x|^2 + acc)   (:115, :208-213)
-                    float s = linear ? v[k] : tau * (-(xx + v[k]));
-                    if (k >= p.K) s = -INFINITY;
-                    v[k] = s;
-                    m = fmaxf(m, s);
+                    float s2 = mul * (add + v[k]);
+                    if (k >= p.K) s2 = -INFINITY;
+                    v[k] = s2;
+                    m = fmaxf(m, s2);
                 }
                 float sum = 0.f;
 #pragma unroll
                 for (int k = 0; k < 64; ++k) {
-                    const float e = (k < p.K) ? expf(v[k] - m) : 0.f;
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m));     // k >= K: ex2(-inf) = 0
                     v[k] = e;
                     sum += e;
                 }
+                const float inv = 1.f / sum;
                 float bv = -1.f;
                 const int KP = p.K | 1;                             // odd row stride: conflict-free thread-per-row stores
 #pragma unroll
                 for (int k = 0; k < 64; ++k) {
-                    const float pk = v[k] / sum;                    // softmax (:127)
+                    const float pk = v[k] * inv;                    // softmax (:127)
                     if (k < p.K) {
                         sP[r * KP + k] = pk;
                         if (pk > bv) { bv = pk; best = k; }         // argmax over p_code, first max (:130)
                     }
                 }
             } else {
-                // ---------------- running top-k over the codebook chunks -------------------------------------
-                TopK<NCAND> top;
-                top.init();
+                // ---------------- running minimum + candidate list over the codebook chunks ----------------
+                // |approx - exact| <= eps for every code of this row (see header), so the exact arg-min lies
+                // among the codes whose approximate value is within W = 2 eps of the approximate minimum.
+                // Fast path per 32 columns: one min-reduction and one compare; only batches that reach the
+                // running threshold append (value, code) pairs to the row's list in shared memory.
+                const float xn = sqrtf(xx);
+                const float rel = PASSES == 3 ? 6.0f * 9.5367431640625e-7f : 3.0f * 9.765625e-4f;   // 6*2^-20 | 3*2^-10
+                const float W = 2.f * (1.02f * rel * xn * emax + 2e-6f * (xn + emax) * (xn + emax));
+                float mn = INFINITY, thr = INFINITY;
+                int cnt = 0;
+                bool overflow = false;
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
                     const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
                     mbar_wait(&t_full[buf], tph);
@@ -397,10 +392,32 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         float v[32];
                         tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
+                        if (!full_chunk) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float val = (full_chunk || col0 + j < p.K) ? v[j] : INFINITY;
-                            if (val < top.v[NCAND - 1]) top.insert(val, col0 + j);
+                            for (int j = 0; j < 32; ++j) if (col0 + j >= p.K) v[j] = INFINITY;
+                        }
+                        float bm = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) bm = fminf(bm, v[j]);
+                        if (bm <= thr) {
+                            mn = fminf(mn, bm);
+                            thr = mn + W;
+                            if (cnt > 0 && cnt >= CAP - 4) {
+                                // make room: drop entries that fell out of the (tighter) window
+                                int kept = 0;
+                                for (int c2 = 0; c2 < cnt; ++c2) {
+                                    const uint2 e = sCand[c2 * BM + r];
+                                    if (__uint_as_float(e.x) <= thr) sCand[(kept++) * BM + r] = e;
+                                }
+                                cnt = kept;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (v[j] <= thr) {
+                                    if (cnt < CAP) sCand[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
+                                    else overflow = true;
+                                }
+                            }
                         }
                     }
                     tcgen05_fence_before();
@@ -408,29 +425,29 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                     ++c_it;
                 }
-                // provable candidate window: |approx - exact| <= eps for every code of this row
-                const float rel = PASSES == 3 ? 6.0f * 9.5367431640625e-7f : 3.0f * 9.765625e-4f;   // 6*2^-20 | 3*2^-10
-                const float eps = 1.02f * rel * sqrtf(xx) * emax + 2e-6f * (fabsf(top.v[0]) + xx);
-                const float window = top.v[0] + 2.f * eps;
-                int ncand = 1;
-#pragma unroll
-                for (int j = 1; j < NCAND; ++j) ncand += (top.v[j] <= window);
-                const bool full_scan = valid && ncand == NCAND && p.K > NCAND;
-                const bool rerank = valid && ncand > 1;
-                best = top.i[0];
+                // survivors of the final window -> exact fp32 re-rank (same expression / fmaf order as the SIMT kernel)
+                int ncand = 0;
+                float bs_ = -INFINITY;
+                int first = 0;
+                for (int c2 = 0; c2 < cnt; ++c2) {
+                    const uint2 e = sCand[c2 * BM + r];
+                    if (__uint_as_float(e.x) <= thr) { if (ncand == 0) first = (int)e.y; ++ncand; }
+                }
+                const bool full_scan = valid && overflow;
+                const bool rerank = valid && !overflow && ncand > 1;
+                best = first;
                 if (full_scan) {
-                    float bs_ = -INFINITY;
                     for (int k = 0; k < p.K; ++k) {
-                        const float s = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
-                        if (s > bs_) { bs_ = s; best = k; }
+                        const float sc = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
+                        if (sc > bs_) { bs_ = sc; best = k; }
                     }
                 } else if (rerank) {
-                    float bs_ = exact_score<KB>(sXt, r, xx, p.table, p.bias, top.i[0], tau);
-#pragma unroll
-                    for (int j = 1; j < NCAND; ++j) {
-                        if (j < ncand) {
-                            const float s = exact_score<KB>(sXt, r, xx, p.table, p.bias, top.i[j], tau);
-                            if (s > bs_ || (s == bs_ && top.i[j] < best)) { bs_ = s; best = top.i[j]; }
+                    for (int c2 = 0; c2 < cnt; ++c2) {
+                        const uint2 e = sCand[c2 * BM + r];
+                        if (__uint_as_float(e.x) <= thr) {
+                            const int k = (int)e.y;
+                            const float sc = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
+                            if (sc > bs_ || (sc == bs_ && k < best)) { bs_ = sc; best = k; }
                         }
                     }
                 }
@@ -569,7 +586,7 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
 template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const TcP& p, cudaStream_t s) {
     const size_t smem = (size_t)XS * KB * XBLK * (PASSES == 3 ? 2 : 1) + XBLK + (size_t)BS * BN * 128 +
-                        (PCODE ? BM * 65 * 4 : 0) + 1024 + 256;
+                        (PCODE ? BM * 65 * 4 : 16 * BM * 8) + 1024 + 256;
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
     auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -624,7 +641,7 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     if (mode == TC_SEARCH3) {
         if (K <= 128) {                                            // whole codebook resident in shared memory
             if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, p, s);
-            if (D == 64) return launch_tc<2, 128, 2, 5, 3, true, false>(tx, th, tl, p, s);
+            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, p, s);
         }
         if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, p, s);
         if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, p, s);

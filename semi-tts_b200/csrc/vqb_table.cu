@@ -53,19 +53,21 @@ table_backward_kernel(const float* __restrict__ dtable, const float* __restrict_
         }
         return;
     }
-    // projection part: one thread per (j, a) pair plus one per bias element
-    const int t = ((int)blockIdx.x - n_elem_blocks) * blockDim.x + threadIdx.x;
+    // projection part: one warp per output (j, a) / bias element j; lanes stride over the K codes
+    const int o = (((int)blockIdx.x - n_elem_blocks) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const int n_w = Da * A;
-    if (t >= n_w + Da) return;
-    const int j = t < n_w ? t / A : t - n_w;
-    const int a = t < n_w ? t % A : -1;
+    if (o >= n_w + Da) return;
+    const int j = o < n_w ? o / A : o - n_w;
+    const int a = o < n_w ? o % A : -1;
     float acc = 0.f;
-    for (int k = 0; k < K; ++k) {
+    for (int k = lane; k < K; k += 32) {
         float v = dtable[(size_t)k * D + Dl + j];
         if (colsum) v = fmaf(2.f * table[(size_t)k * D + Dl + j], colsum[k], v);
         acc += (a >= 0) ? v * attr[(size_t)k * A + a] : v;
     }
-    if (a >= 0) d_proj_w[(size_t)j * A + a] = acc; else d_proj_b[j] = acc;
+    acc = warp_sum(acc);
+    if (lane == 0) { if (a >= 0) d_proj_w[(size_t)j * A + a] = acc; else d_proj_b[j] = acc; }
 }
 
 }  // namespace vqb
@@ -102,7 +104,7 @@ extern "C" int vqb_table_backward(const float* dtable, const float* table, const
     if (!has_attr) { n_attr = 0; dim_attr = 0; }
     const int64_t n_elem = n_codes * (dim - dim_attr);
     const int n_elem_blocks = (int)ceil_div(n_elem, 256);
-    const int n_proj_blocks = has_attr ? (int)ceil_div(dim_attr * n_attr + dim_attr, 256) : 0;
+    const int n_proj_blocks = has_attr ? (int)ceil_div((dim_attr * n_attr + dim_attr) * 32, 256) : 0;
     table_backward_kernel<<<n_elem_blocks + n_proj_blocks, 256, 0, (cudaStream_t)stream>>>(
         dtable, table, colsum, phn_attr, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr,
         n_elem_blocks, d_learnable, d_proj_w, d_proj_b);
