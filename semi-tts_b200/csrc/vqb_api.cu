@@ -142,7 +142,10 @@ static int validate_bwd(const vqb_bwd_args* a) {
 extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
     if (!bytes) return invalid("vqb_backward_workspace: bytes is NULL");
     *bytes = 0;
-    return validate_bwd(a);
+    int rc = validate_bwd(a);
+    if (rc) return rc;
+    if (a->n_rows > 0) return backward_tensor_workspace(a, bytes);
+    return VQB_OK;
 }
 
 extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
@@ -182,5 +185,6 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->dx) ||
         !aligned16(a->d_score_w) || (a->g_q && !aligned16(a->g_q)) || (a->d_gather && !aligned16(a->d_gather)))
         return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
+    if (backward_tensor_supported(a)) return launch_backward_tensor(a, s);
     return launch_backward_simt(a, s);
 }

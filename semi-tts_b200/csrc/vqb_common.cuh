@@ -61,5 +61,8 @@ int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K,
 bool forward_tensor_supported(const vqb_fwd_args* a);
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
 int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
+bool backward_tensor_supported(const vqb_bwd_args* a);
+int backward_tensor_workspace(const vqb_bwd_args* a, size_t* bytes);
+int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s);
 
 }  // namespace vqb

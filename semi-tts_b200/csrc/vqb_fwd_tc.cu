@@ -75,7 +75,7 @@ build_operands_kernel(const float* __restrict__ w, const float* __restrict__ bia
         sq = fmaf(raw, raw, sq);
     }
     if (threadIdx.x < 32) {
-        const float b = bias[k];
+        const float b = bias ? bias[k] : 0.f;
         const float b0 = tf32_trunc(b);
         const float r1 = b - b0;
         const float b1 = tf32_trunc(r1);
@@ -89,6 +89,11 @@ build_operands_kernel(const float* __restrict__ w, const float* __restrict__ bia
     __syncthreads();
     if (threadIdx.x == 0)
         atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(red[0] + red[1] + red[2] + red[3])));
+}
+
+void launch_build_operands(const float* w, const float* bias, int K, int D, float scale, float* hi, float* lo,
+                           float* emax, cudaStream_t s) {
+    build_operands_kernel<<<(unsigned)K, 128, 0, s>>>(w, bias, K, D, scale, hi, lo, emax);
 }
 
 // exact score of code k for the row held (swizzled) in shared memory -- same expression and fmaf order as
@@ -533,7 +538,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // host side
 // -----------------------------------------------------------------------------------------------------------
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
-                     uint32_t box_rows) {
+                     uint32_t box_rows, bool atom32b) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -551,7 +556,8 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     cuuint32_t box[2] = {32, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("libvqb200: cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,

@@ -64,6 +64,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -110,6 +115,36 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr) {
     d |= (uint64_t)2 << 61;               // bits 61-63 layout: SWIZZLE_128B
     return d;
 }
+// MN-major operand with the 128-byte swizzle: the M (or N) index runs along the 128-byte rows (32 fp32 per
+// group, groups `lbo_bytes` apart) and the K index runs across rows (8 rows = one 1024-byte swizzle atom,
+// atoms `sbo_bytes` apart).  A TMA box [rows][32 fp32] is exactly such a group with K = the row index.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem_ptr) & 0x3FFFF) >> 4;
+    uint64_t d = addr;
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// tf32 MN-major operands only exist with the "128-byte swizzle, 32-byte atom" layout (descriptor layout type 1;
+// TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks of a 128-byte row are XOR-ed with (row mod 4),
+// the swizzle atom is 4 rows (512 B); `sbo_bytes` is the distance between 4-row atoms along K.
+__device__ __forceinline__ uint64_t umma_desc_mn_32b(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem_ptr) & 0x3FFFF) >> 4;
+    uint64_t d = addr;
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;               // layout: SWIZZLE_128B_BASE32B
+    return d;
+}
+// byte offset of 16-byte chunk c16 (0..7) of row r in a [rows][128 B] block stored with that swizzle
+__device__ __forceinline__ uint32_t sw32b_offset(int r, int c16) {
+    return (uint32_t)(r * 128 + ((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4)));
+}
+constexpr uint32_t UMMA_A_MN = 1u << 15;   // instruction-descriptor bits: operand is MN-major
+constexpr uint32_t UMMA_B_MN = 1u << 16;
 // Instruction descriptor: D = fp32, A/B format `fmt` (0 f16, 1 bf16, 2 tf32), both K-major, shape M x N
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -147,6 +182,6 @@ __device__ __forceinline__ bool elect_one() {
 
 // host: build a 2-D fp32 row-major tensor map [rows][cols], box = box_rows x 32 floats, SWIZZLE_128B
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
-                     uint32_t box_rows);
+                     uint32_t box_rows, bool atom32b = false);
 
 }  // namespace vqb

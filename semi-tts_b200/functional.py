@@ -119,6 +119,10 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.dx, a.d_score_w, a.colsum, a.d_gather, a.d_temp = ptr(dx), ptr(d_w), ptr(colsum), ptr(d_gather), ptr(d_temp)
     with torch.cuda.device(dev):
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.vqb_backward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
+        ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8) if nbytes.value else None
+        a.workspace, a.workspace_bytes = ptr(ws), nbytes.value
         _lib.check(lib.vqb_backward(ctypes.byref(a), _stream(x2d)))
     return dx, d_w, colsum, d_gather, d_temp
 
@@ -197,7 +201,8 @@ class _VQL2(torch.autograd.Function):
         dev = x2d.device
         g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
-        flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TEMP_GRAD if ctx.temp_grad else 0)
+        flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TEMP_GRAD if ctx.temp_grad else 0) | \
+            (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         d_temp = colsum = None
         if g_p2 is None and g_q2 is None:
             dx, d_w = None, torch.zeros(K, D, device=dev, dtype=torch.float32)
@@ -285,7 +290,7 @@ class _VQLinear(torch.autograd.Function):
             return (None,) * 8
         g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
-        flags = _fwd_flags(_lib.SCORE_LINEAR, cfg)
+        flags = _fwd_flags(_lib.SCORE_LINEAR, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         dx, d_w, colsum, d_tab, _ = _run_backward(flags, 0, x2d, w, None, table, None, p_code, idx, g_p2, g_q2,
                                                   True, True)
         d_emb, d_pw, d_pb = _table_backward(d_tab, None, None, phn_attr, ctx.Da)

@@ -301,3 +301,35 @@ def test_config2_size_against_cpu_port_and_properties():
         tab = m.embedding.weight.data
         _, q2, _, _ = m(tab[m.last_idx])
         assert torch.equal(m.last_idx.cpu(), idx)
+
+
+@pytest.mark.parametrize("B,S,first_n", [(4, 128, 2), (3, 256, 1), (5, 77, 0), (2, 128, 2)])
+def test_tensor_core_backward_vs_oracle_and_simt(B, S, first_n):
+    """tcgen05 backward (tile-aligned real/fake split, ragged last tile) against the fp64 oracle and the
+    exact-fp32 CUDA-core backward."""
+    g = load_golden("l2_attr_stopgrad")
+    gen = torch.Generator().manual_seed(B * 1000 + S)
+    x_cpu = torch.randn(B, S, 64, generator=gen)
+    gp_cpu = torch.randn(B, S, 43, generator=gen)
+    gq_cpu = torch.randn(B, S, 64, generator=gen)
+    res = {}
+    for tc in (True, False):
+        m = build_module(g, "l2")
+        m.tensor_cores = tc
+        x = x_cpu.cuda().requires_grad_(True)
+        p, q, _, _ = m(x, first_n)
+        torch.autograd.backward([p, q], [gp_cpu.cuda(), gq_cpu.cuda()])
+        res[tc] = (x.grad.cpu().numpy(), _grad(m.learnable_table), _grad(m.proj_attr.weight), _grad(m.proj_attr.bias),
+                   p.detach().cpu().numpy(), m.last_idx.cpu().numpy())
+    E64 = _table64(g)
+    f64 = O.l2_forward(x_cpu.numpy(), E64, 1.0)
+    assert np.array_equal(res[True][5], f64["idx"])
+    b64 = O.l2_backward(x_cpu.numpy(), E64, 1.0, f64["p_code"], f64["idx"], gp_cpu.numpy(), gq_cpu.numpy(),
+                        first_n_real_rows=first_n * S)
+    t64 = O.table_backward(b64["dtable"], g["sd.phn_attr.weight"], g["sd.proj_attr.weight"])
+    for tc in (True, False):
+        dx, dlt, dpw, dpb = res[tc][:4]
+        assert rel_err(dx, b64["dx"]) < TOL, tc
+        assert rel_err(dlt, t64["d_learnable"]) < TOL, tc
+        assert rel_err(dpw, t64["d_proj_w"]) < TOL, tc
+        assert rel_err(dpb, t64["d_proj_b"]) < TOL, tc
