@@ -237,6 +237,9 @@ def run_ours(args, rank, world, local_rank):
     try:
         pool = None
         for s in sets:
+            for p_ in m.parameters():
+                p_.grad = None                  # as after optimizer.zero_grad(): backward assigns, it does not accumulate
+            s[0].grad = None
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 step(s)

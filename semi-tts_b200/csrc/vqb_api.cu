@@ -78,6 +78,11 @@ static int check_common(const char* fn, int64_t N, int64_t D, int64_t K) {
 
 using namespace vqb;
 
+namespace vqb { void set_debug_timeline(void* p); }
+// undocumented developer hook: device buffer of 128 u64 that CTA 0 of the tensor-core forward fills with
+// (tag << 56 | globaltimer ns) marks; pass NULL to disable
+extern "C" __attribute__((visibility("default"))) void vqb_debug_set_timeline(void* dev_ptr) { vqb::set_debug_timeline(dev_ptr); }
+
 extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
 extern "C" const char* vqb_last_error(void) { return g_err; }
 

@@ -18,7 +18,10 @@
 //              D2 stays in TMEM for the whole kernel: the K x D reduction over all of the CTA's rows costs one
 //              flush per CTA.  tf32 MN-major operands must use the 128B-swizzle/32B-atom layout, K-major ones the
 //              plain 128B swizzle, so C is written in both layouts; the C_lo pass reuses the same two buffers.
-//   warp 2     index-keyed scatter of g_q into a shared-memory accumulator [64][D] (flushed once per CTA)
+//                GEMM 3  D3[* x 64]   += ones^T x [C ; then C_lo]: the column sums of C, also resident in TMEM
+//   warp 2     index-keyed scatter of g_q into a shared-memory accumulator [64][D]
+//   The K x D sums are flushed once per CTA as plain stores into a per-CTA partial buffer; a small reduce kernel
+//   adds the partials in a fixed order (no atomics anywhere: gradients are bit-reproducible).
 //   warps 4-7  then read D1 from TMEM, form dx and stage it for coalesced 128-bit stores.
 #include <cudaTypedefs.h>
 #include <math.h>
@@ -32,6 +35,9 @@ constexpr int BBM = 128;                // rows per tile
 constexpr int BXBLK = BBM * 128;        // one row-tile K-block: [128 rows][32 fp32] = 16 KB
 constexpr int BEBLK = 64 * 128;         // one table group: [64 codes][32 fp32] = 8 KB
 constexpr int BWD_THREADS = 256;
+// per-CTA partial record: [0] x part of C^T x, [1] x_lo part, [2] scatter sums (each 64 x 64), [3] column sums (64)
+constexpr int PART_KD = 64 * 64;
+constexpr int PARTIAL_FLOATS = 3 * PART_KD + 64;
 
 struct BwdTcP {
     const float* p;
@@ -43,9 +49,13 @@ struct BwdTcP {
     float* dW;
     float* colsum;
     float* dG;                // LINEAR: scatter destination; L2: NULL (scatter goes to dW)
+    float* partial;           // [grid][PARTIAL_FLOATS] per-CTA partial sums
+    unsigned long long* dbg;  // optional timeline buffer (developer hook)
     int N, K, n_real, num_tiles;
     unsigned flags;
 };
+
+#define VQB_BTL(tag) do { if (p.dbg && r == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
 
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
@@ -67,7 +77,8 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sCmn = sC + 2 * BXBLK;                  // [2][16 KB]  C, then C_lo: MN-major, SW128/32B  (GEMM 2 B); staging of g_p before
     uint8_t* sE = sCmn + 2 * BXBLK;                  // [2KB][8 KB] E_hi groups, then E_lo groups (SW128/32B)
     float* sAcc = reinterpret_cast<float*>(sE + 2 * KB * BEBLK);    // [64][D] scatter accumulator
-    int* sIdx = reinterpret_cast<int*>(sAcc + 64 * D);              // [128]
+    uint8_t* sOnes = reinterpret_cast<uint8_t*>(sAcc + 64 * D);     // [128 rows][32 fp32] of 1.0 (GEMM 3 A operand)
+    int* sIdx = reinterpret_cast<int*>(sOnes + BXBLK);              // [128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIdx + BBM);
     uint64_t* e_full = bars;
     uint64_t* in_full = bars + 1;
@@ -93,11 +104,14 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     if (warp == 3) tmem_alloc<TMEM_COLS>(tmem_slot);
     for (int i = threadIdx.x; i < 64 * D; i += BWD_THREADS) sAcc[i] = 0.f;
+    for (int i = threadIdx.x; i < BXBLK / 16; i += BWD_THREADS)
+        reinterpret_cast<float4*>(sOnes)[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t d1 = tmem_base, d2 = tmem_base + 128;
+    const uint32_t d1 = tmem_base, d2 = tmem_base + 128, d3 = tmem_base + 192;
 
     auto tile_is_real = [&](int tile) { return p.n_real <= 0 || (tile + 1) * BBM <= p.n_real || p.n_real >= p.N; };
 
@@ -156,6 +170,8 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                             const uint64_t a = umma_desc_mn_32b(sX + ks * 1024, BXBLK, 512);
                             const uint64_t b = umma_desc_mn_32b(sCmn + ks * 1024, BXBLK, 512);
                             umma_tf32(d2, a, b, IDESC2, d2_started || (pass | ks) != 0);
+                            // GEMM 3: every TMEM lane of D3 accumulates sum_r C[r][k] (all A groups alias the ones block)
+                            umma_tf32(d3, umma_desc_mn_32b(sOnes + ks * 1024, 0, 512), b, IDESC2, d2_started || (pass | ks) != 0);
                         }
                     }
                     if (pass == 0) umma_commit(p1_done);
@@ -201,12 +217,9 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(scat_done);
         }
-        if (do_scatter) {
-            float* dst = l2 ? p.dW : p.dG;
-            for (int i = lane; i < K * (D / 4); i += 32) {
-                const float4 a = reinterpret_cast<const float4*>(sAcc)[i];
-                if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(dst + 4 * (size_t)i, a);
-            }
+        {
+            float4* dst = reinterpret_cast<float4*>(p.partial + (size_t)blockIdx.x * PARTIAL_FLOATS + 2 * PART_KD);
+            for (int i = lane; i < PART_KD / 4; i += 32) dst[i] = reinterpret_cast<const float4*>(sAcc)[i];
         }
     } else if (warp >= 4) {
         // =============================== row threads ======================================================
@@ -215,11 +228,10 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const float tau = l2 ? fmaxf(__ldg(p.temp), 0.f) : 1.f;
         const float cmul = l2 ? -tau : 1.f;
-        float cs[64];
-#pragma unroll
-        for (int k = 0; k < 64; ++k) cs[k] = 0.f;
         int real_tiles = 0;
         uint32_t it = 0;
+        int tl_n = 0;
+        VQB_BTL(1);
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
             const int row0 = tile * BBM;
@@ -227,7 +239,9 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const bool valid = r < rows;
             const bool real = tile_is_real(tile);
             real_tiles += real;
+            VQB_BTL(2);
             mbar_wait(in_full, ph);
+            VQB_BTL(3);
             float* stP = reinterpret_cast<float*>(sC);
             float* stG = reinterpret_cast<float*>(sCmn);
             const int nfl = rows * K, nbulk = ((nfl * 4) & ~15) >> 2;
@@ -238,22 +252,26 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            // ---- softmax backward for row r --------------------------------------------------------------
-            float c[64];
-            float s = 0.f;
+            // ---- softmax backward for row r (all loads of the row first, then the arithmetic) ------------------
+            float c[64], gg[64];
 #pragma unroll
             for (int k = 0; k < 64; ++k) {
-                if (valid && k < K) s = fmaf(stG[r * K + k], stP[r * K + k], s);
+                const bool on = valid && k < K;
+                c[k] = on ? stP[r * K + k] : 0.f;
+                gg[k] = on ? stG[r * K + k] : 0.f;
             }
-            float rsum = 0.f;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 64; ++k) s4[k & 3] = fmaf(gg[k], c[k], s4[k & 3]);
+            const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 64; ++k) {
-                float v = 0.f;
-                if (valid && k < K) v = cmul * (stP[r * K + k] * (stG[r * K + k] - s));
-                c[k] = v;
-                rsum += v;
-                if (real) cs[k] += v;
+                c[k] = cmul * (c[k] * (gg[k] - s));
+                r4[k & 3] += c[k];
             }
+            const float rsum = (r4[0] + r4[1]) + (r4[2] + r4[3]);
+            VQB_BTL(4);
             asm volatile("bar.sync 1, 128;" ::: "memory");        // staging fully consumed: C may overwrite it
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
@@ -267,18 +285,21 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
+                float4 xv[8];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const uint32_t off = kb * BXBLK + sw32b_offset(r, ch);
-                    const float4 xv = *reinterpret_cast<const float4*>(sX + off);
-                    *reinterpret_cast<float4*>(sXlo + off) = make_float4(tf32_lo(xv.x), tf32_lo(xv.y), tf32_lo(xv.z), tf32_lo(xv.w));
-                }
+                for (int ch = 0; ch < 8; ++ch) xv[ch] = *reinterpret_cast<const float4*>(sX + kb * BXBLK + sw32b_offset(r, ch));
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<float4*>(sXlo + kb * BXBLK + sw32b_offset(r, ch)) =
+                        make_float4(tf32_lo(xv[ch].x), tf32_lo(xv[ch].y), tf32_lo(xv[ch].z), tf32_lo(xv[ch].w));
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(coef_ready);
+            VQB_BTL(5);
             // second pass: the tf32 remainders of C through the same two buffers, once pass 0 has been consumed
             mbar_wait(p1_done, ph);
+            VQB_BTL(6);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
@@ -292,33 +313,39 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(coef2_ready);
+            VQB_BTL(7);
 
             // ---- dx = g_q + 2 x rowsum(C) - 2 (C @ E)   |   C @ W -----------------------------------------
             mbar_wait(mma_done, ph);
             tcgen05_fence_after();
+            VQB_BTL(8);
             const float r2 = 2.f * rsum;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
                 float a[32], b[32];
                 tmem_ld_32x32(d1 + lane_addr + kb * 32, a);
                 tmem_ld_32x32(d1 + lane_addr + D + kb * 32, b);
+                float4 xv[8], gv[8];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {                   // all loads first: the stores below may alias
+                    xv[ch] = *reinterpret_cast<const float4*>(sX + kb * BXBLK + sw32b_offset(r, ch));
+                    gv[ch] = p.gq ? *reinterpret_cast<const float4*>(sG + kb * BXBLK + sw128_offset(r, ch))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    const uint32_t off = kb * BXBLK + sw32b_offset(r, ch);
                     float4 o;
                     o.x = a[4 * ch] + b[4 * ch]; o.y = a[4 * ch + 1] + b[4 * ch + 1];
                     o.z = a[4 * ch + 2] + b[4 * ch + 2]; o.w = a[4 * ch + 3] + b[4 * ch + 3];
                     if (l2) {
-                        const float4 xv = *reinterpret_cast<const float4*>(sX + off);
-                        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.gq) gv = *reinterpret_cast<const float4*>(sG + kb * BXBLK + sw128_offset(r, ch));
-                        o.x = fmaf(xv.x, r2, gv.x) - 2.f * o.x; o.y = fmaf(xv.y, r2, gv.y) - 2.f * o.y;
-                        o.z = fmaf(xv.z, r2, gv.z) - 2.f * o.z; o.w = fmaf(xv.w, r2, gv.w) - 2.f * o.w;
+                        o.x = fmaf(xv[ch].x, r2, gv[ch].x) - 2.f * o.x; o.y = fmaf(xv[ch].y, r2, gv[ch].y) - 2.f * o.y;
+                        o.z = fmaf(xv[ch].z, r2, gv[ch].z) - 2.f * o.z; o.w = fmaf(xv[ch].w, r2, gv[ch].w) - 2.f * o.w;
                     }
-                    *reinterpret_cast<float4*>(sXlo + off) = o;   // x_lo is dead once mma_done has fired
+                    *reinterpret_cast<float4*>(sXlo + kb * BXBLK + sw32b_offset(r, ch)) = o;   // x_lo is dead after mma_done
                 }
             }
             tcgen05_fence_before();
+            VQB_BTL(9);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             constexpr int D4 = D / 4;
             for (int i = r; i < rows * D4; i += 128) {
@@ -328,28 +355,45 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(tile_free);
+            VQB_BTL(10);
         }
-        // ---- once per CTA: flush the K x D sums held in TMEM and the column sums ------------------------------
-        if (real_tiles > 0) {
+        // ---- once per CTA: the K x D sums and the column sums held in TMEM -> this CTA's partial record -------
+        {
+            float* part = p.partial + (size_t)blockIdx.x * PARTIAL_FLOATS;
             tcgen05_fence_after();
             const float scale = l2 ? -2.f : 1.f;
-            const int d = r & (D - 1);                             // TMEM lanes D..2D-1 hold the x_lo part of the same d
+            const int d = r & (D - 1);
+            float* dst = part + (r >= D ? PART_KD : 0);            // TMEM lanes D..2D-1 hold the x_lo part of the same d
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
                 float a[32];
-                tmem_ld_32x32(d2 + lane_addr + hb * 32, a);
+                if (real_tiles > 0) {
+                    tmem_ld_32x32(d2 + lane_addr + hb * 32, a);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int k = hb * 32 + j;
-                    if (k < K) atomicAdd(p.dW + (size_t)k * D + d, scale * a[j]);
+                    for (int j = 0; j < 32; ++j) a[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[(hb * 32 + j) * D + d] = scale * a[j];
+            }
+            if (q4 == 0) {                                         // every lane of D3 holds the same column sums
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float a[32];
+                    if (real_tiles > 0) {
+                        tmem_ld_32x32(d3 + lane_addr + hb * 32, a);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) a[j] = 0.f;
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) part[3 * PART_KD + hb * 32 + j] = a[j];
+                    }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 64; ++k) {
-                const float v = warp_sum(cs[k]);
-                if (lane == 0 && k < K) atomicAdd(p.colsum + k, v);
-            }
         }
+        VQB_BTL(11);
     }
 
     tcgen05_fence_before();
@@ -357,11 +401,47 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (warp == 3) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// out[i] += sum over the CTAs' partial records, in a fixed order (deterministic).  grid.x covers the K*D elements
+// (+ one block for the column sums), blockDim = (64, 8): 8 slices of the CTA list per element, combined in smem.
+__global__ void __launch_bounds__(512)
+reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int K, int l2, float* __restrict__ dW,
+                       float* __restrict__ dG, float* __restrict__ colsum) {
+    __shared__ float red[8][64];
+    __shared__ float red2[8][64];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int n_kd = K * 64;
+    const bool cs_block = (int)blockIdx.x * 64 >= n_kd;            // last block: column sums
+    const int i = cs_block ? tx : blockIdx.x * 64 + tx;
+    float a = 0.f, b = 0.f;
+    for (int cta = ty; cta < n_cta; cta += 8) {
+        const float* rec = partial + (size_t)cta * PARTIAL_FLOATS;
+        if (cs_block) {
+            a += rec[3 * PART_KD + tx];
+        } else if (i < n_kd) {
+            a += rec[i] + rec[PART_KD + i];
+            b += rec[2 * PART_KD + i];
+        }
+    }
+    red[ty][tx] = a; red2[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sa += red[j][tx]; sb += red2[j][tx]; }
+        if (cs_block) {
+            if (tx < K) colsum[tx] += sa;
+        } else if (i < n_kd) {
+            if (l2) { dW[i] += sa + sb; } else { dW[i] += sa; if (dG) dG[i] += sb; }
+        }
+    }
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------
-void launch_build_operands(const float* w, const float* bias, int K, int D, float scale, float* hi, float* lo,
-                           float* emax, cudaStream_t s);
+unsigned long long* get_debug_timeline();
+void launch_build_operands(const float* w, const float* bias, int K, int Kpad, int D, float scale, float pad_bias,
+                           float* hi, float* lo, float* emax, cudaStream_t s);
 
 static size_t b_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t b_hi_bytes(int64_t K, int64_t D) { return b_align256((size_t)K * (D + 32) * 4); }
@@ -377,13 +457,14 @@ bool backward_tensor_supported(const vqb_bwd_args* a) {
 }
 
 int backward_tensor_workspace(const vqb_bwd_args* a, size_t* bytes) {
-    *bytes = backward_tensor_supported(a) ? b_hi_bytes(a->n_codes, a->dim) + b_lo_bytes(a->n_codes, a->dim) + 256 : 0;
+    *bytes = backward_tensor_supported(a) ? b_hi_bytes(a->n_codes, a->dim) + b_lo_bytes(a->n_codes, a->dim) + 256 +
+                                                 (size_t)sm_count() * PARTIAL_FLOATS * 4 : 0;
     return VQB_OK;
 }
 
 int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     const int64_t N = a->n_rows, K = a->n_codes, D = a->dim;
-    const size_t need = b_hi_bytes(K, D) + b_lo_bytes(K, D) + 256;
+    const size_t need = b_hi_bytes(K, D) + b_lo_bytes(K, D) + 256 + (size_t)sm_count() * PARTIAL_FLOATS * 4;
     if (!a->workspace || a->workspace_bytes < need) {
         set_error("vqb_backward: workspace too small (%zu < %zu bytes)", a->workspace_bytes, need);
         return VQB_ERR_WORKSPACE;
@@ -391,9 +472,7 @@ int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
     float* hi = reinterpret_cast<float*>(ws);
     float* lo = reinterpret_cast<float*>(ws + b_hi_bytes(K, D));
-    float* emax = reinterpret_cast<float*>(ws + b_hi_bytes(K, D) + b_lo_bytes(K, D));
-    VQB_CUDA(cudaMemsetAsync(emax, 0, 256, s));
-    launch_build_operands(a->score_w, nullptr, (int)K, (int)D, 1.f, hi, lo, emax, s);
+    launch_build_operands(a->score_w, nullptr, (int)K, (int)K, (int)D, 1.f, 0.f, hi, lo, nullptr, s);
     VQB_CHECK_LAUNCH("build_operands_kernel");
 
     CUtensorMap tx, tg, th, tl;
@@ -409,14 +488,20 @@ int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     p.N = (int)N; p.K = (int)K; p.n_real = (int)(a->n_real_rows > 0 ? a->n_real_rows : 0);
     p.num_tiles = (int)ceil_div(N, BBM);
     p.flags = a->flags;
+    p.dbg = get_debug_timeline();
+    p.partial = reinterpret_cast<float*>(ws + b_hi_bytes(K, D) + b_lo_bytes(K, D) + 256);
 
     constexpr int KB = 2;
-    const size_t smem = (size_t)3 * KB * BXBLK + 4 * BXBLK + 2 * KB * BEBLK + 64 * 64 * 4 + BBM * 4 + 256 + 1024;
+    const size_t smem = (size_t)3 * KB * BXBLK + 4 * BXBLK + 2 * KB * BEBLK + 64 * 64 * 4 + BXBLK + BBM * 4 + 256 + 1024;
     auto kern = vqb_bwd_tc_kernel<KB>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     kern<<<grid, BWD_THREADS, smem, s>>>(tx, tg, th, tl, p);
     VQB_CHECK_LAUNCH("vqb_bwd_tc_kernel");
+    const int n_blocks = (int)ceil_div(K * 64, 64) + 1;
+    reduce_partials_kernel<<<n_blocks, dim3(64, 8), 0, s>>>(p.partial, grid, (int)K, (a->flags & VQB_SCORE_L2) ? 1 : 0,
+                                                           a->d_score_w, p.dG, a->colsum);
+    VQB_CHECK_LAUNCH("reduce_partials_kernel");
     return VQB_OK;
 }
 

@@ -46,6 +46,7 @@ struct TcP {
     unsigned long long* hist;
     double* sqerr;
     unsigned int* stats;       // [0] rows re-ranked, [1] rows that needed the full exact scan
+    unsigned long long* dbg;   // optional timeline buffer (vqb_debug_set_timeline), NULL in production
     int N, K, D, num_tiles, num_chunks;
     unsigned flags;
 };
@@ -57,14 +58,21 @@ __device__ __forceinline__ float tf32_rn(float v) {
 }
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// hi[k] = [tf32_rn(scale * w_k) (D floats) | bias_k as three tf32-exact words | 0 x 29]   ([K][D+32])
-// lo[k] = scale * w_k - hi[k]                                                              ([K][D])
+// hi[k] = [tf32_rn(scale * w_k) (D floats) | bias_k as three tf32-exact words | 0 x 29]   ([Kpad][D+32])
+// lo[k] = scale * w_k - hi[k]                                                              ([Kpad][D])
 // emax  = max_k |w_k|
+// Rows K..Kpad-1 (padding up to a whole chunk) are zero with bias `pad_bias` (+1e30 for the L2 score, -1e30 for
+// LINEAR), so a padded code can never be the arg-min / receive probability mass: no masking in the epilogues.
 __global__ void __launch_bounds__(128)
 build_operands_kernel(const float* __restrict__ w, const float* __restrict__ bias, int K, int D, float scale,
-                      float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ emax) {
+                      float pad_bias, float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ emax) {
     const int k = blockIdx.x;
     float* hrow = hi + (size_t)k * (D + 32);
+    if (k >= K) {
+        for (int d = threadIdx.x; d < D + 32; d += blockDim.x) hrow[d] = d == D ? pad_bias : 0.f;
+        if (lo) for (int d = threadIdx.x; d < D; d += blockDim.x) lo[(size_t)k * D + d] = 0.f;
+        return;
+    }
     float sq = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         const float raw = w[(size_t)k * D + d];
@@ -87,13 +95,13 @@ build_operands_kernel(const float* __restrict__ w, const float* __restrict__ bia
     sq = warp_sum(sq);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0 && emax)
         atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(red[0] + red[1] + red[2] + red[3])));
 }
 
-void launch_build_operands(const float* w, const float* bias, int K, int D, float scale, float* hi, float* lo,
-                           float* emax, cudaStream_t s) {
-    build_operands_kernel<<<(unsigned)K, 128, 0, s>>>(w, bias, K, D, scale, hi, lo, emax);
+void launch_build_operands(const float* w, const float* bias, int K, int Kpad, int D, float scale, float pad_bias,
+                           float* hi, float* lo, float* emax, cudaStream_t s) {
+    build_operands_kernel<<<(unsigned)Kpad, 128, 0, s>>>(w, bias, K, D, scale, pad_bias, hi, lo, emax);
 }
 
 // exact score of code k for the row held (swizzled) in shared memory -- same expression and fmaf order as
@@ -117,10 +125,12 @@ __device__ __forceinline__ float exact_score(const uint8_t* sXt, int r, float xx
     return tau * (-dist);
 }
 
+#define VQB_TL(tag) do { if (p.dbg && et == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
+
 template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
-                  const __grid_constant__ CUtensorMap tm_lo, TcP p) {
+                  const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
     constexpr int PIECES = PASSES == 3 ? 2 * KB + 1 : KB + 1;     // per chunk: hi/lo per K-block + the bias block
     constexpr int TMEM_COLS = 2 * BN;
@@ -147,12 +157,14 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[120] = globaltimer_ns();
 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_hi);
         if (PASSES == 3) tma_prefetch_desc(&tm_lo);
+        tma_prefetch_desc(&tm_q);
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
@@ -162,6 +174,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int i = threadIdx.x; i < XBLK / 16; i += TC_THREADS)
         reinterpret_cast<float4*>(sAug)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[121] = globaltimer_ns();
     if (threadIdx.x < BM)
         *reinterpret_cast<float4*>(sAug + sw128_offset(threadIdx.x, 0)) = make_float4(1.f, 1.f, 1.f, 0.f);
     fence_proxy_async_smem();
@@ -169,6 +182,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[122] = globaltimer_ns();
     constexpr uint32_t IDESC = umma_idesc(2u, BM, BN);
 
     if (warp == 0) {
@@ -286,15 +300,19 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int et = (warp - 2) * 32 + lane;                      // 0..127 among the epilogue threads
         const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
         const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
-        const float emax = __ldg(p.emax);
+        const float emax = PCODE ? 0.f : __ldg(p.emax);
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         uint32_t x_it = 0, c_it = 0;
         float se_acc = 0.f;
+        int tl_n = 0;
+        VQB_TL(1);
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
             uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
             uint8_t* sXl = sXlo + (size_t)xs * KB * XBLK;
+            VQB_TL(2);
             mbar_wait(&x_full[xs], xph);
+            VQB_TL(3);
             const int row0 = tile * BM;
             const int rows = min(BM, p.N - row0);
             const bool valid = r < rows;
@@ -302,17 +320,22 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             float xx = 0.f;
 #pragma unroll 1
             for (int kb = 0; kb < KB; ++kb) {
+                float4 xv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)                         // all loads first: the stores below may alias
+                    xv[c] = *reinterpret_cast<const float4*>(sXt + kb * XBLK + sw128_offset(r, c));
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint32_t off = kb * XBLK + sw128_offset(r, c);
-                    const float4 xv = *reinterpret_cast<const float4*>(sXt + off);
-                    xx = fmaf(xv.x, xv.x, xx); xx = fmaf(xv.y, xv.y, xx);
-                    xx = fmaf(xv.z, xv.z, xx); xx = fmaf(xv.w, xv.w, xx);
-                    if (PASSES == 3) {
+                    xx = fmaf(xv[c].x, xv[c].x, xx); xx = fmaf(xv[c].y, xv[c].y, xx);
+                    xx = fmaf(xv[c].z, xv[c].z, xx); xx = fmaf(xv[c].w, xv[c].w, xx);
+                }
+                if (PASSES == 3) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
                         float4 lo;
-                        lo.x = xv.x - tf32_trunc(xv.x); lo.y = xv.y - tf32_trunc(xv.y);
-                        lo.z = xv.z - tf32_trunc(xv.z); lo.w = xv.w - tf32_trunc(xv.w);
-                        *reinterpret_cast<float4*>(sXl + off) = lo;
+                        lo.x = xv[c].x - tf32_trunc(xv[c].x); lo.y = xv[c].y - tf32_trunc(xv[c].y);
+                        lo.z = xv[c].z - tf32_trunc(xv[c].z); lo.w = xv[c].w - tf32_trunc(xv[c].w);
+                        *reinterpret_cast<float4*>(sXl + kb * XBLK + sw128_offset(r, c)) = lo;
                     }
                 }
             }
@@ -321,6 +344,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xlo_full[xs]);
             }
+            VQB_TL(4);
 
             int best = 0;
             if (PCODE) {
@@ -328,6 +352,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
                 mbar_wait(&t_full[buf], tph);
                 tcgen05_fence_after();
+                VQB_TL(5);
                 float v[64];
                 {
                     float t[32];
@@ -348,33 +373,43 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const float LOG2E = 1.4426950408889634f;
                 const float mul = linear ? LOG2E : -tau * LOG2E;
                 const float add = linear ? 0.f : xx;
-                float m = -INFINITY;
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int k = 0; k < 64; ++k) {
-                    float s2 = mul * (add + v[k]);
-                    if (k >= p.K) s2 = -INFINITY;
+                    const float s2 = mul * (add + v[k]);            // padded codes: acc = +-1e30 -> s2 = -huge
                     v[k] = s2;
-                    m = fmaxf(m, s2);
+                    m4[k & 3] = fmaxf(m4[k & 3], s2);
                 }
-                float sum = 0.f;
+                if (mul == 0.f) {                                   // temp <= 0: uniform over the K real codes only
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) if (k >= p.K) v[k] = -INFINITY;
+                }
+                const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                // four interleaved chains (k mod 4) for the sum and for the first-index arg-max of exp(score - max)
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                float bv4[4] = {-1.f, -1.f, -1.f, -1.f};
+                int bi4[4] = {0, 1, 2, 3};
 #pragma unroll
                 for (int k = 0; k < 64; ++k) {
                     float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m));     // k >= K: ex2(-inf) = 0
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m));     // padded codes: ex2(-huge) = 0
                     v[k] = e;
-                    sum += e;
+                    s4[k & 3] += e;
+                    if (e > bv4[k & 3]) { bv4[k & 3] = e; bi4[k & 3] = k; }
                 }
-                const float inv = 1.f / sum;
-                float bv = -1.f;
-                const int KP = p.K | 1;                             // odd row stride: conflict-free thread-per-row stores
+                // argmax over p_code = e * inv (monotone in e), first index on ties (:130)
+                float bv = bv4[0];
+                best = bi4[0];
 #pragma unroll
-                for (int k = 0; k < 64; ++k) {
-                    const float pk = v[k] * inv;                    // softmax (:127)
-                    if (k < p.K) {
-                        sP[r * KP + k] = pk;
-                        if (pk > bv) { bv = pk; best = k; }         // argmax over p_code, first max (:130)
-                    }
-                }
+                for (int j = 1; j < 4; ++j)
+                    if (bv4[j] > bv || (bv4[j] == bv && bi4[j] < best)) { bv = bv4[j]; best = bi4[j]; }
+                const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+                // staging row stride: K itself when K is odd (conflict-free and contiguous -> one bulk store per
+                // tile), K+1 when K is even (conflict-free; copied out by the threads)
+                float* prow = sP + r * (p.K | 1);
+#pragma unroll
+                for (int k = 0; k < 64; ++k)
+                    if (k < p.K) prow[k] = v[k] * inv;              // softmax (:127)
             } else {
                 // ---------------- running minimum + candidate list over the codebook chunks ----------------
                 // |approx - exact| <= eps for every code of this row (see header), so the exact arg-min lies
@@ -391,16 +426,11 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
                     mbar_wait(&t_full[buf], tph);
                     tcgen05_fence_after();
-                    const bool full_chunk = (chunk + 1) * BN <= p.K;
 #pragma unroll 1
                     for (int c = 0; c < BN / 32; ++c) {
                         float v[32];
                         tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
-                        if (!full_chunk) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (col0 + j >= p.K) v[j] = INFINITY;
-                        }
                         float bm = v[0];
 #pragma unroll
                         for (int j = 1; j < 32; ++j) bm = fminf(bm, v[j]);
@@ -465,30 +495,54 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 }
             }
 
+            VQB_TL(6);
             // ---- gather + straight-through, staged in place over the x tile ----------------------------------
             if (valid) {
                 const float* crow = p.gtab + (size_t)best * p.D;
                 const bool skip = (p.flags & VQB_SKIP) != 0;
+                // L2 score with the codebook resident in shared memory: e = -(hi + lo) / 2 exactly (hi + lo == -2 e)
+                constexpr bool SMEM_GATHER = RESIDENT && PASSES == 3;
+                const bool from_smem = SMEM_GATHER && !linear;
+                const bool want_se = p.sqerr != nullptr;
 #pragma unroll 1
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int hb = 0; hb < 2 * KB; ++hb) {               // half K-blocks: 4 chunks of 16 bytes
+                    const int kb = hb >> 1, c0 = (hb & 1) * 4;
+                    float4 xv[4], cv[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float4* xp = reinterpret_cast<float4*>(sXt + kb * XBLK + sw128_offset(r, c));
-                        const float4 xv = *xp;
-                        const float4 cv = ldg4(crow + kb * 32 + c * 4);
+                    for (int c = 0; c < 4; ++c)                     // all loads first: the stores below may alias
+                        xv[c] = *reinterpret_cast<const float4*>(sXt + kb * XBLK + sw128_offset(r, c0 + c));
+                    if (from_smem) {
+                        float4 h[4], l[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            h[c] = *reinterpret_cast<const float4*>(sB + (size_t)(2 * kb) * PIECE + sw128_offset(best, c0 + c));
+                            l[c] = *reinterpret_cast<const float4*>(sB + (size_t)(2 * kb + 1) * PIECE + sw128_offset(best, c0 + c));
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            cv[c] = make_float4(-0.5f * (h[c].x + l[c].x), -0.5f * (h[c].y + l[c].y),
+                                                -0.5f * (h[c].z + l[c].z), -0.5f * (h[c].w + l[c].w));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) cv[c] = ldg4(crow + kb * 32 + (c0 + c) * 4);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
                         float4 o;
                         if (linear) {
-                            o = cv;                                                         // (:194-197)
+                            o = cv[c];                                                      // (:194-197)
                         } else {
                             // new_latent = enc_embs + picked_code - enc_embs.detach()  (:145)
-                            o.x = __fsub_rn(__fadd_rn(xv.x, cv.x), xv.x); o.y = __fsub_rn(__fadd_rn(xv.y, cv.y), xv.y);
-                            o.z = __fsub_rn(__fadd_rn(xv.z, cv.z), xv.z); o.w = __fsub_rn(__fadd_rn(xv.w, cv.w), xv.w);
-                            if (skip) o = xv;                                               // (:142)
+                            o.x = __fsub_rn(__fadd_rn(xv[c].x, cv[c].x), xv[c].x); o.y = __fsub_rn(__fadd_rn(xv[c].y, cv[c].y), xv[c].y);
+                            o.z = __fsub_rn(__fadd_rn(xv[c].z, cv[c].z), xv[c].z); o.w = __fsub_rn(__fadd_rn(xv[c].w, cv[c].w), xv[c].w);
+                            if (skip) o = xv[c];                                            // (:142)
                         }
-                        const float d0 = xv.x - cv.x, d1 = xv.y - cv.y, d2 = xv.z - cv.z, d3 = xv.w - cv.w;
-                        se_acc = fmaf(d0, d0, se_acc); se_acc = fmaf(d1, d1, se_acc);
-                        se_acc = fmaf(d2, d2, se_acc); se_acc = fmaf(d3, d3, se_acc);
-                        *xp = o;
+                        if (want_se) {
+                            const float d0 = xv[c].x - cv[c].x, d1 = xv[c].y - cv[c].y, d2 = xv[c].z - cv[c].z, d3 = xv[c].w - cv[c].w;
+                            se_acc = fmaf(d0, d0, se_acc); se_acc = fmaf(d1, d1, se_acc);
+                            se_acc = fmaf(d2, d2, se_acc); se_acc = fmaf(d3, d3, se_acc);
+                        }
+                        *reinterpret_cast<float4*>(sXt + kb * XBLK + sw128_offset(r, c0 + c)) = o;
                     }
                 }
                 p.idx[row0 + r] = best;
@@ -498,26 +552,39 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const unsigned peers = __match_any_sync(0xffffffffu, valid ? best : -1);
                 if (valid && lane == (__ffs(peers) - 1)) atomicAdd(p.hist + best, (unsigned long long)__popc(peers));
             }
+            VQB_TL(7);
+            fence_proxy_async_smem();                               // this thread's tile / p_code writes -> async proxy
             asm volatile("bar.sync 1, 128;" ::: "memory");          // epilogue warps only
-            constexpr int D4 = KB * 8;
-            for (int i = et; i < rows * D4; i += 128) {
-                const int rr = i / D4, c = i % D4;
-                const float4 o = *reinterpret_cast<const float4*>(sXt + (c >> 3) * XBLK + sw128_offset(rr, c & 7));
-                stg4_stream(p.q + (size_t)(row0 + rr) * p.D + 4 * c, o);
+            if (et == 0) {
+                // new_latent tile: TMA store straight from the swizzled tile (rows beyond N are clipped by TMA)
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) tma_store_2d(&tm_q, sXt + kb * XBLK, kb * 32, row0);
+                if (PCODE && (p.K & 1)) {
+                    const uint32_t bytes = (uint32_t)(rows * p.K * 4) & ~15u;
+                    if (bytes) bulk_store_1d(p.pcode + (size_t)row0 * p.K, sP, bytes);
+                }
+                tma_store_commit();
             }
             if (PCODE) {
-                const int KP = p.K | 1;
                 float* dst = p.pcode + (size_t)row0 * p.K;
                 const int n = rows * p.K;
-                int rr = et / p.K, k = et - rr * p.K;               // running (row, code) of element i
-                const int step_r = 128 / p.K, step_k = 128 - step_r * p.K;
-                for (int i = et; i < n; i += 128) {
-                    __stcs(dst + i, sP[rr * KP + k]);
-                    rr += step_r; k += step_k;
-                    if (k >= p.K) { k -= p.K; ++rr; }
+                if (p.K & 1) {
+                    const int done = (int)(((uint32_t)(n * 4) & ~15u) >> 2);   // < 16 bytes of a ragged last tile
+                    if (et < n - done) dst[done + et] = sP[done + et];
+                } else {
+                    const int KP = p.K | 1;
+                    int rr = et / p.K, k = et - rr * p.K;           // running (row, code) of element i
+                    const int step_r = 128 / p.K, step_k = 128 - step_r * p.K;
+                    for (int i = et; i < n; i += 128) {
+                        __stcs(dst + i, sP[rr * KP + k]);
+                        rr += step_r; k += step_k;
+                        if (k >= p.K) { k -= p.K; ++rr; }
+                    }
                 }
             }
-            fence_proxy_async_smem();
+            VQB_TL(8);
+            if (et == 0) tma_store_wait_read();                     // shared memory may be overwritten from here on
+            VQB_TL(9);
             asm volatile("bar.sync 1, 128;" ::: "memory");          // sP / x tile fully drained before reuse
             if (lane == 0) mbar_arrive(&x_empty[xs]);               // the x slot may be refilled by TMA
             ++x_it;
@@ -526,12 +593,15 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             se_acc = warp_sum(se_acc);
             if (lane == 0) atomicAdd(p.sqerr, (double)se_acc);
         }
+        if (et == 0) tma_store_wait_all();
+        VQB_TL(10);
     }
 
     // ---- teardown ----------------------------------------------------------------------------------------
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[123] = globaltimer_ns();
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -567,9 +637,14 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     return VQB_OK;
 }
 
+static unsigned long long* g_timeline = nullptr;
+void set_debug_timeline(void* p) { g_timeline = reinterpret_cast<unsigned long long*>(p); }
+unsigned long long* get_debug_timeline() { return g_timeline; }
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t hi_bytes(int64_t K, int64_t D) { return align256((size_t)K * (D + 32) * 4); }
-static size_t lo_bytes(int64_t K, int64_t D) { return align256((size_t)K * D * 4); }
+static int64_t pad_codes(int64_t K, int64_t bn) { return (K + bn - 1) / bn * bn; }
+static size_t hi_bytes(int64_t K, int64_t D) { return align256((size_t)pad_codes(K, 128) * (D + 32) * 4); }
+static size_t lo_bytes(int64_t K, int64_t D) { return align256((size_t)pad_codes(K, 128) * D * 4); }
 
 // which kernel configuration serves this call (0 = none: use the exact SIMT path)
 enum TcMode { TC_NONE = 0, TC_PCODE, TC_SEARCH3, TC_SEARCH1 };
@@ -590,14 +665,15 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
 }
 
 template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
-static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const TcP& p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
+                     cudaStream_t s) {
     const size_t smem = (size_t)XS * KB * XBLK * (PASSES == 3 ? 2 : 1) + XBLK + (size_t)BS * BN * 128 +
                         (PCODE ? BM * 65 * 4 : 16 * BM * 8) + 1024 + 256;
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
     auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, TC_THREADS, smem, s>>>(tx, th, tl, p);
+    kern<<<grid, TC_THREADS, smem, s>>>(tx, th, tl, tq, p);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
 }
@@ -619,45 +695,47 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     uint8_t* tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
     float* emax = reinterpret_cast<float*>(tail);
     unsigned int* stats = a->search_stats ? a->search_stats : reinterpret_cast<unsigned int*>(tail + 16);
-    VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));
-    build_operands_kernel<<<(unsigned)K, 128, 0, s>>>(a->score_w, a->score_b, (int)K, (int)D, linear ? 1.f : -2.f,
-                                                      hi, mode == TC_SEARCH1 ? nullptr : lo, emax);
+    if (mode != TC_PCODE) VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));   // emax / stats are only used by the search epilogue
+    const int BN = mode == TC_PCODE ? 64 : 128;
+    const int64_t Kpad = pad_codes(K, BN);
+    launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, linear ? 1.f : -2.f, linear ? -1e30f : 1e30f,
+                          hi, mode == TC_SEARCH1 ? nullptr : lo, mode == TC_PCODE ? nullptr : emax, s);
     VQB_CHECK_LAUNCH("build_operands_kernel");
 
-    const int BN = mode == TC_PCODE ? 64 : 128;
-    CUtensorMap tx, th, tl;
+    CUtensorMap tx, th, tl, tq;
     int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM);
     if (rc) return rc;
-    if ((rc = make_tmap_2d_f32(&th, hi, (uint64_t)K, (uint64_t)(D + 32), (uint64_t)(D + 32), BN))) return rc;
-    if ((rc = make_tmap_2d_f32(&tl, lo, (uint64_t)K, (uint64_t)D, (uint64_t)D, BN))) return rc;
+    if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM))) return rc;
+    if ((rc = make_tmap_2d_f32(&th, hi, (uint64_t)Kpad, (uint64_t)(D + 32), (uint64_t)(D + 32), BN))) return rc;
+    if ((rc = make_tmap_2d_f32(&tl, lo, (uint64_t)Kpad, (uint64_t)D, (uint64_t)D, BN))) return rc;
 
     TcP p;
     p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.emax = emax;
     p.pcode = a->p_code; p.idx = (long long*)a->idx; p.q = a->new_latent;
-    p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum; p.stats = stats;
+    p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum; p.stats = stats; p.dbg = g_timeline;
     p.N = (int)N; p.K = (int)K; p.D = (int)D;
     p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
     p.flags = a->flags;
 
     //                      KB  BN  XS BS PASSES RESIDENT PCODE
     if (mode == TC_PCODE) {
-        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true>(tx, th, tl, p, s);
-        return launch_tc<2, 64, 2, 5, 3, true, true>(tx, th, tl, p, s);
+        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true>(tx, th, tl, tq, p, s);
+        return launch_tc<2, 64, 2, 5, 3, true, true>(tx, th, tl, tq, p, s);
     }
     if (mode == TC_SEARCH3) {
         if (K <= 128) {                                            // whole codebook resident in shared memory
-            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, p, s);
-            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, p, s);
+            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, tq, p, s);
+            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, tq, p, s);
         }
-        if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, p, s);
-        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, p, s);
-        return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, p, s);
+        if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s);
+        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s);
+        return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s);
     }
     switch (D) {
-        case 32:  return launch_tc<1, 128, 2, 4, 1, false, false>(tx, th, tl, p, s);
-        case 64:  return launch_tc<2, 128, 2, 4, 1, false, false>(tx, th, tl, p, s);
-        case 128: return launch_tc<4, 128, 1, 4, 1, false, false>(tx, th, tl, p, s);
-        default:  return launch_tc<8, 128, 1, 4, 1, false, false>(tx, th, tl, p, s);
+        case 32:  return launch_tc<1, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s);
+        case 64:  return launch_tc<2, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s);
+        case 128: return launch_tc<4, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s);
+        default:  return launch_tc<8, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s);
     }
 }
 

@@ -106,10 +106,13 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     N, D = x2d.shape
     K = score_w.shape[0]
     dev = x2d.device
-    d_w = torch.zeros(K, D, device=dev, dtype=torch.float32)
-    colsum = torch.zeros(K, device=dev, dtype=torch.float32)
-    d_gather = torch.zeros(K, D, device=dev, dtype=torch.float32) if separate_gather else None
-    d_temp = torch.zeros(1, device=dev, dtype=torch.float32) if flags & _lib.TEMP_GRAD else None
+    # one zero-filled buffer (one fill kernel) carved into the accumulation targets
+    n_g = K * D if separate_gather else 0
+    zeros = torch.zeros(K * D + n_g + K + 4, device=dev, dtype=torch.float32)
+    d_w = zeros[:K * D].view(K, D)
+    d_gather = zeros[K * D:K * D + n_g].view(K, D) if separate_gather else None
+    colsum = zeros[K * D + n_g:K * D + n_g + K]
+    d_temp = zeros[K * D + n_g + K:K * D + n_g + K + 1] if flags & _lib.TEMP_GRAD else None
     dx = torch.empty(N, D, device=dev, dtype=torch.float32) if want_dx_buffer else None
     a = _lib.BwdArgs()
     a.struct_size = ctypes.sizeof(_lib.BwdArgs)
