@@ -199,7 +199,16 @@ def _time_kernels(V, m, sets, iters=24):
     return statistics.mean(fwd_ms), statistics.mean(bwd_ms)
 
 
+def _log(rank, msg):
+    print("[bench rank %d %.1fs] %s" % (rank, time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(args, rank, world, local_rank):
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)      # a wedged collective must not eat the GPU budget
     import semi_tts_b200 as V
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (GPU arm) needs a B200; there is no CPU fallback -- use --impl reference for the CPU arm")
@@ -207,8 +216,10 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
     if dist_on:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        _log(rank, "process group up (world %d)" % world)
     torch.manual_seed(0)
     m = V.L2Embedding(K, False, **_codebook_kwargs()).to(dev)
     m.train()
@@ -233,6 +244,7 @@ def run_ours(args, rank, world, local_rank):
             step(s)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    _log(rank, "warm-up done, capturing graphs")
     graphs, use_graph = [], True
     try:
         pool = None
@@ -241,7 +253,8 @@ def run_ours(args, rank, world, local_rank):
                 p_.grad = None                  # as after optimizer.zero_grad(): backward assigns, it does not accumulate
             s[0].grad = None
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            # thread_local: the NCCL watchdog thread must not invalidate the capture
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 step(s)
             pool = g.pool()
             graphs.append(g)
@@ -249,8 +262,14 @@ def run_ours(args, rank, world, local_rank):
         use_graph = False
         graphs = []
         torch.cuda.synchronize()
-        if rank == 0:
-            print("bench: CUDA-graph capture failed (%s); timing eager launches" % str(e).splitlines()[0], file=sys.stderr)
+        _log(rank, "CUDA-graph capture failed (%s); timing eager launches" % str(e).splitlines()[0])
+    if dist_on:
+        # every rank must take the same path, or the collectives no longer match up
+        ok = torch.tensor([1 if use_graph else 0], device=dev)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            use_graph, graphs = False, []
+    _log(rank, "launch mode: %s" % ("cuda_graph" if use_graph else "eager"))
 
     def run_steps(n, first=0):
         for i in range(n):
@@ -265,6 +284,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     run_steps(max(args.warmup, 3))
+    _log(rank, "timed warm-up done")
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -281,6 +301,7 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_total = float(t.item())
     value = N_ROWS * world * args.steps / (ms_total * 1e-3)
+    _log(rank, "device-resident timing done: %.3f ms/step" % (ms_total / args.steps))
 
     # ---- e2e: public module API, HOST (pinned) inputs, H2D + D2H inside the timed region ---------------------
     host_sets = [_inputs(5000 + 1000 * rank + i, "cpu", pin=True) for i in range(4)]
@@ -318,6 +339,7 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    _log(rank, "e2e timing done")
     e2e_value = N_ROWS * world * e2e_steps / (e2e_ms * 1e-3)
     h2d = 4 * (B * S * D * 2 + B * S * K)
     d2h = 8 * B * S + 4 * (n_grad + K)
@@ -354,9 +376,16 @@ def run_ours(args, rank, world, local_rank):
                                  "sample": "%d full steps of the same workload on the host (oracle/torch_port.py)" % cpu_done},
                 "clocks": clocks}
         print(json.dumps(line))
+    faulthandler.cancel_dump_traceback_later()
+    sys.stdout.flush()
     if dist_on:
+        _log(rank, "final barrier")
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        # CUDA graphs that captured NCCL work keep the communicator referenced; tearing it down from Python has been
+        # seen to wedge, so leave the process without running destructors (all results are already flushed)
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -369,10 +398,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL prints its version banner) must not pollute stdout: the contract is ONE JSON line there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args, rank)
+        sys.stdout.flush()
         return
     run_ours(args, rank, world, local_rank)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -31,33 +31,53 @@ def unpack_into(flat, tensors):
         off += n
 
 
+def _flat_view(grads):
+    """If the gradients are consecutive views of one storage (as the backward of this package produces them),
+    return that span as a single 1-D tensor; otherwise None."""
+    if not grads:
+        return None
+    first = grads[0]
+    try:
+        base_ptr = first.untyped_storage().data_ptr()
+    except Exception:                                   # noqa: BLE001
+        return None
+    off = first.storage_offset()
+    for g in grads:
+        if not g.is_contiguous() or g.dtype != first.dtype or g.untyped_storage().data_ptr() != base_ptr \
+                or g.storage_offset() != off:
+            return None
+        off += g.numel()
+    n = off - first.storage_offset()
+    return torch.as_strided(first, (n,), (1,), first.storage_offset())
+
+
 def allreduce_codebook_grads(module, group=None, average=False, include_usage=True):
-    """Sum (or average) the quantizer's parameter gradients and its usage histogram across ranks with a
-    single all-reduce and no host synchronisation (CUDA-graph capturable).  The int64 histogram rides
-    along as two fp32 words per code (count >> 12 and count & 0xFFF), each exactly representable and
-    exactly summable for counts < 2^36 and world <= 4096."""
+    """Sum (or average) the quantizer's parameter gradients and its usage histogram across ranks: the only
+    exchange of the data-parallel path.  No host synchronisation (CUDA-graph capturable).
+    Gradients produced by this package's backward are views of one flat buffer and are reduced in place by ONE
+    all-reduce; the int64 histogram is reduced by a second, 8*K-byte one.  Gradients from elsewhere (e.g. after
+    accumulation into pre-existing .grad tensors) are packed into a temporary buffer first."""
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = dist.get_world_size(group)
     if world == 1:
         return
     grads = [p.grad for p in module.parameters() if p.requires_grad and p.grad is not None]
+    if grads:
+        flat = _flat_view(grads)
+        if flat is not None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat /= world
+        else:
+            packed = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            off = 0
+            for g in grads:
+                n = g.numel()
+                chunk = packed[off:off + n].view_as(g)
+                g.copy_(chunk / world if average else chunk)
+                off += n
     usage = getattr(module, "usage", None)
-    counts = usage.counts if (include_usage and usage is not None and usage.counts is not None) else None
-    parts = [g.reshape(-1) for g in grads]
-    if counts is not None:
-        parts += [(counts >> 12).to(torch.float32), (counts & 0xFFF).to(torch.float32)]
-    if not parts:
-        return
-    flat = torch.cat(parts)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        chunk = flat[off:off + n].view_as(g)
-        g.copy_(chunk / world if average else chunk)
-        off += n
-    if counts is not None:
-        k = counts.numel()
-        hi, lo = flat[off:off + k], flat[off + k:off + 2 * k]
-        counts.copy_((hi.to(torch.int64) << 12) + lo.to(torch.int64))
+    if include_usage and usage is not None and usage.counts is not None:
+        dist.all_reduce(usage.counts, op=dist.ReduceOp.SUM, group=group)

@@ -63,9 +63,13 @@ def _table_backward(dtable, table, colsum, phn_attr, Da):
     A = phn_attr.shape[1] if phn_attr is not None else 0
     if phn_attr is None:
         Da = 0
-    d_learn = torch.empty(K, D - Da, device=dtable.device, dtype=torch.float32)
-    d_w = torch.empty(Da, A, device=dtable.device, dtype=torch.float32) if Da else None
-    d_b = torch.empty(Da, device=dtable.device, dtype=torch.float32) if Da else None
+    # the three parameter gradients are views of ONE flat buffer, so the data-parallel layer can all-reduce them
+    # in place with a single collective and no pack / unpack kernels (dist.allreduce_codebook_grads)
+    n_l, n_w = K * (D - Da), Da * A
+    flat = torch.empty(n_l + n_w + Da, device=dtable.device, dtype=torch.float32)
+    d_learn = flat[:n_l].view(K, D - Da)
+    d_w = flat[n_l:n_l + n_w].view(Da, A) if Da else None
+    d_b = flat[n_l + n_w:] if Da else None
     with torch.cuda.device(dtable.device):
         _lib.check(lib.vqb_table_backward(ptr(dtable), ptr(table), ptr(colsum), ptr(phn_attr), K, D, A, Da,
                                           ptr(d_learn), ptr(d_w), ptr(d_b), _stream(dtable)))

