@@ -66,10 +66,15 @@ VQB_API int vqb_device_count(void);
  *   enorm[K]   = sum_d table[k,d]^2                      (the |e|^2 term of src/embed.py:211)
  * phn_attr / proj_w / proj_b may be NULL (n_attr = dim_attr = 0): table = learnable.
  * table_bf16 (optional, may be NULL): bf16 copy [K, D] for the tensor-core search.
+ * operand_cache (optional, may be NULL): vqb_operand_cache_bytes() bytes that receive, in the same launch, the
+ *   tf32 hi/lo operand copies of the table that the tensor-core forward (L2 score) and backward consume; pass
+ *   the buffer on in vqb_fwd_args.operand_cache / vqb_bwd_args.operand_cache to skip their own operand pass.
  * ------------------------------------------------------------------------------------------- */
+VQB_API size_t vqb_operand_cache_bytes(int64_t n_codes, int64_t dim);
 VQB_API int vqb_assemble_table(const float* learnable, const float* phn_attr, const float* proj_w,
                        const float* proj_b, int64_t n_codes, int64_t dim, int64_t n_attr,
-                       int64_t dim_attr, float* table, float* enorm, void* table_bf16, void* stream);
+                       int64_t dim_attr, float* table, float* enorm, void* table_bf16,
+                       void* operand_cache, void* stream);
 
 /* Backward of the assembly (autograd of src/embed.py:109-112):
  *   dtable[k,:] += 2 * table[k,:] * colsum[k]     if colsum != NULL (the |e|^2 term of the L2 route)
@@ -102,6 +107,7 @@ typedef struct vqb_fwd_args {
     double*  sq_err_sum;         /* [1]     += sum (x - E[idx])^2 (numerator of the loss extensions), or NULL */
     uint32_t* search_stats;      /* [2]     tensor-core fused mode only, or NULL: += rows re-ranked in exact fp32,
                                             += rows that needed the full exact scan                      */
+    const void* operand_cache;   /* from vqb_assemble_table (L2 score only), or NULL                    */
     void*    workspace;          /* vqb_forward_workspace() bytes, or NULL if that is 0                 */
     size_t   workspace_bytes;
 } vqb_fwd_args;
@@ -140,6 +146,7 @@ typedef struct vqb_bwd_args {
     float* colsum;               /* [K]   += */
     float* d_gather;             /* [K,D] += (LINEAR only; L2 accumulates the scatter into d_score_w) */
     float* d_temp;               /* [1]   += (only with VQB_TEMP_GRAD) */
+    const void* operand_cache;   /* from vqb_assemble_table (L2 score only), or NULL */
     void*  workspace;
     size_t workspace_bytes;
 } vqb_bwd_args;

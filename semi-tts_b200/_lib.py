@@ -24,7 +24,7 @@ class FwdArgs(ctypes.Structure):
                 ("n_rows", ctypes.c_int64), ("dim", ctypes.c_int64), ("n_codes", ctypes.c_int64),
                 ("x", _p), ("score_w", _p), ("score_b", _p), ("score_w_bf16", _p), ("gather_table", _p),
                 ("temp", _p), ("p_code", _p), ("idx", _p), ("new_latent", _p), ("hist", _p),
-                ("sq_err_sum", _p), ("search_stats", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
+                ("sq_err_sum", _p), ("search_stats", _p), ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
 
 
 class BwdArgs(ctypes.Structure):
@@ -34,10 +34,10 @@ class BwdArgs(ctypes.Structure):
                 ("x", _p), ("score_w", _p), ("score_b", _p), ("gather_table", _p), ("temp", _p),
                 ("p_code", _p), ("idx", _p), ("g_p", _p), ("g_q", _p),
                 ("dx", _p), ("d_score_w", _p), ("colsum", _p), ("d_gather", _p), ("d_temp", _p),
-                ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
+                ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
 
 
-EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_assemble_table",
+EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
            "vqb_backward", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward"]
 
@@ -62,7 +62,8 @@ def load():
         lib.vqb_last_error.restype = ctypes.c_char_p
         lib.vqb_device_count.restype = ctypes.c_int
         i64, sz = ctypes.c_int64, ctypes.c_size_t
-        lib.vqb_assemble_table.argtypes = [_p, _p, _p, _p, i64, i64, i64, i64, _p, _p, _p, _p]
+        lib.vqb_assemble_table.argtypes = [_p, _p, _p, _p, i64, i64, i64, i64, _p, _p, _p, _p, _p]
+        lib.vqb_operand_cache_bytes.argtypes = [i64, i64]
         lib.vqb_table_backward.argtypes = [_p, _p, _p, _p, i64, i64, i64, i64, _p, _p, _p, _p]
         lib.vqb_forward_workspace.argtypes = [ctypes.POINTER(FwdArgs), ctypes.POINTER(sz)]
         lib.vqb_forward.argtypes = [ctypes.POINTER(FwdArgs), _p]
@@ -76,6 +77,7 @@ def load():
             if name not in ("vqb_last_error",):
                 fn.restype = ctypes.c_int if name != "vqb_last_error" else ctypes.c_char_p
         lib.vqb_last_error.restype = ctypes.c_char_p
+        lib.vqb_operand_cache_bytes.restype = ctypes.c_size_t
         if lib.vqb_abi_version() != ABI_VERSION:
             raise RuntimeError("semi-tts_b200: libvqb200.so ABI %d != expected %d -- rebuild"
                                % (lib.vqb_abi_version(), ABI_VERSION))

@@ -69,7 +69,7 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     static_assert(KB == 2, "instantiated for D = 64");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
     uint8_t* sX = smem;                              // [KB][16 KB] x tile            (GEMM 2: A groups 0..KB-1)
     uint8_t* sXlo = sX + TILE;                       // [KB][16 KB] x_lo, later dx    (GEMM 2: A groups KB..2KB-1)
     uint8_t* sG = sXlo + TILE;                       // [KB][16 KB] g_q tile
@@ -402,32 +402,36 @@ vqb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 }
 
 // out[i] += sum over the CTAs' partial records, in a fixed order (deterministic).  grid.x covers the K*D elements
-// (+ one block for the column sums), blockDim = (64, 8): 8 slices of the CTA list per element, combined in smem.
-__global__ void __launch_bounds__(512)
+// (+ one block for the column sums), blockDim = (64, 16): 16 slices of the CTA list per element (independent
+// accumulators, loads unrolled for memory-level parallelism), combined through shared memory.
+__global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int K, int l2, float* __restrict__ dW,
                        float* __restrict__ dG, float* __restrict__ colsum) {
-    __shared__ float red[8][64];
-    __shared__ float red2[8][64];
+    __shared__ float red[16][64];
+    __shared__ float red2[16][64];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int n_kd = K * 64;
     const bool cs_block = (int)blockIdx.x * 64 >= n_kd;            // last block: column sums
     const int i = cs_block ? tx : blockIdx.x * 64 + tx;
-    float a = 0.f, b = 0.f;
-    for (int cta = ty; cta < n_cta; cta += 8) {
-        const float* rec = partial + (size_t)cta * PARTIAL_FLOATS;
-        if (cs_block) {
-            a += rec[3 * PART_KD + tx];
-        } else if (i < n_kd) {
-            a += rec[i] + rec[PART_KD + i];
-            b += rec[2 * PART_KD + i];
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f;
+    if (cs_block) {
+#pragma unroll 4
+        for (int cta = ty; cta < n_cta; cta += 16) a0 += __ldg(partial + (size_t)cta * PARTIAL_FLOATS + 3 * PART_KD + tx);
+    } else if (i < n_kd) {
+#pragma unroll 4
+        for (int cta = ty; cta < n_cta; cta += 16) {
+            const float* rec = partial + (size_t)cta * PARTIAL_FLOATS + i;
+            a0 += __ldg(rec);
+            a1 += __ldg(rec + PART_KD);
+            b0 += __ldg(rec + 2 * PART_KD);
         }
     }
-    red[ty][tx] = a; red2[ty][tx] = b;
+    red[ty][tx] = a0 + a1; red2[ty][tx] = b0;
     __syncthreads();
     if (ty == 0) {
         float sa = 0.f, sb = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sa += red[j][tx]; sb += red2[j][tx]; }
+        for (int j = 0; j < 16; ++j) { sa += red[j][tx]; sb += red2[j][tx]; }
         if (cs_block) {
             if (tx < K) colsum[tx] += sa;
         } else if (i < n_kd) {
@@ -444,8 +448,8 @@ void launch_build_operands(const float* w, const float* bias, int K, int Kpad, i
                            float* hi, float* lo, float* emax, cudaStream_t s);
 
 static size_t b_align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t b_hi_bytes(int64_t K, int64_t D) { return b_align256((size_t)K * (D + 32) * 4); }
-static size_t b_lo_bytes(int64_t K, int64_t D) { return b_align256((size_t)K * D * 4); }
+static size_t b_hi_bytes(int64_t K, int64_t D) { return cache_hi_bytes(K, D); }
+static size_t b_lo_bytes(int64_t K, int64_t D) { return cache_lo_bytes(K, D); }
 
 bool backward_tensor_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
@@ -457,23 +461,34 @@ bool backward_tensor_supported(const vqb_bwd_args* a) {
 }
 
 int backward_tensor_workspace(const vqb_bwd_args* a, size_t* bytes) {
-    *bytes = backward_tensor_supported(a) ? b_hi_bytes(a->n_codes, a->dim) + b_lo_bytes(a->n_codes, a->dim) + 256 +
+    const bool cached = a->operand_cache && (a->flags & VQB_SCORE_L2);
+    *bytes = backward_tensor_supported(a) ? (cached ? 0 : b_hi_bytes(a->n_codes, a->dim) + b_lo_bytes(a->n_codes, a->dim)) + 256 +
                                                  (size_t)sm_count() * PARTIAL_FLOATS * 4 : 0;
     return VQB_OK;
 }
 
 int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     const int64_t N = a->n_rows, K = a->n_codes, D = a->dim;
-    const size_t need = b_hi_bytes(K, D) + b_lo_bytes(K, D) + 256 + (size_t)sm_count() * PARTIAL_FLOATS * 4;
+    const bool cached = a->operand_cache && (a->flags & VQB_SCORE_L2);
+    const size_t op_bytes = cached ? 0 : b_hi_bytes(K, D) + b_lo_bytes(K, D);
+    const size_t need = op_bytes + 256 + (size_t)sm_count() * PARTIAL_FLOATS * 4;
     if (!a->workspace || a->workspace_bytes < need) {
         set_error("vqb_backward: workspace too small (%zu < %zu bytes)", a->workspace_bytes, need);
         return VQB_ERR_WORKSPACE;
     }
     uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
-    float* hi = reinterpret_cast<float*>(ws);
-    float* lo = reinterpret_cast<float*>(ws + b_hi_bytes(K, D));
-    launch_build_operands(a->score_w, nullptr, (int)K, (int)K, (int)D, 1.f, 0.f, hi, lo, nullptr, s);
-    VQB_CHECK_LAUNCH("build_operands_kernel");
+    float* hi;
+    float* lo;
+    if (cached) {     // [fwd_hi | fwd_lo | bwd_hi | bwd_lo]
+        uint8_t* oc = reinterpret_cast<uint8_t*>(const_cast<void*>(a->operand_cache)) + b_hi_bytes(K, D) + b_lo_bytes(K, D);
+        hi = reinterpret_cast<float*>(oc);
+        lo = reinterpret_cast<float*>(oc + b_hi_bytes(K, D));
+    } else {
+        hi = reinterpret_cast<float*>(ws);
+        lo = reinterpret_cast<float*>(ws + b_hi_bytes(K, D));
+        launch_build_operands(a->score_w, nullptr, (int)K, (int)K, (int)D, 1.f, 0.f, hi, lo, nullptr, s);
+        VQB_CHECK_LAUNCH("build_operands_kernel");
+    }
 
     CUtensorMap tx, tg, th, tl;
     int rc;
@@ -489,7 +504,7 @@ int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     p.num_tiles = (int)ceil_div(N, BBM);
     p.flags = a->flags;
     p.dbg = get_debug_timeline();
-    p.partial = reinterpret_cast<float*>(ws + b_hi_bytes(K, D) + b_lo_bytes(K, D) + 256);
+    p.partial = reinterpret_cast<float*>(ws + op_bytes + 256);
 
     constexpr int KB = 2;
     const size_t smem = (size_t)3 * KB * BXBLK + 4 * BXBLK + 2 * KB * BEBLK + 64 * 64 * 4 + BXBLK + BBM * 4 + 256 + 1024;
@@ -499,7 +514,7 @@ int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     kern<<<grid, BWD_THREADS, smem, s>>>(tx, tg, th, tl, p);
     VQB_CHECK_LAUNCH("vqb_bwd_tc_kernel");
     const int n_blocks = (int)ceil_div(K * 64, 64) + 1;
-    reduce_partials_kernel<<<n_blocks, dim3(64, 8), 0, s>>>(p.partial, grid, (int)K, (a->flags & VQB_SCORE_L2) ? 1 : 0,
+    reduce_partials_kernel<<<n_blocks, dim3(64, 16), 0, s>>>(p.partial, grid, (int)K, (a->flags & VQB_SCORE_L2) ? 1 : 0,
                                                            a->d_score_w, p.dG, a->colsum);
     VQB_CHECK_LAUNCH("reduce_partials_kernel");
     return VQB_OK;

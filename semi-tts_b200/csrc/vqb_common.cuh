@@ -53,6 +53,18 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ float tf32_rn(float v) {      // round to tf32 (10-bit mantissa), ties away
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// operand cache layout (vqb_operand_cache_bytes): fwd_hi [Kp][D+32] | fwd_lo [Kp][D] | bwd_hi [Kp][D+32] | bwd_lo [Kp][D]
+static inline int64_t cache_rows(int64_t K) { return (K + 127) / 128 * 128; }
+static inline size_t cache_hi_bytes(int64_t K, int64_t D) { return ((size_t)cache_rows(K) * (D + 32) * 4 + 255) & ~(size_t)255; }
+static inline size_t cache_lo_bytes(int64_t K, int64_t D) { return ((size_t)cache_rows(K) * D * 4 + 255) & ~(size_t)255; }
+
 // entry points implemented in the individual .cu files (host side, return VQB_* codes)
 int launch_forward_simt(const vqb_fwd_args* a, cudaStream_t s);
 int launch_backward_simt(const vqb_bwd_args* a, cudaStream_t s);

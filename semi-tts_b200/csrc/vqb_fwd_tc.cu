@@ -32,7 +32,6 @@ using namespace tc;
 
 constexpr int BM = 128;                 // rows per tile (UMMA M)
 constexpr int XBLK = BM * 128;          // one x K-block: [128 rows][32 fp32] = 16 KB
-constexpr int TC_THREADS = 192;
 
 struct TcP {
     const float* table;        // [K][D] fp32 score table (exact re-rank)
@@ -51,12 +50,6 @@ struct TcP {
     unsigned flags;
 };
 
-__device__ __forceinline__ float tf32_rn(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // hi[k] = [tf32_rn(scale * w_k) (D floats) | bias_k as three tf32-exact words | 0 x 29]   ([Kpad][D+32])
 // lo[k] = scale * w_k - hi[k]                                                              ([Kpad][D])
@@ -125,10 +118,10 @@ __device__ __forceinline__ float exact_score(const uint8_t* sXt, int r, float xx
     return tau * (-dist);
 }
 
-#define VQB_TL(tag) do { if (p.dbg && et == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
+#define VQB_TL(tag) do { if (p.dbg && et == 0 && wg == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG>
+__global__ void __launch_bounds__(64 + 128 * NWG, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
@@ -137,16 +130,23 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     constexpr int CAP = 16;                                       // per-row candidate list capacity (SEARCH)
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
     static_assert(!PCODE || BN == 64, "the p_code epilogue keeps one 64-column accumulator in registers");
+    // NWG epilogue warpgroups work on alternate tiles (tile t -> group t % NWG, x slot t % XS, TMEM buffer t & 1,
+    // its own p_code staging); with NWG = 2 the x_lo tile is single-buffered (XLS = 1) and handed back by the
+    // MMA warp through xlo_free as soon as the third MMA pass of a tile has been issued.
+    static_assert(NWG == 1 || (PCODE && XS == 2 && RESIDENT && PASSES == 3), "two warpgroups: p_code mode only");
+    constexpr int NTHREADS = 64 + 128 * NWG;
+    constexpr int XLS = NWG == 2 ? 1 : XS;                        // x_lo slots
+    constexpr int SP_FLOATS = BM * 65;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
     uint8_t* sX = smem;                                                        // [XS][KB][16 KB]
     uint8_t* sXlo = sX + (size_t)XS * KB * XBLK;                               // [XS][KB][16 KB]  (PASSES == 3)
-    uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0);         // [16 KB] A block [1,1,1,0,...]
+    uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0);        // [16 KB] A block [1,1,1,0,...]
     uint8_t* sB = sAug + XBLK;                                                 // [BS][PIECE]
     float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65] p_code staging (PCODE)
     uint2* sCand = reinterpret_cast<uint2*>(sP);                               // [CAP][128] (value, code)  (SEARCH)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? BM * 65 * 4 : CAP * BM * 8));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * SP_FLOATS * 4 : CAP * BM * 8));
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
     uint64_t* xlo_full = x_empty + XS;
@@ -154,7 +154,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint64_t* b_empty = b_full + BS;
     uint64_t* t_full = b_empty + BS;
     uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* xlo_free = t_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xlo_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[120] = globaltimer_ns();
@@ -168,10 +169,11 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        mbar_init(xlo_free, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
-    for (int i = threadIdx.x; i < XBLK / 16; i += TC_THREADS)
+    for (int i = threadIdx.x; i < XBLK / 16; i += NTHREADS)
         reinterpret_cast<float4*>(sAug)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[121] = globaltimer_ns();
@@ -220,9 +222,10 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
                 const uint8_t* xt = sX + (size_t)xs * KB * XBLK;
-                const uint8_t* xlt = sXlo + (size_t)xs * KB * XBLK;
+                const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
+                const uint8_t* xlt = sXlo + (size_t)xls * KB * XBLK;
                 mbar_wait(&x_full[xs], xph);
-                if (PASSES == 3 && !RESIDENT) mbar_wait(&xlo_full[xs], xph);
+                if (PASSES == 3 && !RESIDENT) mbar_wait(&xlo_full[xls], xlph);
                 tcgen05_fence_after();
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
                     const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
@@ -252,7 +255,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, true);
                             }
-                            mbar_wait(&xlo_full[xs], xph);
+                            mbar_wait(&xlo_full[xls], xlph);
                             tcgen05_fence_after();
 #pragma unroll
                             for (int kb = 0; kb < KB; ++kb) {
@@ -261,6 +264,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, true);
                             }
+                            if (NWG == 2) umma_commit(xlo_free);    // the single x_lo tile may be rewritten
                         }
                     } else {
                         for (int j = 0; j < PIECES; ++j) {
@@ -297,19 +301,23 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // =============================== epilogue (thread = row) ==========================================
         const int q4 = warp & 3;                                    // TMEM lane quadrant this warp may read
         const int r = q4 * 32 + lane;                               // row within the tile == TMEM lane
-        const int et = (warp - 2) * 32 + lane;                      // 0..127 among the epilogue threads
+        const int wg = (warp - 2) >> 2;                             // epilogue warpgroup (0 .. NWG-1)
+        const int et = ((warp - 2) & 3) * 32 + lane;                // 0..127 within the warpgroup
+        const uint32_t bar_id = 1 + wg;                             // named barrier of this warpgroup
+        float* sPg = sP + (PCODE ? wg * SP_FLOATS : 0);
         const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
         const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
         const float emax = PCODE ? 0.f : __ldg(p.emax);
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-        uint32_t x_it = 0, c_it = 0;
+        uint32_t x_it = wg, c_it = wg;                              // tile counter of this warpgroup (c_it: chunks)
         float se_acc = 0.f;
         int tl_n = 0;
         VQB_TL(1);
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x + wg * gridDim.x; tile < p.num_tiles; tile += NWG * gridDim.x) {
             const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
+            const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
             uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
-            uint8_t* sXl = sXlo + (size_t)xs * KB * XBLK;
+            uint8_t* sXl = sXlo + (size_t)xls * KB * XBLK;
             VQB_TL(2);
             mbar_wait(&x_full[xs], xph);
             VQB_TL(3);
@@ -317,6 +325,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int rows = min(BM, p.N - row0);
             const bool valid = r < rows;
             // |x|^2 in the exact kernel's fmaf order; x_lo = x - trunc_tf32(x) for the third MMA pass
+            if (NWG == 2) mbar_wait(xlo_free, xlph ^ 1);            // previous tile's third MMA pass has read x_lo
             float xx = 0.f;
 #pragma unroll 1
             for (int kb = 0; kb < KB; ++kb) {
@@ -342,7 +351,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (PASSES == 3) {
                 fence_proxy_async_smem();                           // generic writes -> tcgen05.mma operand reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&xlo_full[xs]);
+                if (lane == 0) mbar_arrive(&xlo_full[xls]);
             }
             VQB_TL(4);
 
@@ -366,7 +375,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);          // TMEM buffer free: next tile's MMA may start
-                ++c_it;
+                c_it += NWG;
                 // scores in the log2 domain: s2 = log2(e) * score, so that exp(score - max) = ex2(s2 - max2)
                 //   L2:     score = relu(temp) * -(|x|^2 + acc),  acc = |e|^2 - 2 x.e     (:115, :208-213)
                 //   LINEAR: score = acc = x.w + b                                          (:190)
@@ -406,7 +415,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
                 // staging row stride: K itself when K is odd (conflict-free and contiguous -> one bulk store per
                 // tile), K+1 when K is even (conflict-free; copied out by the threads)
-                float* prow = sP + r * (p.K | 1);
+                float* prow = sPg + r * (p.K | 1);
 #pragma unroll
                 for (int k = 0; k < 64; ++k)
                     if (k < p.K) prow[k] = v[k] * inv;              // softmax (:127)
@@ -496,57 +505,66 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
 
             VQB_TL(6);
-            // ---- gather + straight-through, staged in place over the x tile ----------------------------------
-            if (valid) {
-                const float* crow = p.gtab + (size_t)best * p.D;
+            // ---- gather + straight-through, in place over the x tile -------------------------------------------
+            // Coalesced mapping: 16 consecutive threads handle the 16 sixteen-byte chunks of one row, so the
+            // codeword reads (all chunks of ONE code row) and the tile accesses are free of bank conflicts.
+            int* sIdxG = reinterpret_cast<int*>(tmem_slot + 4) + wg * BM;
+            sIdxG[r] = valid ? best : -1;
+            if (valid) p.idx[row0 + r] = best;
+            VQB_TL(11);
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            VQB_TL(12);
+            {
                 const bool skip = (p.flags & VQB_SKIP) != 0;
                 // L2 score with the codebook resident in shared memory: e = -(hi + lo) / 2 exactly (hi + lo == -2 e)
                 constexpr bool SMEM_GATHER = RESIDENT && PASSES == 3;
                 const bool from_smem = SMEM_GATHER && !linear;
                 const bool want_se = p.sqerr != nullptr;
+                constexpr int D4 = KB * 8;                          // 16-byte chunks per row
+                constexpr int ITER = BM * D4 / 128;                 // chunks per thread
 #pragma unroll 1
-                for (int hb = 0; hb < 2 * KB; ++hb) {               // half K-blocks: 4 chunks of 16 bytes
-                    const int kb = hb >> 1, c0 = (hb & 1) * 4;
+                for (int j0 = 0; j0 < ITER; j0 += 4) {
                     float4 xv[4], cv[4];
+                    int rr[4], cc[4], code[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)                     // all loads first: the stores below may alias
-                        xv[c] = *reinterpret_cast<const float4*>(sXt + kb * XBLK + sw128_offset(r, c0 + c));
-                    if (from_smem) {
-                        float4 h[4], l[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            h[c] = *reinterpret_cast<const float4*>(sB + (size_t)(2 * kb) * PIECE + sw128_offset(best, c0 + c));
-                            l[c] = *reinterpret_cast<const float4*>(sB + (size_t)(2 * kb + 1) * PIECE + sw128_offset(best, c0 + c));
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            cv[c] = make_float4(-0.5f * (h[c].x + l[c].x), -0.5f * (h[c].y + l[c].y),
-                                                -0.5f * (h[c].z + l[c].z), -0.5f * (h[c].w + l[c].w));
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) cv[c] = ldg4(crow + kb * 32 + (c0 + c) * 4);
+                    for (int u = 0; u < 4; ++u) {                   // all loads first: the stores below may alias
+                        const int i = et + 128 * (j0 + u);
+                        rr[u] = i / D4; cc[u] = i % D4;
+                        code[u] = sIdxG[rr[u]];
+                        xv[u] = *reinterpret_cast<const float4*>(sXt + (cc[u] >> 3) * XBLK + sw128_offset(rr[u], cc[u] & 7));
                     }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = code[u] < 0 ? 0 : code[u];
+                        if (from_smem) {
+                            const float4 h = *reinterpret_cast<const float4*>(sB + (size_t)(2 * (cc[u] >> 3)) * PIECE + sw128_offset(k, cc[u] & 7));
+                            const float4 l = *reinterpret_cast<const float4*>(sB + (size_t)(2 * (cc[u] >> 3) + 1) * PIECE + sw128_offset(k, cc[u] & 7));
+                            cv[u] = make_float4(-0.5f * (h.x + l.x), -0.5f * (h.y + l.y), -0.5f * (h.z + l.z), -0.5f * (h.w + l.w));
+                        } else {
+                            cv[u] = ldg4(p.gtab + (size_t)k * p.D + 4 * cc[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
                         float4 o;
                         if (linear) {
-                            o = cv[c];                                                      // (:194-197)
+                            o = cv[u];                                                      // (:194-197)
                         } else {
                             // new_latent = enc_embs + picked_code - enc_embs.detach()  (:145)
-                            o.x = __fsub_rn(__fadd_rn(xv[c].x, cv[c].x), xv[c].x); o.y = __fsub_rn(__fadd_rn(xv[c].y, cv[c].y), xv[c].y);
-                            o.z = __fsub_rn(__fadd_rn(xv[c].z, cv[c].z), xv[c].z); o.w = __fsub_rn(__fadd_rn(xv[c].w, cv[c].w), xv[c].w);
-                            if (skip) o = xv[c];                                            // (:142)
+                            o.x = __fsub_rn(__fadd_rn(xv[u].x, cv[u].x), xv[u].x); o.y = __fsub_rn(__fadd_rn(xv[u].y, cv[u].y), xv[u].y);
+                            o.z = __fsub_rn(__fadd_rn(xv[u].z, cv[u].z), xv[u].z); o.w = __fsub_rn(__fadd_rn(xv[u].w, cv[u].w), xv[u].w);
+                            if (skip) o = xv[u];                                            // (:142)
                         }
-                        if (want_se) {
-                            const float d0 = xv[c].x - cv[c].x, d1 = xv[c].y - cv[c].y, d2 = xv[c].z - cv[c].z, d3 = xv[c].w - cv[c].w;
+                        if (want_se && code[u] >= 0) {
+                            const float d0 = xv[u].x - cv[u].x, d1 = xv[u].y - cv[u].y, d2 = xv[u].z - cv[u].z, d3 = xv[u].w - cv[u].w;
                             se_acc = fmaf(d0, d0, se_acc); se_acc = fmaf(d1, d1, se_acc);
                             se_acc = fmaf(d2, d2, se_acc); se_acc = fmaf(d3, d3, se_acc);
                         }
-                        *reinterpret_cast<float4*>(sXt + kb * XBLK + sw128_offset(r, c0 + c)) = o;
+                        *reinterpret_cast<float4*>(sXt + (cc[u] >> 3) * XBLK + sw128_offset(rr[u], cc[u] & 7)) = o;
                     }
                 }
-                p.idx[row0 + r] = best;
             }
+            VQB_TL(13);
             if (p.hist) {
                 // warp-aggregated histogram: one atomic per distinct code per warp
                 const unsigned peers = __match_any_sync(0xffffffffu, valid ? best : -1);
@@ -554,14 +572,14 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
             VQB_TL(7);
             fence_proxy_async_smem();                               // this thread's tile / p_code writes -> async proxy
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // epilogue warps only
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // this warpgroup only
             if (et == 0) {
                 // new_latent tile: TMA store straight from the swizzled tile (rows beyond N are clipped by TMA)
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) tma_store_2d(&tm_q, sXt + kb * XBLK, kb * 32, row0);
                 if (PCODE && (p.K & 1)) {
                     const uint32_t bytes = (uint32_t)(rows * p.K * 4) & ~15u;
-                    if (bytes) bulk_store_1d(p.pcode + (size_t)row0 * p.K, sP, bytes);
+                    if (bytes) bulk_store_1d(p.pcode + (size_t)row0 * p.K, sPg, bytes);
                 }
                 tma_store_commit();
             }
@@ -570,13 +588,13 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const int n = rows * p.K;
                 if (p.K & 1) {
                     const int done = (int)(((uint32_t)(n * 4) & ~15u) >> 2);   // < 16 bytes of a ragged last tile
-                    if (et < n - done) dst[done + et] = sP[done + et];
+                    if (et < n - done) dst[done + et] = sPg[done + et];
                 } else {
                     const int KP = p.K | 1;
                     int rr = et / p.K, k = et - rr * p.K;           // running (row, code) of element i
                     const int step_r = 128 / p.K, step_k = 128 - step_r * p.K;
                     for (int i = et; i < n; i += 128) {
-                        __stcs(dst + i, sP[rr * KP + k]);
+                        __stcs(dst + i, sPg[rr * KP + k]);
                         rr += step_r; k += step_k;
                         if (k >= p.K) { k -= p.K; ++rr; }
                     }
@@ -585,9 +603,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             VQB_TL(8);
             if (et == 0) tma_store_wait_read();                     // shared memory may be overwritten from here on
             VQB_TL(9);
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // sP / x tile fully drained before reuse
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // sP / x tile fully drained before reuse
             if (lane == 0) mbar_arrive(&x_empty[xs]);               // the x slot may be refilled by TMA
-            ++x_it;
+            x_it += NWG;
         }
         if (p.sqerr) {
             se_acc = warp_sum(se_acc);
@@ -643,8 +661,8 @@ unsigned long long* get_debug_timeline() { return g_timeline; }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static int64_t pad_codes(int64_t K, int64_t bn) { return (K + bn - 1) / bn * bn; }
-static size_t hi_bytes(int64_t K, int64_t D) { return align256((size_t)pad_codes(K, 128) * (D + 32) * 4); }
-static size_t lo_bytes(int64_t K, int64_t D) { return align256((size_t)pad_codes(K, 128) * D * 4); }
+static size_t hi_bytes(int64_t K, int64_t D) { return cache_hi_bytes(K, D); }
+static size_t lo_bytes(int64_t K, int64_t D) { return cache_lo_bytes(K, D); }
 
 // which kernel configuration serves this call (0 = none: use the exact SIMT path)
 enum TcMode { TC_NONE = 0, TC_PCODE, TC_SEARCH3, TC_SEARCH1 };
@@ -660,20 +678,23 @@ static TcMode tc_mode(const vqb_fwd_args* a) {
 bool forward_tensor_supported(const vqb_fwd_args* a) { return tc_mode(a) != TC_NONE; }
 
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
-    *bytes = tc_mode(a) == TC_NONE ? 0 : hi_bytes(a->n_codes, a->dim) + lo_bytes(a->n_codes, a->dim) + 256;
+    const TcMode mode = tc_mode(a);
+    const bool cached = a->operand_cache && (a->flags & VQB_SCORE_L2) && mode == TC_PCODE;
+    *bytes = mode == TC_NONE ? 0 : (cached ? 0 : hi_bytes(a->n_codes, a->dim) + lo_bytes(a->n_codes, a->dim)) + (mode == TC_PCODE ? 0 : 256);
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s) {
-    const size_t smem = (size_t)XS * KB * XBLK * (PASSES == 3 ? 2 : 1) + XBLK + (size_t)BS * BN * 128 +
-                        (PCODE ? BM * 65 * 4 : 16 * BM * 8) + 1024 + 256;
+    constexpr int XLS = NWG == 2 ? 1 : XS;
+    const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + XBLK + (size_t)BS * BN * 128 +
+                        (PCODE ? NWG * BM * 65 * 4 : 16 * BM * 8) + 1024 + 256 + 2 * BM * 4;
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, TC_THREADS, smem, s>>>(tx, th, tl, tq, p);
+    kern<<<grid, 64 + 128 * NWG, smem, s>>>(tx, th, tl, tq, p);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
 }
@@ -683,24 +704,37 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     if (N == 0) return VQB_OK;
     const TcMode mode = tc_mode(a);
     if (mode == TC_NONE) return invalid("vqb_forward: shape not supported by the tensor-core path");
-    const size_t need = hi_bytes(K, D) + lo_bytes(K, D) + 256;
-    if (!a->workspace || a->workspace_bytes < need) {
+    const bool linear = !(a->flags & VQB_SCORE_L2);
+    const bool cached = a->operand_cache && !linear && mode == TC_PCODE;   // the cache carries no |e|_max: p_code mode only
+    const size_t need = (cached ? 0 : hi_bytes(K, D) + lo_bytes(K, D)) + (mode == TC_PCODE ? 0 : 256);
+    if (need && (!a->workspace || a->workspace_bytes < need)) {
         set_error("vqb_forward: workspace too small (%zu < %zu bytes)", a->workspace_bytes, need);
         return VQB_ERR_WORKSPACE;
     }
-    const bool linear = !(a->flags & VQB_SCORE_L2);
     uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
-    float* hi = reinterpret_cast<float*>(ws);
-    float* lo = reinterpret_cast<float*>(ws + hi_bytes(K, D));
-    uint8_t* tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
+    float* hi;
+    float* lo;
+    uint8_t* tail;
+    if (cached) {
+        uint8_t* oc = reinterpret_cast<uint8_t*>(const_cast<void*>(a->operand_cache));
+        hi = reinterpret_cast<float*>(oc);
+        lo = reinterpret_cast<float*>(oc + hi_bytes(K, D));
+        tail = ws;
+    } else {
+        hi = reinterpret_cast<float*>(ws);
+        lo = reinterpret_cast<float*>(ws + hi_bytes(K, D));
+        tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
+    }
     float* emax = reinterpret_cast<float*>(tail);
     unsigned int* stats = a->search_stats ? a->search_stats : reinterpret_cast<unsigned int*>(tail + 16);
     if (mode != TC_PCODE) VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));   // emax / stats are only used by the search epilogue
     const int BN = mode == TC_PCODE ? 64 : 128;
     const int64_t Kpad = pad_codes(K, BN);
-    launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, linear ? 1.f : -2.f, linear ? -1e30f : 1e30f,
-                          hi, mode == TC_SEARCH1 ? nullptr : lo, mode == TC_PCODE ? nullptr : emax, s);
-    VQB_CHECK_LAUNCH("build_operands_kernel");
+    if (!cached) {
+        launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, linear ? 1.f : -2.f, linear ? -1e30f : 1e30f,
+                              hi, mode == TC_SEARCH1 ? nullptr : lo, mode == TC_PCODE ? nullptr : emax, s);
+        VQB_CHECK_LAUNCH("build_operands_kernel");
+    }
 
     CUtensorMap tx, th, tl, tq;
     int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM);
@@ -719,8 +753,8 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
 
     //                      KB  BN  XS BS PASSES RESIDENT PCODE
     if (mode == TC_PCODE) {
-        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true>(tx, th, tl, tq, p, s);
-        return launch_tc<2, 64, 2, 5, 3, true, true>(tx, th, tl, tq, p, s);
+        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true, 2>(tx, th, tl, tq, p, s);
+        return launch_tc<2, 64, 2, 5, 3, true, true, 2>(tx, th, tl, tq, p, s);
     }
     if (mode == TC_SEARCH3) {
         if (K <= 128) {                                            // whole codebook resident in shared memory

@@ -140,9 +140,10 @@ int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K,
                        int64_t* hist, cudaStream_t s) {
     if (n == 0) return VQB_OK;
     if (D % 4 != 0) return invalid("scatter_add: D must be a multiple of 4 (got %lld)", (long long)D);
+    // per-warp private copies only pay off while 8 warps of them fit (small codebooks, e.g. K=43: 11 KB each);
+    // larger tables go straight to 128-bit global reductions
     const size_t per_warp = (size_t)K * D * 4;
-    int wpb = 8;
-    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    const int wpb = 8;
     if (g && per_warp * wpb <= 96 * 1024)
         return launch_scatter_v<true>((const long long*)idx, n, g, (int)K, (int)D, dtable,
                                       (unsigned long long*)hist, wpb, per_warp * wpb, s);

@@ -5,13 +5,25 @@
 namespace vqb {
 
 // One CTA per code row: table[k,:] = cat(learnable[k,:], attr[k,:] @ W^T + b); enorm[k] = |table[k,:]|^2.
+// With an operand cache the same launch also writes the tf32 hi/lo operand copies used by the tensor-core
+// kernels (forward: -2 e with |e|^2 as the bias block; backward: e), including the padded rows K..Kp-1.
 __global__ void __launch_bounds__(128)
 assemble_table_kernel(const float* __restrict__ learnable, const float* __restrict__ attr,
                       const float* __restrict__ proj_w, const float* __restrict__ proj_b,
                       int K, int D, int A, int Da, float* __restrict__ table,
-                      float* __restrict__ enorm, __nv_bfloat16* __restrict__ table_bf16) {
+                      float* __restrict__ enorm, __nv_bfloat16* __restrict__ table_bf16,
+                      float* __restrict__ f_hi, float* __restrict__ f_lo, float* __restrict__ b_hi,
+                      float* __restrict__ b_lo) {
     const int k = blockIdx.x;
     const int Dl = D - Da;
+    if (k >= K) {                                      // padded operand rows (only launched with a cache)
+        for (int d = threadIdx.x; d < D + 32; d += blockDim.x) {
+            f_hi[(size_t)k * (D + 32) + d] = d == D ? 1e30f : 0.f;
+            b_hi[(size_t)k * (D + 32) + d] = 0.f;
+            if (d < D) { f_lo[(size_t)k * D + d] = 0.f; b_lo[(size_t)k * D + d] = 0.f; }
+        }
+        return;
+    }
     float sq = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float v;
@@ -26,13 +38,25 @@ assemble_table_kernel(const float* __restrict__ learnable, const float* __restri
         }
         table[(size_t)k * D + d] = v;
         if (table_bf16) table_bf16[(size_t)k * D + d] = __float2bfloat16_rn(v);
+        if (f_hi) {
+            const float m2 = -2.f * v, h = tf32_rn(m2), hb = tf32_rn(v);
+            f_hi[(size_t)k * (D + 32) + d] = h;  f_lo[(size_t)k * D + d] = m2 - h;
+            b_hi[(size_t)k * (D + 32) + d] = hb; b_lo[(size_t)k * D + d] = v - hb;
+        }
         sq = fmaf(v, v, sq);
     }
     __shared__ float red[4];
     sq = warp_sum(sq);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
     __syncthreads();
-    if (threadIdx.x == 0 && enorm) enorm[k] = (red[0] + red[1]) + (red[2] + red[3]);
+    const float ee = (red[0] + red[1]) + (red[2] + red[3]);
+    if (threadIdx.x == 0 && enorm) enorm[k] = ee;
+    if (f_hi && threadIdx.x < 32) {                    // bias block: |e|^2 as three tf32-exact words, then zeros
+        const float b0 = tf32_trunc(ee), r1 = ee - b0, b1 = tf32_trunc(r1), b2 = r1 - b1;
+        const int j = threadIdx.x;
+        f_hi[(size_t)k * (D + 32) + D + j] = j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : 0.f));
+        b_hi[(size_t)k * (D + 32) + D + j] = 0.f;
+    }
 }
 
 // d_learnable = eff[:, :Dl];  d_proj_w = eff[:, Dl:]^T @ attr;  d_proj_b = colsum(eff[:, Dl:])
@@ -74,10 +98,14 @@ table_backward_kernel(const float* __restrict__ dtable, const float* __restrict_
 
 using namespace vqb;
 
+extern "C" size_t vqb_operand_cache_bytes(int64_t n_codes, int64_t dim) {
+    return 2 * (cache_hi_bytes(n_codes, dim) + cache_lo_bytes(n_codes, dim));
+}
+
 extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr, const float* proj_w,
                                   const float* proj_b, int64_t n_codes, int64_t dim, int64_t n_attr,
                                   int64_t dim_attr, float* table, float* enorm, void* table_bf16,
-                                  void* stream) {
+                                  void* operand_cache, void* stream) {
     if (!learnable || !table) return invalid("vqb_assemble_table: learnable/table is NULL");
     if (n_codes <= 0 || dim <= 0) return invalid("vqb_assemble_table: bad shape K=%lld D=%lld",
                                                  (long long)n_codes, (long long)dim);
@@ -85,9 +113,18 @@ extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr,
     if (has_attr && (!proj_w || !proj_b || n_attr <= 0 || dim_attr <= 0 || dim_attr >= dim))
         return invalid("vqb_assemble_table: phn_attr given but projection is missing or 0 < D_a < D violated");
     if (!has_attr) { n_attr = 0; dim_attr = 0; }
-    assemble_table_kernel<<<(unsigned)n_codes, 128, 0, (cudaStream_t)stream>>>(
+    float *f_hi = nullptr, *f_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+    unsigned rows = (unsigned)n_codes;
+    if (operand_cache) {
+        uint8_t* oc = reinterpret_cast<uint8_t*>(operand_cache);
+        const size_t hb = cache_hi_bytes(n_codes, dim), lb = cache_lo_bytes(n_codes, dim);
+        f_hi = reinterpret_cast<float*>(oc);          f_lo = reinterpret_cast<float*>(oc + hb);
+        b_hi = reinterpret_cast<float*>(oc + hb + lb); b_lo = reinterpret_cast<float*>(oc + 2 * hb + lb);
+        rows = (unsigned)cache_rows(n_codes);
+    }
+    assemble_table_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(
         learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
-        enorm, (__nv_bfloat16*)table_bf16);
+        enorm, (__nv_bfloat16*)table_bf16, f_hi, f_lo, b_hi, b_lo);
     VQB_CHECK_LAUNCH("assemble_table_kernel");
     return VQB_OK;
 }

@@ -35,8 +35,8 @@ def _c(t):
 # ------------------------------------------------------------------------------------------------
 # raw (non-differentiable) table assembly: src/embed.py:109-112
 # ------------------------------------------------------------------------------------------------
-def assemble_table(learnable, phn_attr=None, proj_w=None, proj_b=None, want_bf16=False):
-    """Returns (table[K,D], enorm[K], table_bf16 or None).  No autograd."""
+def assemble_table(learnable, phn_attr=None, proj_w=None, proj_b=None, want_bf16=False, want_cache=False):
+    """Returns (table[K,D], enorm[K], table_bf16 or None[, operand_cache]).  No autograd."""
     lib = _lib.load()
     _require(learnable, "learnable_table")
     learnable = _c(learnable.detach())
@@ -50,9 +50,14 @@ def assemble_table(learnable, phn_attr=None, proj_w=None, proj_b=None, want_bf16
     table = torch.empty(K, D, device=learnable.device, dtype=torch.float32)
     enorm = torch.empty(K, device=learnable.device, dtype=torch.float32)
     tbf = torch.empty(K, D, device=learnable.device, dtype=torch.bfloat16) if want_bf16 else None
+    cache = None
+    if want_cache:
+        cache = torch.empty(lib.vqb_operand_cache_bytes(K, D), device=learnable.device, dtype=torch.uint8)
     with torch.cuda.device(learnable.device):
         _lib.check(lib.vqb_assemble_table(ptr(learnable), ptr(phn_attr), ptr(proj_w), ptr(proj_b), K, D, A, Da,
-                                          ptr(table), ptr(enorm), ptr(tbf), _stream(learnable)))
+                                          ptr(table), ptr(enorm), ptr(tbf), ptr(cache), _stream(learnable)))
+    if want_cache:
+        return table, enorm, tbf, cache
     return table, enorm, tbf
 
 
@@ -77,7 +82,7 @@ def _table_backward(dtable, table, colsum, phn_attr, Da):
 
 
 def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, hist, want_sqerr,
-                 score_w_bf16=None, search_stats=None):
+                 score_w_bf16=None, search_stats=None, operand_cache=None):
     lib = _lib.load()
     N, D = x2d.shape
     K = score_w.shape[0]
@@ -94,6 +99,7 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
     a.score_w_bf16 = ptr(score_w_bf16)
     a.temp, a.p_code, a.idx, a.new_latent = ptr(temp), ptr(p_code), ptr(idx), ptr(q)
     a.hist, a.sq_err_sum, a.search_stats = ptr(hist), ptr(sq), ptr(search_stats)
+    a.operand_cache = ptr(operand_cache)
     with torch.cuda.device(dev):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
@@ -104,7 +110,7 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
 
 
 def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp, p_code, idx, g_p, g_q,
-                  want_dx_buffer, separate_gather):
+                  want_dx_buffer, separate_gather, operand_cache=None):
     """Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None)."""
     lib = _lib.load()
     N, D = x2d.shape
@@ -125,6 +131,7 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.x, a.score_w, a.score_b, a.gather_table, a.temp = ptr(x2d), ptr(score_w), ptr(score_b), ptr(gather_table), ptr(temp)
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.dx, a.d_score_w, a.colsum, a.d_gather, a.d_temp = ptr(dx), ptr(d_w), ptr(colsum), ptr(d_gather), ptr(d_temp)
+    a.operand_cache = ptr(operand_cache)
     with torch.cuda.device(dev):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vqb_backward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
@@ -173,7 +180,10 @@ class _VQL2(torch.autograd.Function):
             raise RuntimeError("semi-tts_b200: enc_embs must be [B, S, D]")
         B, S, D = x.shape
         x2d = _c(x.detach()).view(B * S, D)
-        table, enorm, tbf = assemble_table(learnable, phn_attr, proj_w, proj_b)
+        want_cache = cfg.tensor_cores and cfg.want_pcode
+        res = assemble_table(learnable, phn_attr, proj_w, proj_b, want_cache=want_cache)
+        table, enorm, tbf = res[:3]
+        cache = res[3] if want_cache else None
         K = table.shape[0]
         if table.shape[1] != D:
             raise RuntimeError("semi-tts_b200: enc_embs has D=%d but the codebook has D=%d" % (D, table.shape[1]))
@@ -182,7 +192,8 @@ class _VQL2(torch.autograd.Function):
         flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         temp_c = _c(temp.detach())
         p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
-                                          cfg.want_losses, tbf)
+                                          cfg.want_losses, tbf, None, cache)
+        ctx.op_cache = cache
         ctx.set_materialize_grads(False)                    # an unused output must arrive as None, not zeros
         ctx.cfg, ctx.shape = cfg, (B, S, D, K)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
@@ -220,7 +231,7 @@ class _VQL2(torch.autograd.Function):
             dx = g_q2
         else:
             dx, d_w, colsum, _, d_temp = _run_backward(flags, cfg.n_real_rows, x2d, table, enorm, table, temp,
-                                                       p_code, idx, g_p2, g_q2, True, False)
+                                                       p_code, idx, g_p2, g_q2, True, False, ctx.op_cache)
         if have_loss:
             if dx is None:
                 dx, acc = torch.empty(N, D, device=dev, dtype=torch.float32), False

@@ -6,10 +6,11 @@ from helpers import build_module
 from semi_tts_b200 import _lib
 g = load_golden("l2_attr_stopgrad")
 m = build_module(g, "l2"); m.eval()
+m.track_usage = os.environ.get("NOHIST") is None
 x = torch.randn(64, 800, 64, device="cuda")
 lib = _lib.load()
 buf = torch.zeros(128, dtype=torch.int64, device="cuda")
-names = {1: "start", 2: "tile_begin", 3: "x_full", 4: "xlo_done", 5: "t_full", 6: "softmax_done", 7: "gather_done", 8: "stores_issued", 9: "store_read_done", 10: "end"}
+names = {1: "start", 2: "tile_begin", 3: "x_full", 4: "xlo_done", 5: "t_full", 6: "softmax_done", 7: "gather_done", 8: "stores_issued", 9: "store_read_done", 10: "end", 11: "idx_written", 12: "after_bar", 13: "gather_loop_done"}
 with torch.no_grad():
     for _ in range(3): m(x)
     torch.cuda.synchronize()
