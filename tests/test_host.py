@@ -132,8 +132,9 @@ def _gloo_worker(rank, world, port, q):
             p.grad = torch.randn(p.shape, generator=gen)
     m.usage.counts = torch.randint(0, 1000, (43,), generator=gen)
     V.dist.allreduce_codebook_grads(m)
-    out = {n: p.grad.clone() for n, p in m.named_parameters() if p.requires_grad}
-    out["usage"] = m.usage.counts.clone()
+    # numpy payloads: torch tensors travel through a Queue by shared fd, which races with worker exit
+    out = {n: p.grad.numpy().copy() for n, p in m.named_parameters() if p.requires_grad}
+    out["usage"] = m.usage.counts.numpy().copy()
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -162,8 +163,8 @@ def test_allreduce_of_codebook_grads_and_histogram_gloo_world2():
         expect["usage"] = expect.get("usage", 0) + torch.randint(0, 1000, (43,), generator=gen)
     for rank in range(2):
         for n, v in expect.items():
-            assert torch.allclose(res[rank][n].to(v.dtype), v, atol=1e-6), (rank, n)
-        assert res[rank]["usage"].dtype == torch.int64
+            assert torch.allclose(torch.from_numpy(res[rank][n]).to(v.dtype), v, atol=1e-6), (rank, n)
+        assert res[rank]["usage"].dtype == np.int64
 
 
 def test_flat_gradient_view_detection():
