@@ -2,6 +2,7 @@
 // selection, thread-local error string.  No CPU fallback exists anywhere in this library.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "vqb_common.cuh"
 
@@ -149,7 +150,12 @@ extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
     *bytes = 0;
     int rc = validate_bwd(a);
     if (rc) return rc;
-    if (a->n_rows > 0) return backward_tensor_workspace(a, bytes);
+    if (a->n_rows > 0) {
+        size_t b1 = 0, b2 = 0;
+        backward_tensor_workspace(a, &b1);
+        backward_h2_workspace(a, &b2);
+        *bytes = b1 > b2 ? b1 : b2;
+    }
     return VQB_OK;
 }
 
@@ -190,6 +196,9 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->dx) ||
         !aligned16(a->d_score_w) || (a->g_q && !aligned16(a->g_q)) || (a->d_gather && !aligned16(a->d_gather)))
         return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
+    const char* pick = getenv("VQB_BWD_KERNEL");                    // developer override: "tf32" = first-generation kernel
+    const bool want_tf32 = pick && strcmp(pick, "tf32") == 0;
+    if (!want_tf32 && backward_h2_supported(a)) return launch_backward_h2(a, s);
     if (backward_tensor_supported(a)) return launch_backward_tensor(a, s);
     return launch_backward_simt(a, s);
 }

@@ -76,5 +76,10 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
 bool backward_tensor_supported(const vqb_bwd_args* a);
 int backward_tensor_workspace(const vqb_bwd_args* a, size_t* bytes);
 int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s);
+// fp16x2 generation of the parity-mode backward (vqb_bwd_h2.cu); VQB_BWD_KERNEL=tf32 in the environment selects the
+// first-generation tf32 kernel instead (kept as a comparator)
+bool backward_h2_supported(const vqb_bwd_args* a);
+int backward_h2_workspace(const vqb_bwd_args* a, size_t* bytes);
+int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s);
 
 }  // namespace vqb

@@ -303,10 +303,11 @@ def test_config2_size_against_cpu_port_and_properties():
         assert torch.equal(m.last_idx.cpu(), idx)
 
 
-@pytest.mark.parametrize("B,S,first_n", [(4, 128, 2), (3, 256, 1), (5, 77, 0), (2, 128, 2)])
+@pytest.mark.parametrize("B,S,first_n", [(4, 128, 2), (3, 256, 1), (5, 77, 0), (2, 128, 2), (4, 100, 1), (1, 50, 0),
+                                          (40, 400, 7)])
 def test_tensor_core_backward_vs_oracle_and_simt(B, S, first_n):
-    """tcgen05 backward (tile-aligned real/fake split, ragged last tile) against the fp64 oracle and the
-    exact-fp32 CUDA-core backward."""
+    """tcgen05 backward (real/fake split on and off a tile edge, ragged last tile, several tiles per CTA) against
+    the fp64 oracle and the exact-fp32 CUDA-core backward."""
     g = load_golden("l2_attr_stopgrad")
     gen = torch.Generator().manual_seed(B * 1000 + S)
     x_cpu = torch.randn(B, S, 64, generator=gen)

@@ -10,7 +10,7 @@ x = torch.randn(64, 800, 64, device="cuda", requires_grad=True)
 gp = torch.randn(64, 800, 43, device="cuda"); gq = torch.randn(64, 800, 64, device="cuda")
 lib = _lib.load()
 buf = torch.zeros(128, dtype=torch.int64, device="cuda")
-names = {1: "start", 2: "tile_begin", 3: "in_full", 4: "softmax_bwd_done", 5: "C_written", 6: "p1_done", 7: "Clo_written", 8: "mma_done", 9: "dx_staged", 10: "dx_stored", 11: "flushed"}
+names = {1: "start", 2: "tile_begin", 3: "pg_full", 4: "softmax_bwd_done", 5: "operands_written", 6: "colsum_done", 7: "d1_done", 8: "g_and_scatter_ready", 9: "dx_written", 10: "mma_done", 11: "tile_end", 12: "loop_end", 13: "flushed"}
 for _ in range(3):
     p, q, _, _ = m(x); torch.autograd.backward([p, q], [gp, gq])
 torch.cuda.synchronize()
@@ -20,7 +20,10 @@ lib.vqb_debug_set_timeline(ctypes.c_void_p(buf.data_ptr()))
 torch.autograd.backward([p, q], [gp, gq])
 torch.cuda.synchronize()
 lib.vqb_debug_set_timeline(None)
-v = [int(t) for t in buf.cpu().tolist()[:120] if t != 0]
+names.update({20: "acc_tile_begin", 21: "sorted_list_ready", 22: "g_full", 23: "acc_done", 30: "sort_tile_begin", 31: "sort_buffer_free", 32: "codes_loaded", 33: "sorted"})
+raw = buf.cpu().tolist()
+v = [int(t) for t in raw[:120] if t != 0]
+v = sorted(v, key=lambda e: e & ((1 << 56) - 1))
 t0 = v[0] & ((1 << 56) - 1); prev = t0
 for e in v:
     tag, t = (e >> 56) & 0xFF, e & ((1 << 56) - 1)
