@@ -41,6 +41,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this workload, from the committed
+    `ncu --set full` summary (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(p):
+        d = json.load(open(p)).get(kernel)
+        if d:
+            return d.get("dram_bytes_per_launch")
+    return None
+
+
 def _phn_attr_tsv():
     from helpers import phn_attr_tsv
     return phn_attr_tsv()
@@ -152,7 +163,7 @@ def _time_kernels(V, m, sets, iters=24):
     import ctypes
     from semi_tts_b200 import functional as VF, _lib
     attr, pw, pb = m.phn_attr.weight, m.proj_attr.weight, m.proj_attr.bias
-    table, enorm, _ = VF.assemble_table(m.learnable_table, attr, pw, pb)
+    table, enorm, _, cache = VF.assemble_table(m.learnable_table, attr, pw, pb, want_cache=True)
     flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.TENSOR_CORES if m.tensor_cores else 0)
     outs = [VF._run_forward(flags, s[0].view(N_ROWS, D), table, enorm, table, m.temp, True, None, False) for s in sets]
     stream = torch.cuda.current_stream()
@@ -168,6 +179,7 @@ def _time_kernels(V, m, sets, iters=24):
         a.n_rows, a.dim, a.n_codes = N_ROWS, D, K
         a.x, a.score_w, a.score_b, a.gather_table = s[0].data_ptr(), table.data_ptr(), enorm.data_ptr(), table.data_ptr()
         a.temp, a.p_code, a.idx, a.new_latent = m.temp.data_ptr(), p_code.data_ptr(), idx.data_ptr(), q.data_ptr()
+        a.operand_cache = cache.data_ptr()          # as the module passes it (built once per step with the table)
         nb = ctypes.c_size_t(0)
         _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nb)))
         ws = torch.empty(max(nb.value, 1), dtype=torch.uint8, device="cuda")
@@ -180,6 +192,7 @@ def _time_kernels(V, m, sets, iters=24):
         b.x, b.score_w, b.score_b, b.gather_table, b.temp = s[0].data_ptr(), table.data_ptr(), enorm.data_ptr(), table.data_ptr(), m.temp.data_ptr()
         b.p_code, b.idx, b.g_p, b.g_q = p_code.data_ptr(), idx.data_ptr(), s[1].data_ptr(), s[2].data_ptr()
         b.dx, b.d_score_w, b.colsum = dx.data_ptr(), dw.data_ptr(), cs.data_ptr()
+        b.operand_cache = cache.data_ptr()
         nb = ctypes.c_size_t(0)
         _lib.check(lib.vqb_backward_workspace(ctypes.byref(b), ctypes.byref(nb)))
         wsb = torch.empty(max(nb.value, 1), dtype=torch.uint8, device="cuda")
@@ -196,7 +209,9 @@ def _time_kernels(V, m, sets, iters=24):
         torch.cuda.synchronize()
         if i >= 4:
             fwd_ms.append(ev[0].elapsed_time(ev[1])); bwd_ms.append(ev[1].elapsed_time(ev[2]))
-    return statistics.mean(fwd_ms), statistics.mean(bwd_ms)
+    kf = lib.vqb_forward_kernel_name(ctypes.byref(fa[0])).decode()
+    kb = lib.vqb_backward_kernel_name(ctypes.byref(ba[0])).decode()
+    return statistics.mean(fwd_ms), statistics.mean(bwd_ms), kf, kb
 
 
 def _log(rank, msg):
@@ -246,9 +261,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     _log(rank, "warm-up done, capturing graphs")
     graphs, use_graph = [], True
+    lib_ = V._lib.load()
+    launches_per_step = 0
     try:
         pool = None
         for s in sets:
+            l0 = lib_.vqb_launch_count()
             for p_ in m.parameters():
                 p_.grad = None                  # as after optimizer.zero_grad(): backward assigns, it does not accumulate
             s[0].grad = None
@@ -256,6 +274,7 @@ def run_ours(args, rank, world, local_rank):
             # thread_local: the NCCL watchdog thread must not invalidate the capture
             with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 step(s)
+            launches_per_step = int(lib_.vqb_launch_count() - l0)      # this library's kernels in one captured step
             pool = g.pool()
             graphs.append(g)
     except Exception as e:           # noqa: BLE001 -- report and fall back to eager launches of the same kernels
@@ -269,7 +288,11 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
         if int(ok.item()) == 0:
             use_graph, graphs = False, []
-    _log(rank, "launch mode: %s" % ("cuda_graph" if use_graph else "eager"))
+    if not use_graph:
+        l0 = lib_.vqb_launch_count()
+        step(sets[0])
+        launches_per_step = int(lib_.vqb_launch_count() - l0)
+    _log(rank, "launch mode: %s, %d libvqb200 kernels per step" % ("cuda_graph" if use_graph else "eager", launches_per_step))
 
     def run_steps(n, first=0):
         for i in range(n):
@@ -309,28 +332,55 @@ def run_ours(args, rank, world, local_rank):
     h_idx = torch.empty(B, S, dtype=torch.int64).pin_memory()
     h_grad = torch.empty(n_grad + K, dtype=torch.float32).pin_memory()
 
-    def e2e_step(hs):
-        x = hs[0].to(dev, non_blocking=True).requires_grad_(True)
-        gp = hs[1].to(dev, non_blocking=True)
-        gq = hs[2].to(dev, non_blocking=True)
+    # double-buffered pipeline: a copy stream uploads step i+1's pinned host inputs while the compute stream runs step i;
+    # every step still pays its own H2D (x, g_p, g_q) and D2H (indices, codebook gradients, histogram) inside the region
+    NBUF = 3
+    comp, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    dbuf = [[torch.empty_like(t, device=dev) for t in host_sets[0]] for _ in range(NBUF)]
+    for b_ in dbuf:
+        b_[0].requires_grad_(True)
+    ready = [torch.cuda.Event() for _ in range(NBUF)]
+    free = [torch.cuda.Event() for _ in range(NBUF)]
+
+    def upload(i):
+        b_, hs = dbuf[i % NBUF], host_sets[i % 4]
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(free[i % NBUF])
+            with torch.no_grad():
+                for d_, h_ in zip(b_, hs):
+                    d_.copy_(h_, non_blocking=True)
+            ready[i % NBUF].record(copy_s)
+
+    def e2e_step(i):
+        x, gp, gq = dbuf[i % NBUF]
+        comp.wait_event(ready[i % NBUF])
+        x.grad = None
         for p_ in m.parameters():
             p_.grad = None
         p, q, _, _ = m(x)
         torch.autograd.backward([p, q], [gp, gq])
+        free[i % NBUF].record(comp)
         if dist_on:
             V.dist.allreduce_codebook_grads(m)
         h_idx.copy_(m.last_idx, non_blocking=True)
         flat = torch.cat([p_.grad.reshape(-1) for p_ in m.parameters() if p_.requires_grad] + [m.usage.counts.float()])
         h_grad.copy_(flat, non_blocking=True)
-        return float(h_grad[0]) if False else None
 
-    e2e_steps = max(3, min(args.steps, 50))
-    for i in range(3):
-        e2e_step(host_sets[i % 4])
+    def e2e_run(n):
+        for k in range(NBUF):
+            free[k].record(comp)
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            e2e_step(i)
+        comp.wait_stream(copy_s)
+
+    e2e_steps = max(3, min(args.steps, 100))
+    e2e_run(4)
     barrier()
     e0.record()
-    for i in range(e2e_steps):
-        e2e_step(host_sets[i % 4])
+    e2e_run(e2e_steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -345,12 +395,10 @@ def run_ours(args, rank, world, local_rank):
     d2h = 8 * B * S + 4 * (n_grad + K)
 
     if rank == 0:
-        fwd_ms, bwd_ms = _time_kernels(V, m, sets)
+        fwd_ms, bwd_ms, kf, kb_ = _time_kernels(V, m, sets)
         peak, peak_src = _peaks()
         fwd_bytes = N_ROWS * (8 * D + 8 + 4 * K)                      # read x, write new_latent, idx(int64), p_code
         bwd_bytes = N_ROWS * (12 * D + 8 * K + 8)                     # read x, g_q, p_code, g_p, idx; write dx
-        kf = "vqb_fwd_tc_kernel" if m.tensor_cores else "vqb_fwd_simt_small_kernel"
-        kb_ = "vqb_bwd_tc_kernel" if m.tensor_cores else "vqb_bwd_simt_kernel"
         dom = (kb_, bwd_ms, bwd_bytes) if bwd_ms >= fwd_ms else (kf, fwd_ms, fwd_bytes)
         achieved = dom[2] / (dom[1] * 1e-3) / 1e9
         cpu_rate, cpu_ms, cpu_done, cores = cpu_fwd_bwd_rate(400, 3, budget_s=12.0)
@@ -365,12 +413,13 @@ def run_ours(args, rank, world, local_rank):
                                world, ", one NCCL all-reduce of dE + histogram per step" if dist_on else "")},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-                "gpu_launches": 4 * args.steps,
+                "gpu_launches": launches_per_step * args.steps,
                 "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": _ncu_traffic(dom[0]), "peak_source": peak_src,
                              "kernel_ms": {kf: fwd_ms, kb_: bwd_ms},
-                             "note": "kernel_ms = CUDA-event time of one vqb_forward / vqb_backward C-ABI call (dominant kernel + its "
-                                     "operand-prep kernel and a 256-byte memset), averaged over ring-rotated inputs",
+                             "note": "kernel_ms = CUDA-event time of one vqb_forward / vqb_backward C-ABI call on the launching "
+                                     "stream (the named kernel; the backward call also runs its fixed-order partial-sum "
+                                     "reduction kernel), averaged over ring-rotated inputs (> L2)",
                              "algorithmic_bytes": {"fwd": fwd_bytes, "bwd": bwd_bytes}},
                 "cpu_baseline": {"value": cpu_rate, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d full steps of the same workload on the host (oracle/torch_port.py)" % cpu_done},

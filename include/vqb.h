@@ -154,6 +154,13 @@ typedef struct vqb_bwd_args {
 VQB_API int vqb_backward_workspace(const vqb_bwd_args* args, size_t* bytes);
 VQB_API int vqb_backward(const vqb_bwd_args* args, void* stream);
 
+/* Name of the dominant kernel vqb_forward / vqb_backward would launch for these arguments (a static string;
+ * no device work).  Measurement aid: bench.py and the tests label timings / assert the tensor-core route with it. */
+/* kernels of this library launched (or captured into a CUDA graph) by this process so far; host-side tally */
+VQB_API uint64_t vqb_launch_count(void);
+VQB_API const char* vqb_forward_kernel_name(const vqb_fwd_args* args);
+VQB_API const char* vqb_backward_kernel_name(const vqb_bwd_args* args);
+
 /* ---------------------------------------------------------------------------------------------
  * Gather-only paths
  * ------------------------------------------------------------------------------------------- */

@@ -39,7 +39,7 @@ class BwdArgs(ctypes.Structure):
 
 EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
-           "vqb_backward", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward"]
+           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward"]
 
 _lib = None
 _lock = threading.Lock()
@@ -72,12 +72,14 @@ def load():
         lib.vqb_inference_gather.argtypes = [_p, i64, _p, i64, i64, _p, _p]
         lib.vqb_scatter_add.argtypes = [_p, i64, _p, i64, i64, _p, _p, _p]
         lib.vqb_loss_backward.argtypes = [_p, _p, _p, i64, i64, i64, _p, _p, _p, ctypes.c_int, _p, _p]
+        lib.vqb_forward_kernel_name.argtypes = [ctypes.POINTER(FwdArgs)]
+        lib.vqb_backward_kernel_name.argtypes = [ctypes.POINTER(BwdArgs)]
         for name in EXPORTS:
-            fn = getattr(lib, name)
-            if name not in ("vqb_last_error",):
-                fn.restype = ctypes.c_int if name != "vqb_last_error" else ctypes.c_char_p
-        lib.vqb_last_error.restype = ctypes.c_char_p
+            getattr(lib, name).restype = ctypes.c_int
+        for name in ("vqb_last_error", "vqb_forward_kernel_name", "vqb_backward_kernel_name"):
+            getattr(lib, name).restype = ctypes.c_char_p
         lib.vqb_operand_cache_bytes.restype = ctypes.c_size_t
+        lib.vqb_launch_count.restype = ctypes.c_uint64
         if lib.vqb_abi_version() != ABI_VERSION:
             raise RuntimeError("semi-tts_b200: libvqb200.so ABI %d != expected %d -- rebuild"
                                % (lib.vqb_abi_version(), ABI_VERSION))

@@ -1,5 +1,6 @@
 // C-ABI entry points of libvqb200.so (declared in include/vqb.h): argument validation, kernel
 // selection, thread-local error string.  No CPU fallback exists anywhere in this library.
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -84,6 +85,12 @@ namespace vqb { void set_debug_timeline(void* p); }
 // (tag << 56 | globaltimer ns) marks; pass NULL to disable
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_timeline(void* dev_ptr) { vqb::set_debug_timeline(dev_ptr); }
 
+namespace vqb {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}
+extern "C" uint64_t vqb_launch_count(void) { return vqb::g_launches.load(std::memory_order_relaxed); }
+
 extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
 extern "C" const char* vqb_last_error(void) { return g_err; }
 
@@ -131,6 +138,12 @@ extern "C" int vqb_forward(const vqb_fwd_args* a, void* stream) {
     if ((a->flags & VQB_TENSOR_CORES) && forward_tensor_supported(a)) return launch_forward_tensor(a, (cudaStream_t)stream);
     if (a->dim > 256) return invalid("vqb_forward: the exact-fp32 path supports D <= 256 (got %lld)", (long long)a->dim);
     return launch_forward_simt(a, (cudaStream_t)stream);
+}
+
+extern "C" const char* vqb_forward_kernel_name(const vqb_fwd_args* a) {
+    if (validate_fwd(a) != VQB_OK) return "invalid";
+    if ((a->flags & VQB_TENSOR_CORES) && forward_tensor_supported(a)) return "vqb_fwd_tc_kernel";
+    return a->n_codes <= 64 ? "vqb_fwd_simt_small_kernel" : "vqb_fwd_simt_generic_kernel";
 }
 
 static int validate_bwd(const vqb_bwd_args* a) {
@@ -201,4 +214,14 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
     if (!want_tf32 && backward_h2_supported(a)) return launch_backward_h2(a, s);
     if (backward_tensor_supported(a)) return launch_backward_tensor(a, s);
     return launch_backward_simt(a, s);
+}
+
+extern "C" const char* vqb_backward_kernel_name(const vqb_bwd_args* a) {
+    if (validate_bwd(a) != VQB_OK) return "invalid";
+    if (!a->g_p && (a->flags & VQB_STOP_GRAD)) return "scatter_hist_kernel";
+    const char* pick = getenv("VQB_BWD_KERNEL");
+    const bool want_tf32 = pick && strcmp(pick, "tf32") == 0;
+    if (!want_tf32 && backward_h2_supported(a)) return "vqb_bwd_h2_kernel";
+    if (backward_tensor_supported(a)) return "vqb_bwd_tc_kernel";
+    return "vqb_bwd_simt_kernel";
 }

@@ -18,8 +18,11 @@ int invalid(const char* fmt, ...);
         if (e_ != cudaSuccess) return ::vqb::cuda_fail(e_, #call);  \
     } while (0)
 
+void count_launch();                  // host-side tally behind vqb_launch_count()
+
 #define VQB_CHECK_LAUNCH(name)                                      \
     do {                                                            \
+        ::vqb::count_launch();                                      \
         cudaError_t e_ = cudaGetLastError();                        \
         if (e_ != cudaSuccess) return ::vqb::cuda_fail(e_, name);   \
     } while (0)

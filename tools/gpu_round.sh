@@ -15,5 +15,5 @@ timeout 300 python tools/sweep_c3.py > gpurun_out/sweep_c3.jsonl 2> gpurun_out/s
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 4 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
 grep -E "passed|failed" gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log | cut -c1-300; cut -c1-700 gpurun_out/bench.json; tail -2 gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_ref.json
-bash tools/ncu_full.sh vqb_bwd_tc_kernel bwd
+bash tools/ncu_full.sh vqb_bwd_h2_kernel bwd
 bash tools/ncu_full.sh vqb_fwd_tc_kernel fwd
