@@ -316,6 +316,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e0.record()
     run_steps(args.steps, first=args.warmup)
+    if dist_on:
+        V.dist.allreduce_usage(m)          # bin/train_vqvae.py:305 reads the histogram once per 500-step window
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -410,7 +412,8 @@ def run_ours(args, rank, world, local_rank):
                            "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
                                RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
                            "parallelism": "dp%d (frames sharded by batch, codebook replicated%s)" % (
-                               world, ", one NCCL all-reduce of dE + histogram per step" if dist_on else "")},
+                               world, ", one NCCL all-reduce of the flat codebook-gradient buffer per step; the usage histogram is "
+                               "exchanged once per timed window, where the trainer reads it" if dist_on else "")},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
                 "gpu_launches": launches_per_step * args.steps,

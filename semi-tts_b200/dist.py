@@ -51,12 +51,14 @@ def _flat_view(grads):
     return torch.as_strided(first, (n,), (1,), first.storage_offset())
 
 
-def allreduce_codebook_grads(module, group=None, average=False, include_usage=True):
+def allreduce_codebook_grads(module, group=None, average=False, include_usage=False):
     """Sum (or average) the quantizer's parameter gradients and its usage histogram across ranks: the only
     exchange of the data-parallel path.  No host synchronisation (CUDA-graph capturable).
     Gradients produced by this package's backward are views of one flat buffer and are reduced in place by ONE
-    all-reduce; the int64 histogram is reduced by a second, 8*K-byte one.  Gradients from elsewhere (e.g. after
-    accumulation into pre-existing .grad tensors) are packed into a temporary buffer first."""
+    all-reduce.  Gradients from elsewhere (e.g. after accumulation into pre-existing .grad tensors) are packed into
+    a temporary buffer first.  The int64 usage histogram is only consumed at plot time (every 500 steps,
+    bin/train_vqvae.py:305), so by default it is exchanged there (`allreduce_usage`, or `include_usage=True` to do it
+    in the same call: a second, 8*K-byte all-reduce of the counts accumulated since the previous exchange)."""
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = dist.get_world_size(group)
@@ -78,6 +80,12 @@ def allreduce_codebook_grads(module, group=None, average=False, include_usage=Tr
                 chunk = packed[off:off + n].view_as(g)
                 g.copy_(chunk / world if average else chunk)
                 off += n
+    if include_usage:
+        allreduce_usage(module, group)
+
+
+def allreduce_usage(module, group=None):
+    """Exchange the usage histogram (counts since the previous exchange are summed over ranks exactly once)."""
     usage = getattr(module, "usage", None)
-    if include_usage and usage is not None and usage.counts is not None:
-        dist.all_reduce(usage.counts, op=dist.ReduceOp.SUM, group=group)
+    if usage is not None:
+        usage.all_reduce(group)

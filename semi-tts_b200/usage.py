@@ -5,6 +5,11 @@ step (bin/train_vqvae.py:256-261) and, every 500 steps, computes `data.count(i)/
 entry 0 forced to zero (src/util.py:139-143) before resetting the list (:310).  Here the counts are
 accumulated by the forward kernel itself into an int64 [K] buffer; `bar()` returns the same numbers
 without a per-step device->host sync.
+
+Data-parallel runs: `counts` holds this rank's rows that have not been exchanged yet, `reduced` the part
+already summed over all ranks.  `all_reduce()` moves `counts` into `reduced` (sum over ranks) and zeroes it,
+so it may be called every step, every N steps or only at plot time -- `bar()` / `total()` always report
+`reduced + counts`, and nothing is ever counted twice.
 """
 import torch
 
@@ -12,7 +17,8 @@ import torch
 class UsageHistogram:
     def __init__(self, n_codes):
         self.n_codes = n_codes
-        self.counts = None            # int64 [K] on the device of the first forward
+        self.counts = None            # int64 [K] on the device of the first forward (this rank, not yet exchanged)
+        self.reduced = None           # int64 [K] already summed over the data-parallel group
 
     def buffer_for(self, ref):
         if self.counts is None or self.counts.device != ref.device:
@@ -22,15 +28,34 @@ class UsageHistogram:
     def reset(self):
         if self.counts is not None:
             self.counts.zero_()
+        if self.reduced is not None:
+            self.reduced.zero_()
+
+    def all_counts(self):
+        """int64 [K]: everything counted since the last reset (exchanged part + this rank's pending part)."""
+        if self.counts is None:
+            return None
+        return self.counts if self.reduced is None else self.counts + self.reduced
+
+    def all_reduce(self, group=None):
+        """Sum the pending per-rank counts over `group` (no host sync; CUDA-graph capturable)."""
+        import torch.distributed as dist
+        if self.counts is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        if self.reduced is None or self.reduced.device != self.counts.device:
+            self.reduced = torch.zeros_like(self.counts)
+        dist.all_reduce(self.counts, op=dist.ReduceOp.SUM, group=group)
+        self.reduced += self.counts
+        self.counts.zero_()
 
     def total(self):
-        return 0 if self.counts is None else int(self.counts.sum().item())
+        return 0 if self.counts is None else int(self.all_counts().sum().item())
 
     def bar(self, zero_pad_tok=True):
         """`cnts` of src/util.py:139-143 as a list of K floats (one host sync, at plot time only)."""
         if self.counts is None:
             return [0.0] * self.n_codes
-        c = self.counts.to(torch.float64)
+        c = self.all_counts().to(torch.float64)
         tot = c.sum()
         out = (c / tot) if tot > 0 else c
         if zero_pad_tok:

@@ -131,10 +131,14 @@ def _gloo_worker(rank, world, port, q):
         if p.requires_grad:
             p.grad = torch.randn(p.shape, generator=gen)
     m.usage.counts = torch.randint(0, 1000, (43,), generator=gen)
-    V.dist.allreduce_codebook_grads(m)
+    V.dist.allreduce_codebook_grads(m, include_usage=True)
+    # a second step's counts, exchanged again: nothing may be counted twice
+    m.usage.counts += torch.randint(0, 1000, (43,), generator=gen)
+    V.dist.allreduce_usage(m)
     # numpy payloads: torch tensors travel through a Queue by shared fd, which races with worker exit
     out = {n: p.grad.numpy().copy() for n, p in m.named_parameters() if p.requires_grad}
-    out["usage"] = m.usage.counts.numpy().copy()
+    out["usage"] = m.usage.all_counts().numpy().copy()
+    out["usage_bar"] = np.asarray(m.usage.bar())
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -160,11 +164,16 @@ def test_allreduce_of_codebook_grads_and_histogram_gloo_world2():
         for n, p in m.named_parameters():
             if p.requires_grad:
                 expect[n] = expect.get(n, 0) + torch.randn(p.shape, generator=gen)
-        expect["usage"] = expect.get("usage", 0) + torch.randint(0, 1000, (43,), generator=gen)
+        expect["usage"] = expect.get("usage", 0) + torch.randint(0, 1000, (43,), generator=gen) \
+            + torch.randint(0, 1000, (43,), generator=gen)
+    bar = expect["usage"].double() / expect["usage"].sum()
+    bar[0] = 0
     for rank in range(2):
         for n, v in expect.items():
             assert torch.allclose(torch.from_numpy(res[rank][n]).to(v.dtype), v, atol=1e-6), (rank, n)
         assert res[rank]["usage"].dtype == np.int64
+        assert np.array_equal(res[rank]["usage"], expect["usage"].numpy())
+        assert np.allclose(res[rank]["usage_bar"], bar.numpy())
 
 
 def test_flat_gradient_view_detection():
