@@ -238,6 +238,8 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     m = V.L2Embedding(K, False, **_codebook_kwargs()).to(dev)
     m.train()
+    if dist_on and not os.environ.get("VQB_NCCL_ALLREDUCE"):
+        V.dist.enable_fused_allreduce(m)         # gradient sum inside the backward's tail kernel (NVLink peer memory)
     # ring of distinct device-resident input sets (weak scaling: every rank owns RING x 64 x 800 frames)
     sets = [_inputs(1000 * rank + i, dev) for i in range(RING)]
     for s in sets:
@@ -412,8 +414,10 @@ def run_ours(args, rank, world, local_rank):
                            "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
                                RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
                            "parallelism": "dp%d (frames sharded by batch, codebook replicated%s)" % (
-                               world, ", one NCCL all-reduce of the flat codebook-gradient buffer per step; the usage histogram is "
-                               "exchanged once per timed window, where the trainer reads it" if dist_on else "")},
+                               world, ", codebook-gradient sum over GPUs %s; the usage histogram is "
+                               "exchanged once per timed window, where the trainer reads it" % (
+                                   "fused into the backward tail kernel (one-shot all-reduce over NVLink peer memory)"
+                                   if m.fused_tail.exchange is not None else "by one NCCL all-reduce per step") if dist_on else "")},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
                 "gpu_launches": launches_per_step * args.steps,

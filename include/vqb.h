@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQB_ABI_VERSION 1
+#define VQB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VQB_API __attribute__((visibility("default")))
@@ -126,6 +126,31 @@ VQB_API int vqb_forward(const vqb_fwd_args* args, void* stream);
  * dx is overwritten.  If g_p == NULL, STOP_GRAD and L2, only the scatter route runs and dx may be
  * NULL (the caller aliases dx = g_q: the straight-through identity costs zero bytes).
  * ------------------------------------------------------------------------------------------- */
+/* Optional fused tail of vqb_backward (L2 score, tensor-core route): the fixed-order sum of the per-CTA partial
+ * gradients, the backward of the table assembly (vqb_table_backward) and -- in data-parallel runs -- the sum of the
+ * result over all GPUs run as ONE kernel behind the main backward kernel, instead of three launches and an NCCL
+ * call.  The cross-GPU step is a one-shot all-reduce over NVLink peer memory: every rank stores its flat gradient
+ * into its own exchange buffer, raises a flag in every peer's buffer, waits for the peers' flags and adds the
+ * world buffers in rank order (so all ranks obtain bit-identical sums).
+ *   With a tail, d_score_w and colsum are scratch: they are overwritten (no pre-zeroing) and hold this GPU's table
+ *   gradient / column sums afterwards.
+ * Exchange buffer of each rank (peer-mapped, e.g. torch symmetric memory), vqb_exchange_bytes(n_flat, world) bytes,
+ * zero-filled once before the first call:  [world x uint32 flags, padded to 128 B | slot 0: n_flat fp32 | slot 1].
+ * Flags carry a call counter (`epoch`), so the buffers need no reset between calls or CUDA-graph replays; all ranks
+ * must make the same sequence of calls. */
+typedef struct vqb_bwd_tail {
+    const float* phn_attr;       /* [K,A] or NULL (then n_attr = dim_attr = 0 and d_flat = d_learnable only) */
+    int64_t n_attr, dim_attr;
+    float* d_flat;               /* [K*D_l + D_a*A + D_a] = d_learnable | d_proj_w | d_proj_b, overwritten */
+    uint32_t* counter;           /* [2] device words, zero before the first call: [0] block ticket (left zero),
+                                    [1] epoch of the exchange (incremented by every call with world > 1) */
+    int32_t world, rank;         /* world <= 1: no exchange */
+    void* const* peer_bufs;      /* DEVICE array [world] of each rank's exchange-buffer address as mapped here */
+} vqb_bwd_tail;
+
+#define VQB_MAX_WORLD 16
+VQB_API size_t vqb_exchange_bytes(int64_t n_flat, int32_t world);
+
 typedef struct vqb_bwd_args {
     uint32_t struct_size;
     uint32_t flags;
@@ -149,6 +174,9 @@ typedef struct vqb_bwd_args {
     const void* operand_cache;   /* from vqb_assemble_table (L2 score only), or NULL */
     void*  workspace;
     size_t workspace_bytes;
+    const vqb_bwd_tail* tail;    /* optional fused tail (see above); NULL = plain accumulate-into semantics.  Only
+                                    taken on the route vqb_backward_kernel_name() reports as "vqb_bwd_h2_kernel"
+                                    with VQB_SCORE_L2; otherwise vqb_backward fails with VQB_ERR_INVALID */
 } vqb_bwd_args;
 
 VQB_API int vqb_backward_workspace(const vqb_bwd_args* args, size_t* bytes);

@@ -5,7 +5,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqb200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # flags (include/vqb.h)
 SCORE_L2 = 0x0001
@@ -27,6 +27,11 @@ class FwdArgs(ctypes.Structure):
                 ("sq_err_sum", _p), ("search_stats", _p), ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
 
 
+class BwdTail(ctypes.Structure):
+    _fields_ = [("phn_attr", _p), ("n_attr", ctypes.c_int64), ("dim_attr", ctypes.c_int64), ("d_flat", _p),
+                ("counter", _p), ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_bufs", _p)]
+
+
 class BwdArgs(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("flags", ctypes.c_uint32),
                 ("n_rows", ctypes.c_int64), ("dim", ctypes.c_int64), ("n_codes", ctypes.c_int64),
@@ -34,12 +39,13 @@ class BwdArgs(ctypes.Structure):
                 ("x", _p), ("score_w", _p), ("score_b", _p), ("gather_table", _p), ("temp", _p),
                 ("p_code", _p), ("idx", _p), ("g_p", _p), ("g_q", _p),
                 ("dx", _p), ("d_score_w", _p), ("colsum", _p), ("d_gather", _p), ("d_temp", _p),
-                ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t)]
+                ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t),
+                ("tail", ctypes.POINTER(BwdTail))]
 
 
 EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
-           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward"]
+           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward"]
 
 _lib = None
 _lock = threading.Lock()
@@ -80,6 +86,8 @@ def load():
             getattr(lib, name).restype = ctypes.c_char_p
         lib.vqb_operand_cache_bytes.restype = ctypes.c_size_t
         lib.vqb_launch_count.restype = ctypes.c_uint64
+        lib.vqb_exchange_bytes.argtypes = [i64, ctypes.c_int32]
+        lib.vqb_exchange_bytes.restype = ctypes.c_size_t
         if lib.vqb_abi_version() != ABI_VERSION:
             raise RuntimeError("semi-tts_b200: libvqb200.so ABI %d != expected %d -- rebuild"
                                % (lib.vqb_abi_version(), ABI_VERSION))

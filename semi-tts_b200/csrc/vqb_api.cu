@@ -211,6 +211,16 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
         return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
     const char* pick = getenv("VQB_BWD_KERNEL");                    // developer override: "tf32" = first-generation kernel
     const bool want_tf32 = pick && strcmp(pick, "tf32") == 0;
+    if (a->tail) {
+        const vqb_bwd_tail* tl = a->tail;
+        if (!l2 || want_tf32 || !backward_h2_supported(a))
+            return invalid("vqb_backward: the fused tail needs the L2 score on the vqb_bwd_h2_kernel route (see vqb_backward_kernel_name)");
+        if (!tl->d_flat || !tl->counter) return invalid("vqb_backward: tail.d_flat and tail.counter are required");
+        if (tl->phn_attr ? (tl->n_attr <= 0 || tl->dim_attr <= 0 || tl->dim_attr >= a->dim) : (tl->n_attr != 0 || tl->dim_attr != 0))
+            return invalid("vqb_backward: tail.phn_attr / n_attr / dim_attr are inconsistent");
+        if (tl->world > 1 && (!tl->peer_bufs || tl->rank < 0 || tl->rank >= tl->world || tl->world > VQB_MAX_WORLD))
+            return invalid("vqb_backward: tail.world=%d rank=%d needs peer_bufs and world <= %d", tl->world, tl->rank, VQB_MAX_WORLD);
+    }
     if (!want_tf32 && backward_h2_supported(a)) return launch_backward_h2(a, s);
     if (backward_tensor_supported(a)) return launch_backward_tensor(a, s);
     return launch_backward_simt(a, s);
@@ -225,3 +235,5 @@ extern "C" const char* vqb_backward_kernel_name(const vqb_bwd_args* a) {
     if (backward_tensor_supported(a)) return "vqb_bwd_tc_kernel";
     return "vqb_bwd_simt_kernel";
 }
+
+extern "C" size_t vqb_exchange_bytes(int64_t n_flat, int32_t world) { return vqb::exchange_bytes(n_flat, world); }

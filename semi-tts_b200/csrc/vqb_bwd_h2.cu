@@ -36,6 +36,7 @@
 #include <cuda_fp16.h>
 #include <limits.h>
 #include <math.h>
+#include <stdio.h>
 #include "vqb_common.cuh"
 #include "vqb_tc.cuh"
 
@@ -142,6 +143,10 @@ vqb_bwd_h2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     if (warp == 1) tmem_alloc<128>(tmem_slot);
     for (int i = threadIdx.x; i < 64 * D; i += H_THREADS) sAcc[i] = 0.f;
+    // PDL: the prologue above overlaps the tail of the previous kernel; everything this kernel reads (p_code / idx from
+    // the forward, the table from the assembly before it) is behind this wait.  The tail kernel may queue up now.
+    pdl_launch();
+    pdl_wait();
 
     // ---- E -> E' = E * 2^-g as fp16 hi / lo tiles [64 codes][128 B], 128-byte swizzle (MN-major B of GEMM 1) --------
     float emx = 0.f;
@@ -672,9 +677,136 @@ reduce_partials_h2_kernel(const float* __restrict__ partial, int n_cta, int K, f
 }
 
 // -----------------------------------------------------------------------------------------------------------
+// Fused tail (vqb_bwd_tail, L2 score): partial sums -> table gradient -> parameter gradients -> sum over GPUs.
+//   phase 1 (every block)   same fixed-order sum as reduce_partials_h2_kernel, but the result OVERWRITES dW / colsum
+//   phase 2 (last block)    backward of the table assembly (src/embed.py:109-112): d_learnable | d_proj_w | d_proj_b
+//   phase 3 (last block)    one-shot all-reduce over NVLink peer memory (see vqb.h); the world buffers are added in
+//                           rank order, so every GPU ends with the same bits
+// The last block is elected with a ticket counter (threadfence reduction pattern); no grid-wide barrier, no atomics on
+// data.  Peer waits are bounded (2 s) and trap, so a lost peer fails the launch instead of wedging the GPU.
+// -----------------------------------------------------------------------------------------------------------
+struct TailP {
+    const float* table;       // [K][64]
+    const float* attr;        // [K][A] or NULL
+    float* d_flat;
+    unsigned int* counter;    // [0] ticket, [1] epoch
+    void* const* peer_bufs;   // device array [world]
+    int A, Da, world, rank;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int EXCH_FLAG_BYTES = 128;      // world (<= VQB_MAX_WORLD) x uint32, padded
+
+__global__ void __launch_bounds__(1024)
+bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* __restrict__ dW,
+                   float* __restrict__ colsum, TailP t) {
+    __shared__ float red[32][33];
+    __shared__ unsigned int s_flag;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + tx;
+    pdl_wait();                                                     // the main backward kernel has completed
+    {
+        const int n_kd = K * 64;
+        const int o = blockIdx.x * 32 + tx;                         // output index over [n_kd | K column sums]
+        const float* src = nullptr;
+        float* dst = nullptr;
+        if (o < n_kd) { src = partial + o; dst = dW + o; }
+        else if (o - n_kd < K) { src = partial + 2 * H_KD + (o - n_kd); dst = colsum + (o - n_kd); }
+        float a = 0.f;
+        if (src) {
+#pragma unroll 5
+            for (int cta = ty; cta < n_cta; cta += 32) a += __ldg(src + (size_t)cta * H_PARTIAL_FLOATS);
+        }
+        red[ty][tx] = a;
+        __syncthreads();
+        if (ty == 0 && dst) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += red[j][tx];
+            __stcg(dst, s);
+        }
+    }
+    // ---- elect the last block -------------------------------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = atomicAdd(t.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+
+    // ---- phase 2: parameter gradients from the table gradient (all reads through L2: written by other blocks) ----
+    const int Dl = 64 - t.Da;
+    const int n_l = K * Dl, n_w = t.Da * t.A, n_flat = n_l + n_w + t.Da;
+    const bool exchange = t.world > 1;
+    unsigned int epoch = 0;
+    float* out = t.d_flat;
+    if (exchange) {
+        epoch = t.counter[1] + 1u;
+        out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(t.peer_bufs[t.rank]) + EXCH_FLAG_BYTES) + (size_t)(epoch & 1u) * n_flat;
+    }
+    for (int i = tid; i < n_l; i += 1024) {
+        const int k = i / Dl, d = i - k * Dl;
+        out[i] = fmaf(2.f * __ldg(t.table + k * 64 + d), __ldcg(colsum + k), __ldcg(dW + k * 64 + d));
+    }
+    {
+        const int warp = tid >> 5, lane = tid & 31;                 // one warp per (j, a) / bias output, lanes over codes
+        for (int o = warp; o < n_w + t.Da; o += 32) {
+            const int j = o < n_w ? o / t.A : o - n_w;
+            const int a = o < n_w ? o - j * t.A : -1;
+            float acc = 0.f;
+            for (int k = lane; k < K; k += 32) {
+                const float v = fmaf(2.f * __ldg(t.table + k * 64 + Dl + j), __ldcg(colsum + k), __ldcg(dW + k * 64 + Dl + j));
+                acc += a >= 0 ? v * __ldg(t.attr + (size_t)k * t.A + a) : v;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) out[n_l + o] = acc;
+        }
+    }
+    if (tid == 0) t.counter[0] = 0u;                                // ticket ready for the next call
+    if (!exchange) return;
+
+    // ---- phase 3: one-shot all-reduce over peer memory ---------------------------------------------------------
+    __threadfence_system();                                         // my slot is visible system-wide ...
+    __syncthreads();
+    if (tid < t.world)                                              // ... before any peer sees my flag
+        st_release_sys(reinterpret_cast<unsigned int*>(t.peer_bufs[tid]) + t.rank, epoch);
+    if (tid < t.world) {
+        const unsigned int* mine = reinterpret_cast<const unsigned int*>(t.peer_bufs[t.rank]) + tid;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (globaltimer_ns() - t0 > 2000000000ull) { printf("libvqb200: rank %d timed out waiting for rank %d (epoch %u)\n", t.rank, tid, epoch); __trap(); }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_flat; i += 1024) {
+        float s = 0.f;
+        for (int r = 0; r < t.world; ++r)
+            s += ld_relaxed_sys_f32(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(t.peer_bufs[r]) + EXCH_FLAG_BYTES) +
+                                    (size_t)(epoch & 1u) * n_flat + i);
+        t.d_flat[i] = s;
+    }
+    if (tid == 0) t.counter[1] = epoch;
+}
+
+// -----------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
+
+size_t exchange_bytes(int64_t n_flat, int world) { return (size_t)EXCH_FLAG_BYTES + 2 * (size_t)n_flat * 4 + 0 * (size_t)world; }
 
 bool backward_h2_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
@@ -717,8 +849,23 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
     if ((int)smem > max_optin_smem()) return invalid("vqb_backward: fp16x2 kernel needs %zu B of shared memory", smem);
     VQB_CUDA(cudaFuncSetAttribute(vqb_bwd_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    vqb_bwd_h2_kernel<<<grid, H_THREADS, smem, s>>>(tx, tg, td, p, stage_bytes);
+    VQB_CUDA(launch_pdl(vqb_bwd_h2_kernel, dim3(grid), dim3(H_THREADS), smem, s, tx, tg, td, p, stage_bytes));
     VQB_CHECK_LAUNCH("vqb_bwd_h2_kernel");
+    if (a->tail) {
+        const vqb_bwd_tail* tl = a->tail;
+        TailP t;
+        t.table = a->gather_table; t.attr = tl->phn_attr; t.d_flat = tl->d_flat; t.counter = tl->counter;
+        t.peer_bufs = tl->peer_bufs; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
+        const int n_out = (int)(K * 64 + K);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)ceil_div(n_out, 32)); cfg.blockDim = dim3(32, 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        VQB_CUDA(cudaLaunchKernelEx(&cfg, bwd_tail_h2_kernel, (const float*)p.partial, grid, (int)K, a->d_score_w, a->colsum, t));
+        VQB_CHECK_LAUNCH("bwd_tail_h2_kernel");
+        return VQB_OK;
+    }
     float* dG = l2 ? nullptr : a->d_gather;
     const int n_out = (int)((dG ? 2 : 1) * K * 64 + K);
     reduce_partials_h2_kernel<<<(unsigned)ceil_div(n_out, 32), dim3(32, 32), 0, s>>>(p.partial, grid, (int)K, a->d_score_w, dG,

@@ -30,6 +30,18 @@ void count_launch();                  // host-side tally behind vqb_launch_count
 int sm_count();                       // SMs of the current device (148 on B200)
 int max_optin_smem();                 // bytes of dynamic smem a CTA may opt in to (227 KB)
 
+// launch with the programmatic-stream-serialization attribute (see pdl_wait / pdl_launch below)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -50,6 +62,12 @@ __device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed
+// and its memory is visible (a no-op without the attribute), pdl_launch() lets the successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -84,5 +102,6 @@ int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s);
 bool backward_h2_supported(const vqb_bwd_args* a);
 int backward_h2_workspace(const vqb_bwd_args* a, size_t* bytes);
 int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s);
+size_t exchange_bytes(int64_t n_flat, int world);
 
 }  // namespace vqb

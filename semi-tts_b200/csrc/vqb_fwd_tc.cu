@@ -186,6 +186,11 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[122] = globaltimer_ns();
     constexpr uint32_t IDESC = umma_idesc(2u, BM, BN);
+    // PDL: let the next kernel in the stream begin its prologue; everything below that depends on the kernel BEFORE
+    // this one (the operand / table preparation) sits behind pdl_wait().  x is older than that kernel, so the
+    // producer may fetch its first tile before waiting.
+    pdl_launch();
+    if (warp != 0) pdl_wait();
 
     if (warp == 0) {
         // =============================== TMA producer =====================================================
@@ -200,6 +205,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     tma_load_2d(sX + ((size_t)xs * KB + kb) * XBLK, &tm_x, kb * 32, tile * BM, &x_full[xs]);
                 ++x_it;
                 if (RESIDENT && resident_loaded) continue;
+                if (!resident_loaded) pdl_wait();
                 resident_loaded = true;
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
                     for (int j = 0; j < PIECES; ++j) {
@@ -694,7 +700,8 @@ static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtenso
     auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, 64 + 128 * NWG, smem, s>>>(tx, th, tl, tq, p);
+    // PDL: the prologue (barriers, TMEM, first x tile) overlaps the tail of the operand-preparation kernel before it
+    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG), smem, s, tx, th, tl, tq, p));
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
 }

@@ -16,6 +16,7 @@ assemble_table_kernel(const float* __restrict__ learnable, const float* __restri
                       float* __restrict__ b_lo) {
     const int k = blockIdx.x;
     const int Dl = D - Da;
+    pdl_launch();                                      // the forward kernel may start its prologue (it waits before reading)
     if (k >= K) {                                      // padded operand rows (only launched with a cache)
         for (int d = threadIdx.x; d < D + 32; d += blockDim.x) {
             f_hi[(size_t)k * (D + 32) + d] = d == D ? 1e30f : 0.f;

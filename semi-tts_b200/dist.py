@@ -51,6 +51,47 @@ def _flat_view(grads):
     return torch.as_strided(first, (n,), (1,), first.storage_offset())
 
 
+class PeerExchange:
+    """Peer-mapped exchange buffers for the fused backward tail (include/vqb.h: vqb_bwd_tail): one buffer per rank
+    in torch symmetric memory (CUDA VMM handles shared at rendezvous, mapped over NVLink), zero-filled once; the device
+    array of the world's buffer addresses is what the kernel receives.  No NCCL call is made per step."""
+
+    def __init__(self, group=None, max_floats=1 << 16, device=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise RuntimeError("semi-tts_b200: the fused exchange supports up to 16 GPUs of one NVLink domain")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.max_floats = int(max_floats)
+        nbytes = _lib.load().vqb_exchange_bytes(self.max_floats, self.world)
+        self.buf = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                      # every rank's zero-fill has landed before anyone raises a flag
+
+    def peer_ptrs_dev(self, n_flat):
+        if n_flat > self.max_floats:
+            raise RuntimeError("semi-tts_b200: exchange buffer holds %d floats, the gradient has %d" % (self.max_floats, n_flat))
+        return self.ptrs.data_ptr()
+
+
+def enable_fused_allreduce(module, group=None):
+    """Sum the quantizer's parameter gradients over `group` INSIDE the backward's tail kernel (one-shot all-reduce over
+    NVLink peer memory) instead of an NCCL call after it.  Collective: call on every rank, once, after the process
+    group is up and the module is on its GPU.  allreduce_codebook_grads() then skips gradients that the fused route
+    has already summed (it still reduces them with NCCL whenever a backward took another route)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    n = sum(p.numel() for p in module.parameters() if p.requires_grad)
+    ex = PeerExchange(group, max_floats=max(n, 1024))
+    module.fused_tail.exchange = ex
+    return ex
+
+
 def allreduce_codebook_grads(module, group=None, average=False, include_usage=False):
     """Sum (or average) the quantizer's parameter gradients and its usage histogram across ranks: the only
     exchange of the data-parallel path.  No host synchronisation (CUDA-graph capturable).
@@ -65,7 +106,14 @@ def allreduce_codebook_grads(module, group=None, average=False, include_usage=Fa
     if world == 1:
         return
     grads = [p.grad for p in module.parameters() if p.requires_grad and p.grad is not None]
-    if grads:
+    tail = getattr(module, "fused_tail", None)
+    if grads and tail is not None and tail.exchange is not None and tail.fused:
+        # already summed over the group by the backward's tail kernel
+        if average:
+            flat = _flat_view(grads)
+            for g in ([flat] if flat is not None else grads):
+                g /= world
+    elif grads:
         flat = _flat_view(grads)
         if flat is not None:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)

@@ -72,6 +72,8 @@ class _QuantizerBase(nn.Module):
         # forward on the tcgen05 kernel where the shape allows it (False: exact-fp32 CUDA-core kernel)
         self.tensor_cores = True
         self.last_idx = None
+        # fused backward tail (partial sums + table backward [+ cross-GPU sum] in one kernel); see functional.FusedTail
+        self.fused_tail = VF.FusedTail()
 
     def _init_attr(self, latent_dim, phn_attr_pth, proj_attr):
         self.use_phn_attr = phn_attr_pth is not None and phn_attr_pth != ""
@@ -148,7 +150,7 @@ class L2Embedding(_QuantizerBase):
             enc_embs, self.learnable_table, attr, pw, pb, self.temp, stop_grad=self.stop_grad, skip=skip,
             n_real_rows=first_n_real_mel * S if first_n_real_mel > 0 else 0,
             want_pcode=not self.fused_search, hist=self._hist(enc_embs), want_losses=want_losses,
-            tensor_cores=self.tensor_cores)
+            tensor_cores=self.tensor_cores, tail=self.fused_tail)
         self.last_idx = idx
         return (p_code, new_latent) + self._losses(vq, commit)
 

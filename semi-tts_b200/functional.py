@@ -109,36 +109,73 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
     return p_code, idx, q, sq
 
 
+class FusedTail:
+    """Per-module state of the fused backward tail (include/vqb.h: vqb_bwd_tail): the ticket / epoch words and, in
+    data-parallel runs, the peer-mapped exchange buffers (dist.enable_fused_allreduce).  `fused` records whether the
+    last backward took the fused route (then the parameter gradients are already summed over the group)."""
+
+    def __init__(self):
+        self.counter = None          # uint32 [2] on the module's device
+        self.exchange = None         # dist.PeerExchange or None
+        self.fused = False
+        self.enabled = True
+
+    def counter_for(self, dev):
+        if self.counter is None or self.counter.device != dev:
+            self.counter = torch.zeros(2, device=dev, dtype=torch.int32)
+        return self.counter
+
+
 def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp, p_code, idx, g_p, g_q,
-                  want_dx_buffer, separate_gather, operand_cache=None):
-    """Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None)."""
+                  want_dx_buffer, separate_gather, operand_cache=None, tail=None, phn_attr=None, Da=0):
+    """Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None, flat or None).
+    `flat` is set when the fused tail ran: [d_learnable | d_proj_w | d_proj_b], already summed over the group."""
     lib = _lib.load()
     N, D = x2d.shape
     K = score_w.shape[0]
     dev = x2d.device
-    # one zero-filled buffer (one fill kernel) carved into the accumulation targets
     n_g = K * D if separate_gather else 0
-    zeros = torch.zeros(K * D + n_g + K + 4, device=dev, dtype=torch.float32)
-    d_w = zeros[:K * D].view(K, D)
-    d_gather = zeros[K * D:K * D + n_g].view(K, D) if separate_gather else None
-    colsum = zeros[K * D + n_g:K * D + n_g + K]
-    d_temp = zeros[K * D + n_g + K:K * D + n_g + K + 1] if flags & _lib.TEMP_GRAD else None
-    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if want_dx_buffer else None
     a = _lib.BwdArgs()
     a.struct_size = ctypes.sizeof(_lib.BwdArgs)
     a.flags = flags
     a.n_rows, a.dim, a.n_codes, a.n_real_rows = N, D, K, n_real_rows
     a.x, a.score_w, a.score_b, a.gather_table, a.temp = ptr(x2d), ptr(score_w), ptr(score_b), ptr(gather_table), ptr(temp)
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
-    a.dx, a.d_score_w, a.colsum, a.d_gather, a.d_temp = ptr(dx), ptr(d_w), ptr(colsum), ptr(d_gather), ptr(d_temp)
     a.operand_cache = ptr(operand_cache)
+    use_tail = bool(tail is not None and tail.enabled and (flags & _lib.SCORE_L2) and not separate_gather
+                    and lib.vqb_backward_kernel_name(ctypes.byref(a)) == b"vqb_bwd_h2_kernel")
+    flat = tl = None
+    if use_tail:
+        # the tail overwrites its scratch and outputs: nothing to zero-fill
+        A = phn_attr.shape[1] if phn_attr is not None else 0
+        Da = Da if phn_attr is not None else 0
+        n_flat = K * (D - Da) + Da * A + Da
+        zeros = torch.empty(K * D + K + 4 + n_flat, device=dev, dtype=torch.float32)
+        flat = zeros[K * D + K + 4:]
+        tl = _lib.BwdTail()
+        tl.phn_attr, tl.n_attr, tl.dim_attr, tl.d_flat = ptr(phn_attr), A, Da, ptr(flat)
+        tl.counter = ptr(tail.counter_for(dev))
+        ex = tail.exchange
+        tl.world, tl.rank, tl.peer_bufs = (ex.world, ex.rank, ex.peer_ptrs_dev(n_flat)) if ex is not None else (1, 0, None)
+        a.tail = ctypes.pointer(tl)
+    else:
+        # one zero-filled buffer (one fill kernel) carved into the accumulation targets
+        zeros = torch.zeros(K * D + n_g + K + 4, device=dev, dtype=torch.float32)
+    d_w = zeros[:K * D].view(K, D)
+    d_gather = zeros[K * D:K * D + n_g].view(K, D) if separate_gather else None
+    colsum = zeros[K * D + n_g:K * D + n_g + K]
+    d_temp = zeros[K * D + n_g + K:K * D + n_g + K + 1] if flags & _lib.TEMP_GRAD else None
+    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if want_dx_buffer else None
+    a.dx, a.d_score_w, a.colsum, a.d_gather, a.d_temp = ptr(dx), ptr(d_w), ptr(colsum), ptr(d_gather), ptr(d_temp)
     with torch.cuda.device(dev):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vqb_backward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
         ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8) if nbytes.value else None
         a.workspace, a.workspace_bytes = ptr(ws), nbytes.value
         _lib.check(lib.vqb_backward(ctypes.byref(a), _stream(x2d)))
-    return dx, d_w, colsum, d_gather, d_temp
+    if tail is not None:
+        tail.fused = use_tail
+    return dx, d_w, colsum, d_gather, d_temp, flat
 
 
 def _loss_backward(x2d, table, idx, g_vq, g_commit, dx, dx_accumulate, dtable):
@@ -152,10 +189,11 @@ def _loss_backward(x2d, table, idx, g_vq, g_commit, dx, dx_accumulate, dtable):
 
 class _Cfg:
     """Per-call options (plain Python, not a tensor)."""
-    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores")
+    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores", "tail")
 
     def __init__(self, stop_grad=True, skip=False, n_real_rows=0, want_pcode=True, hist=None,
-                 want_losses=False, tensor_cores=True):
+                 want_losses=False, tensor_cores=True, tail=None):
+        self.tail = tail
         self.stop_grad, self.skip, self.n_real_rows = bool(stop_grad), bool(skip), int(n_real_rows)
         self.want_pcode, self.hist, self.want_losses = bool(want_pcode), hist, bool(want_losses)
         self.tensor_cores = bool(tensor_cores)
@@ -221,17 +259,26 @@ class _VQL2(torch.autograd.Function):
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
         flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TEMP_GRAD if ctx.temp_grad else 0) | \
             (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
-        d_temp = colsum = None
+        d_temp = colsum = flat = None
+        if cfg.tail is not None:
+            cfg.tail.fused = False
         if g_p2 is None and g_q2 is None:
             dx, d_w = None, torch.zeros(K, D, device=dev, dtype=torch.float32)
         elif g_p2 is None and cfg.stop_grad:
             # scatter-only: dx = g_q, the straight-through identity, returned as the same tensor (zero bytes)
-            _, d_w, _, _, _ = _run_backward(flags & ~_lib.TEMP_GRAD, cfg.n_real_rows, x2d, table, enorm, table, temp,
-                                            None, idx, None, g_q2, False, False)
+            _, d_w, _, _, _, _ = _run_backward(flags & ~_lib.TEMP_GRAD, cfg.n_real_rows, x2d, table, enorm, table, temp,
+                                               None, idx, None, g_q2, False, False)
             dx = g_q2
         else:
-            dx, d_w, colsum, _, d_temp = _run_backward(flags, cfg.n_real_rows, x2d, table, enorm, table, temp,
-                                                       p_code, idx, g_p2, g_q2, True, False, ctx.op_cache)
+            dx, d_w, colsum, _, d_temp, flat = _run_backward(
+                flags, cfg.n_real_rows, x2d, table, enorm, table, temp, p_code, idx, g_p2, g_q2, True, False,
+                ctx.op_cache, tail=None if have_loss else cfg.tail, phn_attr=phn_attr, Da=ctx.Da)
+        if flat is not None:
+            # fused tail: table backward (and the sum over GPUs) already done behind the main kernel
+            Da, A = (ctx.Da, phn_attr.shape[1]) if phn_attr is not None else (0, 0)
+            n_l, n_w = K * (D - Da), Da * A
+            return dx.view(B, S, D), flat[:n_l].view(K, D - Da), None, \
+                (flat[n_l:n_l + n_w].view(Da, A) if Da else None), (flat[n_l + n_w:] if Da else None), None, None
         if have_loss:
             if dx is None:
                 dx, acc = torch.empty(N, D, device=dev, dtype=torch.float32), False
@@ -248,10 +295,10 @@ class _VQL2(torch.autograd.Function):
 
 
 def vq_l2(x, learnable_table, phn_attr, proj_w, proj_b, temp, stop_grad=True, skip=False, n_real_rows=0,
-          want_pcode=True, hist=None, want_losses=False, tensor_cores=True):
+          want_pcode=True, hist=None, want_losses=False, tensor_cores=True, tail=None):
     """L2 quantizer (src/embed.py:105-147).
     Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S] int64, vq_loss or None, commit_loss or None)."""
-    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores)
+    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores, tail)
     return _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
 
 
@@ -309,8 +356,8 @@ class _VQLinear(torch.autograd.Function):
         g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
         flags = _fwd_flags(_lib.SCORE_LINEAR, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
-        dx, d_w, colsum, d_tab, _ = _run_backward(flags, 0, x2d, w, None, table, None, p_code, idx, g_p2, g_q2,
-                                                  True, True)
+        dx, d_w, colsum, d_tab, _, _ = _run_backward(flags, 0, x2d, w, None, table, None, p_code, idx, g_p2, g_q2,
+                                                     True, True)
         d_emb, d_pw, d_pb = _table_backward(d_tab, None, None, phn_attr, ctx.Da)
         return dx.view(B, S, D), d_w, colsum, d_emb, None, d_pw, d_pb, None
 

@@ -334,3 +334,50 @@ def test_tensor_core_backward_vs_oracle_and_simt(B, S, first_n):
         assert rel_err(dlt, t64["d_learnable"]) < TOL, tc
         assert rel_err(dpw, t64["d_proj_w"]) < TOL, tc
         assert rel_err(dpb, t64["d_proj_b"]) < TOL, tc
+
+
+@pytest.mark.parametrize("name", ["l2_attr_stopgrad", "l2_attr_first_n", "l2_config1_16x200", "l2_noattr_k37_d32"])
+def test_fused_backward_tail_matches_the_three_kernel_route(name):
+    """vqb_bwd_tail (partial sums + table backward in one kernel behind the main backward, PDL-chained) must give the
+    same parameter gradients as reduce_partials + vqb_table_backward; repeated calls reuse the ticket counter."""
+    g = load_golden(name)
+    m = build_module(g, "l2")
+    m.train(True)
+    x = _cuda(g["x"])
+    gp, gq = _cuda(g["g_p"]), _cuda(g["g_q"])
+    out = {}
+    for fused in (False, True, True):
+        m.fused_tail.enabled = fused
+        for p_ in m.parameters():
+            p_.grad = None
+        xi = x.clone().requires_grad_(True)
+        p_code, q, _, _ = m(xi, int(g["first_n_real_mel"]))
+        torch.autograd.backward([p_code, q], [gp, gq])
+        torch.cuda.synchronize()
+        res = {n: p_.grad.detach().clone() for n, p_ in m.named_parameters() if p_.grad is not None}
+        res["dx"] = xi.grad.clone()
+        if fused and m.fused_tail.fused:
+            for n, v in res.items():
+                assert torch.allclose(v, out[n], rtol=1e-6, atol=1e-7 * float(out[n].abs().max())), n
+        elif fused:
+            assert x.shape[-1] != 64                        # the fused tail rides on the D = 64 tensor-core backward
+        else:
+            out = res
+    if x.shape[-1] == 64:
+        assert m.fused_tail.fused
+        assert int(m.fused_tail.counter[0].item()) == 0     # ticket word handed back
+
+
+def test_fused_exchange_over_peer_memory_two_gpus():
+    """2+ GPUs only: tools/dist_check.py under torchrun (fused one-shot all-reduce vs NCCL, graph replay)."""
+    import json, os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")],
+                       capture_output=True, text=True, timeout=280)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-2000:])
+    rep = json.loads(lines[-1])
+    assert rep["ok"], rep
