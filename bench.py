@@ -164,7 +164,7 @@ def _time_kernels(V, m, sets, iters=24):
     from semi_tts_b200 import functional as VF, _lib
     attr, pw, pb = m.phn_attr.weight, m.proj_attr.weight, m.proj_attr.bias
     table, enorm, _, cache = VF.assemble_table(m.learnable_table, attr, pw, pb, want_cache=True)
-    flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.TENSOR_CORES if m.tensor_cores else 0)
+    flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.TENSOR_CORES if m.tensor_cores else 0)     # no AFTER_ASSEMBLE: launched alone
     outs = [VF._run_forward(flags, s[0].view(N_ROWS, D), table, enorm, table, m.temp, True, None, False) for s in sets]
     stream = torch.cuda.current_stream()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -238,6 +238,8 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     m = V.L2Embedding(K, False, **_codebook_kwargs()).to(dev)
     m.train()
+    if os.environ.get("VQB_NO_TAIL"):
+        m.fused_tail.enabled = False             # developer switch: three-kernel backward tail
     if dist_on and not os.environ.get("VQB_NCCL_ALLREDUCE"):
         V.dist.enable_fused_allreduce(m)         # gradient sum inside the backward's tail kernel (NVLink peer memory)
     # ring of distinct device-resident input sets (weak scaling: every rank owns RING x 64 x 800 frames)

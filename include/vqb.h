@@ -54,6 +54,12 @@ extern "C" {
                                         K <= 64, D in {32,64}; fused mode: L2 score, D in {32,64,128,256}); other
                                         shapes, or a cleared flag, take the exact-fp32 CUDA-core kernel */
 #define VQB_SEARCH_TENSOR   VQB_TENSOR_CORES
+#define VQB_AFTER_ASSEMBLE  0x0040u  /* vqb_forward only: the caller vouches that the operation enqueued on `stream`
+                                        immediately before this call is vqb_assemble_table (the usual sequence).  The
+                                        forward kernel is then launched with programmatic stream serialization: its
+                                        prologue and first x tile overlap the assembly kernel, and it waits
+                                        (griddepcontrol.wait) before touching the table.  Never set it after a memcpy
+                                        or a foreign kernel that produces x. */
 
 VQB_API int vqb_abi_version(void);
 VQB_API const char* vqb_last_error(void);
@@ -209,6 +215,26 @@ VQB_API int vqb_scatter_add(const int64_t* txt, int64_t n_tokens, const float* g
 VQB_API int vqb_loss_backward(const float* x, const float* table, const int64_t* idx, int64_t n_rows,
                       int64_t dim, int64_t n_codes, const float* g_vq, const float* g_commit,
                       float* dx, int dx_accumulate, float* dtable, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Run-length collapse after the quantizer  (replaces VQVAE.mean_forward, src/vqvae.py:218-257: the
+ * `.cpu().tolist()` + per-utterance Python loop that follows the bottleneck on the unpaired branch, :128)
+ *   A segment starts at frame t when idx[t] != idx[t-1] or the open segment already holds
+ *   max_frames_per_phn + 1 frames (:231); segments of code 0 (blank) are dropped (:233,:239); the
+ *   output row of a kept segment is the mean of its frames (:234,:242,:245); rows beyond lens[b] are 0.
+ * ------------------------------------------------------------------------------------------- */
+/* idx[n] = first index of the maximum of p[n,:K]  (p_code.argmax(-1), src/vqvae.py:223) */
+VQB_API int vqb_row_argmax(const float* p, int64_t n_rows, int64_t n_codes, int64_t* idx, void* stream);
+/* Plan: slot_of_row[B,T] (output slot of each frame, -1 = blank), seg_start[B,T] / seg_count[B,T] (first frame and
+ * frame count of kept segment j < lens[b]; the rest of seg_start is unspecified, of seg_count zero), lens[B]. */
+VQB_API int vqb_segment_plan(const int64_t* idx, int64_t n_utts, int64_t n_frames, int64_t max_frames_per_phn,
+                     int32_t* slot_of_row, int32_t* seg_start, int32_t* seg_count, int64_t* lens, void* stream);
+/* out[B,max_len,D]: segment means, zero rows for j >= lens[b] (max_len = max(lens), read back by the host) */
+VQB_API int vqb_segment_mean(const float* latent, const int32_t* seg_start, const int32_t* seg_count, const int64_t* lens,
+                     int64_t n_utts, int64_t n_frames, int64_t dim, int64_t max_len, float* out, void* stream);
+/* dlatent[B,T,D] = g_out[b, slot, :] / count(slot), 0 for blank frames (autograd of the means) */
+VQB_API int vqb_segment_mean_backward(const float* g_out, const int32_t* slot_of_row, const int32_t* seg_count,
+                     int64_t n_utts, int64_t n_frames, int64_t dim, int64_t max_len, float* dlatent, void* stream);
 
 #ifdef __cplusplus
 }

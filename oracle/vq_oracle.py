@@ -307,6 +307,34 @@ def mean_forward(idx, latent, max_frames_per_phn):
     return padded, np.asarray(lens, dtype=np.int64)
 
 
+def mean_forward_segments(idx_row, max_frames_per_phn):
+    """Kept (non-blank) segments [start, end) of one utterance, by the same scan as mean_forward (:228-245)."""
+    seq = list(np.asarray(idx_row).tolist())
+    T = len(seq)
+    last_idx, last_pos, segs = seq[0], 0, []
+    for t, k in enumerate(seq):
+        if last_idx != k or (t - last_pos) > max_frames_per_phn:
+            if last_idx != 0:
+                segs.append((last_pos, t))
+            last_idx, last_pos = k, t
+    if last_idx != 0:
+        segs.append((last_pos, T))
+    return segs
+
+
+def mean_forward_backward(idx, g_out, max_frames_per_phn):
+    """Autograd of mean_forward w.r.t. latent: every frame of a kept segment receives g_out[b, j] / len(segment);
+    blank frames receive 0 (mean(dim=0) backward of :234/:242; the single-frame case :245 is the same formula)."""
+    idx = np.asarray(idx)
+    g_out = np.asarray(g_out)
+    B, T = idx.shape
+    d = np.zeros((B, T, g_out.shape[-1]), g_out.dtype)
+    for b in range(B):
+        for j, (s, e) in enumerate(mean_forward_segments(idx[b], max_frames_per_phn)):
+            d[b, s:e] = g_out[b, j] / (e - s)
+    return d
+
+
 # --------------------------------------------------------------------------------------
 # helpers for parity reports
 # --------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ SKIP = 0x0008
 TEMP_GRAD = 0x0010
 TENSOR_CORES = 0x0020
 SEARCH_TENSOR = TENSOR_CORES
+AFTER_ASSEMBLE = 0x0040
 
 _p = ctypes.c_void_p
 
@@ -45,7 +46,8 @@ class BwdArgs(ctypes.Structure):
 
 EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
-           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward"]
+           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward",
+           "vqb_row_argmax", "vqb_segment_plan", "vqb_segment_mean", "vqb_segment_mean_backward"]
 
 _lib = None
 _lock = threading.Lock()
@@ -78,6 +80,10 @@ def load():
         lib.vqb_inference_gather.argtypes = [_p, i64, _p, i64, i64, _p, _p]
         lib.vqb_scatter_add.argtypes = [_p, i64, _p, i64, i64, _p, _p, _p]
         lib.vqb_loss_backward.argtypes = [_p, _p, _p, i64, i64, i64, _p, _p, _p, ctypes.c_int, _p, _p]
+        lib.vqb_row_argmax.argtypes = [_p, i64, i64, _p, _p]
+        lib.vqb_segment_plan.argtypes = [_p, i64, i64, i64, _p, _p, _p, _p, _p]
+        lib.vqb_segment_mean.argtypes = [_p, _p, _p, _p, i64, i64, i64, i64, _p, _p]
+        lib.vqb_segment_mean_backward.argtypes = [_p, _p, _p, i64, i64, i64, i64, _p, _p]
         lib.vqb_forward_kernel_name.argtypes = [ctypes.POINTER(FwdArgs)]
         lib.vqb_backward_kernel_name.argtypes = [ctypes.POINTER(BwdArgs)]
         for name in EXPORTS:

@@ -143,10 +143,9 @@ vqb_bwd_h2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     if (warp == 1) tmem_alloc<128>(tmem_slot);
     for (int i = threadIdx.x; i < 64 * D; i += H_THREADS) sAcc[i] = 0.f;
-    // PDL: the prologue above overlaps the tail of the previous kernel; everything this kernel reads (p_code / idx from
-    // the forward, the table from the assembly before it) is behind this wait.  The tail kernel may queue up now.
+    // PDL: the fused tail kernel (launched behind this one with programmatic serialization) may queue up now; it waits
+    // for this grid to complete before it reads the partial records.
     pdl_launch();
-    pdl_wait();
 
     // ---- E -> E' = E * 2^-g as fp16 hi / lo tiles [64 codes][128 B], 128-byte swizzle (MN-major B of GEMM 1) --------
     float emx = 0.f;
@@ -757,23 +756,28 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
         epoch = t.counter[1] + 1u;
         out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(t.peer_bufs[t.rank]) + EXCH_FLAG_BYTES) + (size_t)(epoch & 1u) * n_flat;
     }
+    // stage eff = dW + 2 * table * colsum ([K][64]) and the attribute table ([K][A]) in shared memory with one round of
+    // independent, coalesced loads, then form every output from shared memory (one thread per output)
+    extern __shared__ float s_tail[];
+    float* s_eff = s_tail;                                          // [K][64]
+    float* s_attr = s_tail + K * 64;                                // [K][A]
+    for (int i = tid; i < K * 64; i += 1024)
+        s_eff[i] = fmaf(2.f * __ldg(t.table + i), __ldcg(colsum + (i >> 6)), __ldcg(dW + i));
+    for (int i = tid; i < K * t.A; i += 1024) s_attr[i] = __ldg(t.attr + i);
+    __syncthreads();
     for (int i = tid; i < n_l; i += 1024) {
         const int k = i / Dl, d = i - k * Dl;
-        out[i] = fmaf(2.f * __ldg(t.table + k * 64 + d), __ldcg(colsum + k), __ldcg(dW + k * 64 + d));
+        out[i] = s_eff[k * 64 + d];
     }
-    {
-        const int warp = tid >> 5, lane = tid & 31;                 // one warp per (j, a) / bias output, lanes over codes
-        for (int o = warp; o < n_w + t.Da; o += 32) {
-            const int j = o < n_w ? o / t.A : o - n_w;
-            const int a = o < n_w ? o - j * t.A : -1;
-            float acc = 0.f;
-            for (int k = lane; k < K; k += 32) {
-                const float v = fmaf(2.f * __ldg(t.table + k * 64 + Dl + j), __ldcg(colsum + k), __ldcg(dW + k * 64 + Dl + j));
-                acc += a >= 0 ? v * __ldg(t.attr + (size_t)k * t.A + a) : v;
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) out[n_l + o] = acc;
+    for (int o = tid; o < n_w + t.Da; o += 1024) {                  // d_proj_w[j][a] = sum_k eff[k][Dl+j] attr[k][a]; d_proj_b[j]
+        const int j = o < n_w ? o / t.A : o - n_w;
+        const int a = o < n_w ? o - j * t.A : -1;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float v = s_eff[k * 64 + Dl + j];
+            acc = a >= 0 ? fmaf(v, s_attr[k * t.A + a], acc) : acc + v;
         }
+        out[n_l + o] = acc;
     }
     if (tid == 0) t.counter[0] = 0u;                                // ticket ready for the next call
     if (!exchange) return;
@@ -791,12 +795,29 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
         }
     }
     __syncthreads();
-    for (int i = tid; i < n_flat; i += 1024) {
-        float s = 0.f;
-        for (int r = 0; r < t.world; ++r)
-            s += ld_relaxed_sys_f32(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(t.peer_bufs[r]) + EXCH_FLAG_BYTES) +
-                                    (size_t)(epoch & 1u) * n_flat + i);
-        t.d_flat[i] = s;
+    // all peers' values of an element are requested before the first one is consumed (one NVLink round trip per element,
+    // not `world` of them); the sum itself runs in rank order on every GPU
+    __shared__ const float* s_slot[VQB_MAX_WORLD];
+    if (tid < t.world)
+        s_slot[tid] = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(t.peer_bufs[tid]) + EXCH_FLAG_BYTES) +
+                      (size_t)(epoch & 1u) * n_flat;
+    __syncthreads();
+    for (int i0 = tid; i0 < n_flat; i0 += 2 * 1024) {
+        const int i1 = i0 + 1024;
+        float v0[VQB_MAX_WORLD], v1[VQB_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < VQB_MAX_WORLD; ++r) {
+            v0[r] = 0.f; v1[r] = 0.f;
+            if (r < t.world) {
+                v0[r] = ld_relaxed_sys_f32(s_slot[r] + i0);
+                if (i1 < n_flat) v1[r] = ld_relaxed_sys_f32(s_slot[r] + i1);
+            }
+        }
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < VQB_MAX_WORLD; ++r) if (r < t.world) { a0 += v0[r]; a1 += v1[r]; }
+        t.d_flat[i0] = a0;
+        if (i1 < n_flat) t.d_flat[i1] = a1;
     }
     if (tid == 0) t.counter[1] = epoch;
 }
@@ -849,7 +870,9 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
     if ((int)smem > max_optin_smem()) return invalid("vqb_backward: fp16x2 kernel needs %zu B of shared memory", smem);
     VQB_CUDA(cudaFuncSetAttribute(vqb_bwd_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    VQB_CUDA(launch_pdl(vqb_bwd_h2_kernel, dim3(grid), dim3(H_THREADS), smem, s, tx, tg, td, p, stage_bytes));
+    // a plain stream-ordered launch: what precedes the backward in the stream (the producer of g_p / g_q, possibly a
+    // copy) is not ours to overlap.  The kernel still releases its own successor early (the fused tail).
+    vqb_bwd_h2_kernel<<<grid, H_THREADS, smem, s>>>(tx, tg, td, p, stage_bytes);
     VQB_CHECK_LAUNCH("vqb_bwd_h2_kernel");
     if (a->tail) {
         const vqb_bwd_tail* tl = a->tail;
@@ -858,10 +881,11 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
         t.peer_bufs = tl->peer_bufs; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
         const int n_out = (int)(K * 64 + K);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)ceil_div(n_out, 32)); cfg.blockDim = dim3(32, 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cfg.gridDim = dim3((unsigned)ceil_div(n_out, 32)); cfg.blockDim = dim3(32, 32); cfg.stream = s;
+        cfg.dynamicSmemBytes = (size_t)K * (64 + t.A) * 4;          // <= 64 * (64 + A) * 4: under 48 KB for A <= 128
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.attrs = at; cfg.numAttrs = getenv("VQB_NO_PDL") ? 0 : 1;
         VQB_CUDA(cudaLaunchKernelEx(&cfg, bwd_tail_h2_kernel, (const float*)p.partial, grid, (int)K, a->d_score_w, a->colsum, t));
         VQB_CHECK_LAUNCH("bwd_tail_h2_kernel");
         return VQB_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include "vqb.h"
 
 namespace vqb {
@@ -38,7 +39,8 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    static const bool off = getenv("VQB_NO_PDL") != nullptr;       // developer switch: plain stream-ordered launches
+    cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -692,7 +692,7 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
 
 template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
-                     cudaStream_t s) {
+                     cudaStream_t s, bool pdl) {
     constexpr int XLS = NWG == 2 ? 1 : XS;
     const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + XBLK + (size_t)BS * BN * 128 +
                         (PCODE ? NWG * BM * 65 * 4 : 16 * BM * 8) + 1024 + 256 + 2 * BM * 4;
@@ -700,8 +700,10 @@ static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtenso
     auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    // PDL: the prologue (barriers, TMEM, first x tile) overlaps the tail of the operand-preparation kernel before it
-    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG), smem, s, tx, th, tl, tq, p));
+    // PDL (only when the caller vouches for the predecessor, VQB_AFTER_ASSEMBLE, or when this call itself has just
+    // launched build_operands_kernel): the prologue and the first x tile overlap the operand-preparation kernel
+    if (pdl) VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG), smem, s, tx, th, tl, tq, p));
+    else kern<<<grid, 64 + 128 * NWG, smem, s>>>(tx, th, tl, tq, p);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
 }
@@ -758,25 +760,26 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
     p.flags = a->flags;
 
+    const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     //                      KB  BN  XS BS PASSES RESIDENT PCODE
     if (mode == TC_PCODE) {
-        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true, 2>(tx, th, tl, tq, p, s);
-        return launch_tc<2, 64, 2, 5, 3, true, true, 2>(tx, th, tl, tq, p, s);
+        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true, 2>(tx, th, tl, tq, p, s, pdl);
+        return launch_tc<2, 64, 2, 5, 3, true, true, 2>(tx, th, tl, tq, p, s, pdl);
     }
     if (mode == TC_SEARCH3) {
         if (K <= 128) {                                            // whole codebook resident in shared memory
-            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, tq, p, s);
-            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, tq, p, s);
+            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, tq, p, s, pdl);
+            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, tq, p, s, pdl);
         }
-        if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s);
-        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s);
-        return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s);
+        if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
+        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
+        return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
     }
     switch (D) {
-        case 32:  return launch_tc<1, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s);
-        case 64:  return launch_tc<2, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s);
-        case 128: return launch_tc<4, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s);
-        default:  return launch_tc<8, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s);
+        case 32:  return launch_tc<1, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        case 64:  return launch_tc<2, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        case 128: return launch_tc<4, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        default:  return launch_tc<8, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
     }
 }
 

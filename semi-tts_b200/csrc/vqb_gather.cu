@@ -136,6 +136,190 @@ static int launch_scatter_v(const long long* idx, long long n, const float* g, i
     return VQB_OK;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Large codebooks (the table does not fit per-warp shared-memory copies): sort-free segmented sum.
+//   rank_kernel      rank[r] = position of row r among the rows of its code (atomic ticket per code, which also IS
+//                    the usage histogram of this call);  warp-aggregated: lanes of a warp that hit the same code
+//                    take one atomic between them
+//   offsets_kernel   exclusive scan of the per-code counts -> first slot of each code in the permutation, and the
+//                    work list: one item per (code, chunk of <= CHUNK rows)
+//   permute_kernel   perm[offset[idx[r]] + rank[r]] = r
+//   segsum_kernel    one warp per work item: gathers its rows (whole 16-byte-vectorised rows, several in flight),
+//                    adds them in registers and writes the code's row of dtable once -- a plain store when the code
+//                    has a single chunk, one red.global.add.v4 per chunk otherwise.  No atomics per input row.
+// HBM traffic: g once (4D B/row) + idx twice + 8 B/row of rank/perm, against 4D + 8 algorithmic bytes.
+// The order of the rows inside a code follows the atomic tickets, so the fp32 sums of this path are not
+// bit-reproducible from run to run (the small-codebook path above and the fused backward are).
+// -------------------------------------------------------------------------------------------------
+constexpr int SEG_CHUNK = 128;
+
+__global__ void __launch_bounds__(256)
+rank_kernel(const long long* __restrict__ idx, long long n, int K, int* __restrict__ cnt, int* __restrict__ rank) {
+    const int lane = threadIdx.x & 31;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n + 31; r += (long long)gridDim.x * blockDim.x) {
+        const bool in = r < n;
+        long long k = in ? idx[r] : -1;
+        if (in) k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+        // warp-aggregated ticket: lanes holding the same code form a group; its leader takes `size` tickets at once
+        const unsigned peers = __match_any_sync(0xffffffffu, (int)k);
+        if (in) {
+            const int leader = __ffs(peers) - 1;
+            const int pos = __popc(peers & ((1u << lane) - 1u));
+            int base = 0;
+            if (lane == leader) base = atomicAdd(cnt + k, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            rank[r] = base + pos;
+        }
+    }
+}
+
+// single CTA: offs[k] = sum_{j<k} cnt[j];  item_off[k] = sum_{j<k} ceil(cnt[j] / CHUNK) (first work item of code k);
+// n_items[0] = number of work items
+__global__ void __launch_bounds__(1024)
+offsets_kernel(const int* __restrict__ cnt, int K, int* __restrict__ offs, int* __restrict__ item_off,
+               int* __restrict__ n_items, unsigned long long* __restrict__ hist) {
+    __shared__ int s_w[32], s_w2[32];
+    __shared__ int s_carry[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (int k0 = 0; k0 < K; k0 += 1024) {
+        const int k = k0 + threadIdx.x;
+        const int c = k < K ? cnt[k] : 0;
+        const int m = (c + SEG_CHUNK - 1) / SEG_CHUNK;
+        int a = c, b = m;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) { a += x; b += y; }
+        }
+        if (lane == 31) { s_w[w] = a; s_w2[w] = b; }
+        __syncthreads();
+        int ba = s_carry[0], bb = s_carry[1];
+        for (int i = 0; i < w; ++i) { ba += s_w[i]; bb += s_w2[i]; }
+        const int off = ba + a - c, it0 = bb + b - m;            // exclusive
+        if (k < K) {
+            offs[k] = off;
+            item_off[k] = it0;
+            if (hist && c) atomicAdd(hist + k, (unsigned long long)c);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry[0] = ba + a; s_carry[1] = bb + b; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_items[0] = s_carry[1];
+}
+
+__global__ void __launch_bounds__(256)
+permute_kernel(const long long* __restrict__ idx, long long n, int K, const int* __restrict__ offs,
+               const int* __restrict__ rank, int* __restrict__ perm) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        long long k = idx[r];
+        k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+        perm[__ldg(offs + k) + rank[r]] = (int)r;
+    }
+}
+
+// LPR lanes share one row (LPR * VPL float4 >= D/4); 32 / LPR rows are in flight per warp step, U steps unrolled
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+segsum_kernel(const float* __restrict__ g, const int* __restrict__ perm, const int* __restrict__ cnt,
+              const int* __restrict__ offs, const int* __restrict__ item_off, const int* __restrict__ n_items,
+              int K, int D, float* __restrict__ dtable) {
+    constexpr int RPW = 32 / LPR;                  // rows per warp step
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, col = lane % LPR;
+    const int D4 = D >> 2;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int total = __ldg(n_items);
+    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warps) {
+        // code of this item: the last k with item_off[k] <= item (codes without rows share their successor's offset)
+        int lo = 0, hi = K - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(item_off + mid) <= item) lo = mid; else hi = mid - 1;
+        }
+        const int k = lo;
+        const int code_off = __ldg(offs + k), code_cnt = __ldg(cnt + k);
+        const int first = code_off + (item - __ldg(item_off + k)) * SEG_CHUNK;
+        const int len = min(SEG_CHUNK, code_off + code_cnt - first);
+        float4 acc[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i0 = 0; i0 < len; i0 += U * RPW) {
+            int row[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * RPW + sub;
+                row[u] = i < len ? __ldg(perm + first + i) : -1;
+            }
+            float4 x[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = col + LPR * v;
+                    x[u][v] = (row[u] >= 0 && c < D4) ? ldg4_stream(g + (size_t)row[u] * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) { acc[v].x += x[u][v].x; acc[v].y += x[u][v].y; acc[v].z += x[u][v].z; acc[v].w += x[u][v].w; }
+        }
+        // fold the row groups of the warp together
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o); acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+                acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o); acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+            }
+        if (sub == 0) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = col + LPR * v;
+                if (c < D4) {
+                    float* dst = dtable + (size_t)k * D + 4 * c;
+                    red_add_v4(dst, acc[v]);          // dtable is an accumulation target (+=) in every route
+                }
+            }
+        }
+    }
+}
+
+static int launch_scatter_sorted(const long long* idx, long long n, const float* g, int K, int D, float* dtable,
+                                 unsigned long long* hist, cudaStream_t s) {
+    // stream-ordered scratch (returned to the pool behind the last kernel): cnt[K] | offs[K] | n_items[4] | rank[n] |
+    // perm[n] | item_off[K];  at most m = n / CHUNK + K work items
+    const size_t m = (size_t)(n / SEG_CHUNK) + (size_t)K + 1;
+    const size_t ints = 3 * (size_t)K + 4 + 2 * (size_t)n;
+    int* ws = nullptr;
+    VQB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), ints * sizeof(int), s));
+    int* cnt = ws; int* offs = cnt + K; int* n_items = offs + K; int* rank = n_items + 4; int* perm = rank + n;
+    int* item_off = perm + n;
+    VQB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)K * sizeof(int), s));
+    const long long gcap = (long long)sm_count() * 16;
+    const unsigned grid = (unsigned)(ceil_div(n, 256) < gcap ? ceil_div(n, 256) : gcap);
+    rank_kernel<<<grid, 256, 0, s>>>(idx, n, K, cnt, rank);
+    VQB_CHECK_LAUNCH("rank_kernel");
+    offsets_kernel<<<1, 1024, 0, s>>>(cnt, K, offs, item_off, n_items, hist);
+    VQB_CHECK_LAUNCH("offsets_kernel");
+    permute_kernel<<<grid, 256, 0, s>>>(idx, n, K, offs, rank, perm);
+    VQB_CHECK_LAUNCH("permute_kernel");
+    const long long scap = (long long)sm_count() * 8;
+    const unsigned sgrid = (unsigned)(ceil_div((long long)m, 8) < scap ? ceil_div((long long)m, 8) : scap);
+    const int D4 = D / 4;
+#define VQB_SS(L, V) segsum_kernel<L, V><<<sgrid, 256, 0, s>>>(g, perm, cnt, offs, item_off, n_items, K, D, dtable)
+    if (D4 <= 4) VQB_SS(4, 1); else if (D4 <= 8) VQB_SS(8, 1); else if (D4 <= 16) VQB_SS(16, 1);
+    else if (D4 <= 32) VQB_SS(32, 1); else if (D4 <= 64) VQB_SS(32, 2); else VQB_SS(32, 4);
+#undef VQB_SS
+    VQB_CHECK_LAUNCH("segsum_kernel");
+    VQB_CUDA(cudaFreeAsync(ws, s));
+    return VQB_OK;
+}
+
 int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K, int64_t D, float* dtable,
                        int64_t* hist, cudaStream_t s) {
     if (n == 0) return VQB_OK;
@@ -147,6 +331,11 @@ int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K,
     if (g && per_warp * wpb <= 96 * 1024)
         return launch_scatter_v<true>((const long long*)idx, n, g, (int)K, (int)D, dtable,
                                       (unsigned long long*)hist, wpb, per_warp * wpb, s);
+    // large tables: ticket + permutation + one gather-sum per code (no atomics per row).  Short inputs stay on the
+    // direct 128-bit global reductions: four extra launches would cost more than they save.
+    static const bool direct = getenv("VQB_SCATTER_DIRECT") != nullptr;       // developer switch (A/B)
+    if (g && !direct && n >= 65536)
+        return launch_scatter_sorted((const long long*)idx, n, g, (int)K, (int)D, dtable, (unsigned long long*)hist, s);
     return launch_scatter_v<false>((const long long*)idx, n, g, (int)K, (int)D, dtable,
                                    (unsigned long long*)hist, 8, 0, s);
 }

@@ -115,10 +115,11 @@ class FusedTail:
     last backward took the fused route (then the parameter gradients are already summed over the group)."""
 
     def __init__(self):
+        import os
         self.counter = None          # uint32 [2] on the module's device
         self.exchange = None         # dist.PeerExchange or None
         self.fused = False
-        self.enabled = True
+        self.enabled = not os.environ.get("VQB_NO_TAIL_TEST")     # developer switch
 
     def counter_for(self, dev):
         if self.counter is None or self.counter.device != dev:
@@ -229,6 +230,9 @@ class _VQL2(torch.autograd.Function):
             raise RuntimeError("semi-tts_b200: the ST-onehot variant (stop_grad=False) needs p_code")
         flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         temp_c = _c(temp.detach())
+        if want_cache:
+            # only kernels (the assembly above, at most a one-element fill) sit between here and the forward kernel
+            flags |= _lib.AFTER_ASSEMBLE
         p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
                                           cfg.want_losses, tbf, None, cache)
         ctx.op_cache = cache

@@ -381,3 +381,29 @@ def test_fused_exchange_over_peer_memory_two_gpus():
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-2000:])
     rep = json.loads(lines[-1])
     assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("N,K,D,skew", [(100037, 300, 64, False), (70000, 5000, 256, False), (65536, 1000, 20, True),
+                                        (131072, 8192, 64, False), (90001, 97, 128, True)])
+def test_large_table_scatter_add_sorted_path(N, K, D, skew):
+    """vqb_scatter_add on tables too large for per-warp shared-memory copies (ticket + permutation + per-code
+    gather-sum, no atomics per row): dtable += scatter(idx, g) and the fused usage histogram, against numpy."""
+    import ctypes
+    import semi_tts_b200 as V
+    lib = V._lib.load()
+    rng = np.random.default_rng(N + K)
+    idx = rng.integers(0, K, N)
+    if skew:
+        idx[rng.random(N) < 0.5] = 7                                    # one code owns half the rows (many chunks)
+    g = rng.standard_normal((N, D)).astype(np.float32)
+    base = rng.standard_normal((K, D)).astype(np.float32)               # the target is accumulated into, not overwritten
+    want = base.astype(np.float64)
+    np.add.at(want, idx, g.astype(np.float64))
+    dt = torch.from_numpy(base.copy()).cuda()
+    hist = torch.full((K,), 5, dtype=torch.int64, device="cuda")
+    ti, tg = torch.from_numpy(idx).cuda(), torch.from_numpy(g).cuda()
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    V._lib.check(lib.vqb_scatter_add(ti.data_ptr(), N, tg.data_ptr(), K, D, dt.data_ptr(), hist.data_ptr(), sp))
+    torch.cuda.synchronize()
+    assert rel_err(dt.cpu().numpy(), want) < 1e-6
+    assert np.array_equal(hist.cpu().numpy() - 5, np.bincount(idx, minlength=K))

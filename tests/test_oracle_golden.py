@@ -147,3 +147,22 @@ def test_torch_port_matches_reference(name):
     assert rel_err(pw.grad.numpy(), g["grad.proj_attr.weight"]) < 1e-6
     if "grad.temp" in g:
         assert abs(temp.grad.item() - g["grad.temp"][0]) < 1e-4 * max(1, abs(g["grad.temp"][0]))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_mean_forward_segments_and_backward_are_consistent(tag):
+    """The segment list reproduces mean_forward's output, and the restated backward matches torch autograd of it."""
+    import torch
+    g = load_golden("mean_forward_" + tag)
+    idx, lat, mfp = g["idx"], g["latent"], int(g["max_frames_per_phn"])
+    lt = torch.from_numpy(lat.astype(np.float64)).requires_grad_(True)
+    rows = []
+    for b in range(idx.shape[0]):
+        segs = O.mean_forward_segments(idx[b], mfp)
+        assert len(segs) == int(g["lens"][b])
+        rows.append(torch.stack([lt[b, s:e].mean(0) for s, e in segs]))
+    out = torch.nn.utils.rnn.pad_sequence(rows, batch_first=True)
+    assert np.allclose(out.detach().numpy(), g["out"], atol=1e-6)
+    go = np.random.default_rng(7).standard_normal(out.shape)
+    out.backward(torch.from_numpy(go))
+    assert np.allclose(lt.grad.numpy(), O.mean_forward_backward(idx, go, mfp), atol=1e-12)
