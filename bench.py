@@ -199,16 +199,23 @@ def _time_kernels(V, m, sets, iters=24):
         b.workspace, b.workspace_bytes = wsb.data_ptr(), nb.value
         ba.append(b); keep.append((dx, dw, cs, wsb))
     sp = ctypes.c_void_p(stream.cuda_stream)
+    # the library records these events on the launch stream right before / after the dominant kernel of each call
+    # (vqb_debug_set_kernel_events), so helper kernels of the same call are outside the measured interval
+    for e in ev:
+        e.record(stream)
+    torch.cuda.synchronize()
+    lib.vqb_debug_set_kernel_events.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.vqb_debug_set_kernel_events.restype = None
     for i in range(iters + 4):
         j = i % len(sets)
-        ev[0].record(stream)
+        lib.vqb_debug_set_kernel_events(ctypes.c_void_p(ev[0].cuda_event), ctypes.c_void_p(ev[1].cuda_event))
         _lib.check(lib.vqb_forward(ctypes.byref(fa[j]), sp))
-        ev[1].record(stream)
+        lib.vqb_debug_set_kernel_events(ctypes.c_void_p(ev[2].cuda_event), ctypes.c_void_p(ev[3].cuda_event))
         _lib.check(lib.vqb_backward(ctypes.byref(ba[j]), sp))
-        ev[2].record(stream)
+        lib.vqb_debug_set_kernel_events(None, None)
         torch.cuda.synchronize()
         if i >= 4:
-            fwd_ms.append(ev[0].elapsed_time(ev[1])); bwd_ms.append(ev[1].elapsed_time(ev[2]))
+            fwd_ms.append(ev[0].elapsed_time(ev[1])); bwd_ms.append(ev[2].elapsed_time(ev[3]))
     kf = lib.vqb_forward_kernel_name(ctypes.byref(fa[0])).decode()
     kb = lib.vqb_backward_kernel_name(ctypes.byref(ba[0])).decode()
     return statistics.mean(fwd_ms), statistics.mean(bwd_ms), kf, kb
@@ -426,9 +433,9 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": _ncu_traffic(dom[0]), "peak_source": peak_src,
                              "kernel_ms": {kf: fwd_ms, kb_: bwd_ms},
-                             "note": "kernel_ms = CUDA-event time of one vqb_forward / vqb_backward C-ABI call on the launching "
-                                     "stream (the named kernel; the backward call also runs its fixed-order partial-sum "
-                                     "reduction kernel), averaged over ring-rotated inputs (> L2)",
+                             "note": "kernel_ms = CUDA-event time of the named kernel alone: the library records the two events on "
+                                     "the launch stream immediately around that launch (vqb_debug_set_kernel_events); "
+                                     "averaged over ring-rotated inputs (> L2)",
                              "algorithmic_bytes": {"fwd": fwd_bytes, "bwd": bwd_bytes}},
                 "cpu_baseline": {"value": cpu_rate, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d full steps of the same workload on the host (oracle/torch_port.py)" % cpu_done},

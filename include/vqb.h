@@ -204,9 +204,14 @@ VQB_API const char* vqb_backward_kernel_name(const vqb_bwd_args* args);
 VQB_API int vqb_inference_gather(const int64_t* txt, int64_t n_tokens, const float* table, int64_t n_codes,
                          int64_t dim, float* out, void* stream);
 
-/* dtable[txt[m],:] += g[m,:]  (autograd of the gather; F.embedding backward) */
+/* dtable[txt[m],:] += g[m,:]; hist[txt[m]] += 1 (hist may be NULL)  (autograd of the gather: F.embedding backward,
+ * src/embed.py:134; histogram semantics of bin/train_vqvae.py:256-261).
+ * Small tables (8 copies fit in shared memory) use per-warp private accumulators; large tables with at least 64 Ki
+ * tokens use a ticket + permutation + per-code gather-sum that needs vqb_scatter_workspace() bytes of scratch (without
+ * it, or below that size, rows go to the table by 128-bit global reductions). */
+VQB_API int vqb_scatter_workspace(int64_t n_tokens, int64_t n_codes, int64_t dim, size_t* bytes);
 VQB_API int vqb_scatter_add(const int64_t* txt, int64_t n_tokens, const float* g, int64_t n_codes,
-                    int64_t dim, float* dtable, int64_t* hist, void* stream);
+                    int64_t dim, float* dtable, int64_t* hist, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss extensions (NO reference arithmetic; van den Oord et al. 2017): backward of
  *   vq_loss = commit_loss = mean((x - E[idx])^2):

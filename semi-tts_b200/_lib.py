@@ -46,7 +46,7 @@ class BwdArgs(ctypes.Structure):
 
 EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
-           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_loss_backward",
+           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_scatter_workspace", "vqb_loss_backward",
            "vqb_row_argmax", "vqb_segment_plan", "vqb_segment_mean", "vqb_segment_mean_backward"]
 
 _lib = None
@@ -78,7 +78,8 @@ def load():
         lib.vqb_backward_workspace.argtypes = [ctypes.POINTER(BwdArgs), ctypes.POINTER(sz)]
         lib.vqb_backward.argtypes = [ctypes.POINTER(BwdArgs), _p]
         lib.vqb_inference_gather.argtypes = [_p, i64, _p, i64, i64, _p, _p]
-        lib.vqb_scatter_add.argtypes = [_p, i64, _p, i64, i64, _p, _p, _p]
+        lib.vqb_scatter_add.argtypes = [_p, i64, _p, i64, i64, _p, _p, _p, sz, _p]
+        lib.vqb_scatter_workspace.argtypes = [i64, i64, i64, ctypes.POINTER(sz)]
         lib.vqb_loss_backward.argtypes = [_p, _p, _p, i64, i64, i64, _p, _p, _p, ctypes.c_int, _p, _p]
         lib.vqb_row_argmax.argtypes = [_p, i64, i64, _p, _p]
         lib.vqb_segment_plan.argtypes = [_p, i64, i64, i64, _p, _p, _p, _p, _p]

@@ -89,6 +89,17 @@ namespace vqb {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }
+namespace vqb {
+// measurement hook: a pair of CUDA events recorded on the launch stream immediately before / after the DOMINANT kernel
+// of the next forward / backward / scatter call (not its helper kernels), so that a caller can time that kernel alone
+static cudaEvent_t g_kev0 = nullptr, g_kev1 = nullptr;
+void kernel_event_begin(cudaStream_t s) { if (g_kev0) cudaEventRecord(g_kev0, s); }
+void kernel_event_end(cudaStream_t s) { if (g_kev1) cudaEventRecord(g_kev1, s); }
+}
+extern "C" __attribute__((visibility("default"))) void vqb_debug_set_kernel_events(void* ev_start, void* ev_stop) {
+    vqb::g_kev0 = (cudaEvent_t)ev_start; vqb::g_kev1 = (cudaEvent_t)ev_stop;
+}
+
 extern "C" uint64_t vqb_launch_count(void) { return vqb::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
@@ -168,6 +179,7 @@ extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
         backward_tensor_workspace(a, &b1);
         backward_h2_workspace(a, &b2);
         *bytes = b1 > b2 ? b1 : b2;
+        if (!a->g_p && (a->flags & VQB_STOP_GRAD)) *bytes = scatter_workspace_bytes(a->n_rows, a->n_codes, a->dim);
     }
     return VQB_OK;
 }
@@ -198,7 +210,7 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
         float* dst = l2 ? a->d_score_w : a->d_gather;
         if (!dst) return invalid("vqb_backward: the scatter destination (d_score_w for L2, d_gather for LINEAR) is NULL");
         if (!aligned16(a->g_q) || !aligned16(dst)) return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
-        return launch_scatter_add(a->idx, a->n_rows, a->g_q, a->n_codes, a->dim, dst, nullptr, s);
+        return launch_scatter_add(a->idx, a->n_rows, a->g_q, a->n_codes, a->dim, dst, nullptr, a->workspace, a->workspace_bytes, s);
     }
 
     if (!a->x || !a->score_w || !a->gather_table || !a->p_code || !a->dx || !a->d_score_w || !a->colsum)

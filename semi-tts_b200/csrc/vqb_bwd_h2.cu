@@ -601,6 +601,9 @@ vqb_bwd_h2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             VQB_HTL(11);
         }
         if (r == 0) tma_store_wait_all();
+        // every row thread must be behind r == 0's wait before the dx staging tile (sX) is reused below -- without the
+        // scatter warps (skip branch) barrier 3 is not taken, so the row group synchronises on its own barrier
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         if (do_scatter) asm volatile("bar.sync 3, 192;" ::: "memory");   // both scatter warps have finished their last tile
         VQB_HTL(12);
 
@@ -872,7 +875,9 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     // a plain stream-ordered launch: what precedes the backward in the stream (the producer of g_p / g_q, possibly a
     // copy) is not ours to overlap.  The kernel still releases its own successor early (the fused tail).
+    kernel_event_begin(s);
     vqb_bwd_h2_kernel<<<grid, H_THREADS, smem, s>>>(tx, tg, td, p, stage_bytes);
+    kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_h2_kernel");
     if (a->tail) {
         const vqb_bwd_tail* tl = a->tail;

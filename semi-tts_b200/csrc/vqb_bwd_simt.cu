@@ -305,7 +305,9 @@ static int launch_bwd(BwdP& p, cudaStream_t s) {
     VQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = (int)min((int64_t)p.ntiles, (int64_t)sm_count() * per_sm);
+    kernel_event_begin(s);
     kern<<<grid, BT, smem, s>>>(p);
+    kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_simt_kernel");
     return VQB_OK;
 }

@@ -511,7 +511,9 @@ int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s) {
     auto kern = vqb_bwd_tc_kernel<KB>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    kernel_event_begin(s);
     kern<<<grid, BWD_THREADS, smem, s>>>(tx, tg, th, tl, p);
+    kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_tc_kernel");
     const int n_blocks = (int)ceil_div(K * 64, 64) + 1;
     reduce_partials_kernel<<<n_blocks, dim3(64, 16), 0, s>>>(p.partial, grid, (int)K, (a->flags & VQB_SCORE_L2) ? 1 : 0,

@@ -19,7 +19,9 @@ int invalid(const char* fmt, ...);
         if (e_ != cudaSuccess) return ::vqb::cuda_fail(e_, #call);  \
     } while (0)
 
-void count_launch();                  // host-side tally behind vqb_launch_count()
+void count_launch();
+void kernel_event_begin(cudaStream_t s);   // developer hook (vqb_debug_set_kernel_events): events around the dominant kernel
+void kernel_event_end(cudaStream_t s);                  // host-side tally behind vqb_launch_count()
 
 #define VQB_CHECK_LAUNCH(name)                                      \
     do {                                                            \
@@ -92,7 +94,8 @@ static inline size_t cache_lo_bytes(int64_t K, int64_t D) { return ((size_t)cach
 int launch_forward_simt(const vqb_fwd_args* a, cudaStream_t s);
 int launch_backward_simt(const vqb_bwd_args* a, cudaStream_t s);
 int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K, int64_t D,
-                       float* dtable, int64_t* hist, cudaStream_t s);
+                       float* dtable, int64_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t scatter_workspace_bytes(int64_t n, int64_t K, int64_t D);
 bool forward_tensor_supported(const vqb_fwd_args* a);
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
 int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);

@@ -270,7 +270,9 @@ static int launch_small(const FwdP& p, cudaStream_t s) {
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: D=%d needs %zu B of shared memory", p.D, smem);
     auto kern = vqb_fwd_simt_small_kernel<KC, L2>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel_event_begin(s);
     kern<<<(unsigned)ceil_div(p.N, TILE), TILE, smem, s>>>(p);
+    kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_fwd_simt_small_kernel");
     return VQB_OK;
 }
@@ -282,7 +284,9 @@ static int launch_generic(const FwdP& p, cudaStream_t s) {
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: D=%d needs %zu B of shared memory", p.D, smem);
     auto kern = vqb_fwd_simt_generic_kernel<KC, L2>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel_event_begin(s);
     kern<<<(unsigned)ceil_div(p.N, TILE), TILE, smem, s>>>(p);
+    kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_fwd_simt_generic_kernel");
     return VQB_OK;
 }

@@ -702,8 +702,10 @@ static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtenso
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     // PDL (only when the caller vouches for the predecessor, VQB_AFTER_ASSEMBLE, or when this call itself has just
     // launched build_operands_kernel): the prologue and the first x tile overlap the operand-preparation kernel
+    kernel_event_begin(s);
     if (pdl) VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG), smem, s, tx, th, tl, tq, p));
     else kern<<<grid, 64 + 128 * NWG, smem, s>>>(tx, th, tl, tq, p);
+    kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
 }

@@ -157,6 +157,7 @@ constexpr int SEG_CHUNK = 128;
 __global__ void __launch_bounds__(256)
 rank_kernel(const long long* __restrict__ idx, long long n, int K, int* __restrict__ cnt, int* __restrict__ rank) {
     const int lane = threadIdx.x & 31;
+    pdl_launch();
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n + 31; r += (long long)gridDim.x * blockDim.x) {
         const bool in = r < n;
         long long k = in ? idx[r] : -1;
@@ -174,6 +175,49 @@ rank_kernel(const long long* __restrict__ idx, long long n, int K, int* __restri
     }
 }
 
+// Small codebooks (K <= RANK_SMEM_K): the global ticket counters would be hit by thousands of rows each.  A block
+// takes tickets for a span of RANK_SPAN rows in shared memory first (shared-memory atomics), then reserves, per code
+// present in the span, one contiguous range of global tickets with a single atomic.
+constexpr int RANK_SMEM_K = 2048;
+constexpr int RANK_SPAN = 256 * 16;
+
+__global__ void __launch_bounds__(256)
+rank_smem_kernel(const long long* __restrict__ idx, long long n, int K, int* __restrict__ cnt, int* __restrict__ rank) {
+    __shared__ int s_cnt[RANK_SMEM_K];
+    pdl_launch();
+    const long long n_spans = (n + RANK_SPAN - 1) / RANK_SPAN;
+    for (long long span = blockIdx.x; span < n_spans; span += gridDim.x) {
+        const long long r0 = span * RANK_SPAN;
+        for (int k = threadIdx.x; k < K; k += 256) s_cnt[k] = 0;
+        __syncthreads();
+        int code[16], local[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const long long r = r0 + u * 256 + threadIdx.x;
+            code[u] = -1;
+            if (r < n) {
+                long long k = idx[r];
+                k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+                code[u] = (int)k;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) local[u] = code[u] >= 0 ? atomicAdd(&s_cnt[code[u]], 1) : 0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += 256) {
+            const int c = s_cnt[k];
+            if (c) s_cnt[k] = atomicAdd(cnt + k, c);              // the span's first global ticket for code k
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const long long r = r0 + u * 256 + threadIdx.x;
+            if (code[u] >= 0) rank[r] = s_cnt[code[u]] + local[u];
+        }
+        __syncthreads();
+    }
+}
+
 // single CTA: offs[k] = sum_{j<k} cnt[j];  item_off[k] = sum_{j<k} ceil(cnt[j] / CHUNK) (first work item of code k);
 // n_items[0] = number of work items
 __global__ void __launch_bounds__(1024)
@@ -182,6 +226,8 @@ offsets_kernel(const int* __restrict__ cnt, int K, int* __restrict__ offs, int* 
     __shared__ int s_w[32], s_w2[32];
     __shared__ int s_carry[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    pdl_launch();
+    pdl_wait();                                                // the ticket kernel has completed
     if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
     __syncthreads();
     for (int k0 = 0; k0 < K; k0 += 1024) {
@@ -214,6 +260,8 @@ offsets_kernel(const int* __restrict__ cnt, int K, int* __restrict__ offs, int* 
 __global__ void __launch_bounds__(256)
 permute_kernel(const long long* __restrict__ idx, long long n, int K, const int* __restrict__ offs,
                const int* __restrict__ rank, int* __restrict__ perm) {
+    pdl_launch();
+    pdl_wait();                                                // offsets (and, before them, the tickets) are final
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
         long long k = idx[r];
         k = k < 0 ? 0 : (k >= K ? K - 1 : k);
@@ -233,6 +281,7 @@ segsum_kernel(const float* __restrict__ g, const int* __restrict__ perm, const i
     const int sub = lane / LPR, col = lane % LPR;
     const int D4 = D >> 2;
     const int warps = (gridDim.x * blockDim.x) >> 5;
+    pdl_wait();                                                // the permutation is complete
     const int total = __ldg(n_items);
     for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warps) {
         // code of this item: the last k with item_off[k] <= item (codes without rows share their successor's offset)
@@ -289,39 +338,55 @@ segsum_kernel(const float* __restrict__ g, const int* __restrict__ perm, const i
     }
 }
 
+static size_t sorted_ws_bytes(long long n, long long K) { return (3 * (size_t)K + 4 + 2 * (size_t)n) * sizeof(int); }
+
 static int launch_scatter_sorted(const long long* idx, long long n, const float* g, int K, int D, float* dtable,
-                                 unsigned long long* hist, cudaStream_t s) {
-    // stream-ordered scratch (returned to the pool behind the last kernel): cnt[K] | offs[K] | n_items[4] | rank[n] |
-    // perm[n] | item_off[K];  at most m = n / CHUNK + K work items
+                                 unsigned long long* hist, void* workspace, cudaStream_t s) {
+    // caller-provided scratch: cnt[K] | offs[K] | n_items[4] | rank[n] | perm[n] | item_off[K];
+    // at most m = n / CHUNK + K work items
     const size_t m = (size_t)(n / SEG_CHUNK) + (size_t)K + 1;
-    const size_t ints = 3 * (size_t)K + 4 + 2 * (size_t)n;
-    int* ws = nullptr;
-    VQB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), ints * sizeof(int), s));
+    int* ws = reinterpret_cast<int*>(workspace);
     int* cnt = ws; int* offs = cnt + K; int* n_items = offs + K; int* rank = n_items + 4; int* perm = rank + n;
     int* item_off = perm + n;
     VQB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)K * sizeof(int), s));
     const long long gcap = (long long)sm_count() * 16;
     const unsigned grid = (unsigned)(ceil_div(n, 256) < gcap ? ceil_div(n, 256) : gcap);
-    rank_kernel<<<grid, 256, 0, s>>>(idx, n, K, cnt, rank);
+    // the four kernels are chained with programmatic dependent launch (each one is this library's own predecessor):
+    // launch latencies overlap, every kernel waits for its predecessor's completion before it reads its results
+    kernel_event_begin(s);
+    if (K <= RANK_SMEM_K) {
+        const long long spans = ceil_div(n, RANK_SPAN);
+        rank_smem_kernel<<<(unsigned)(spans < gcap ? spans : gcap), 256, 0, s>>>(idx, n, K, cnt, rank);
+    } else {
+        rank_kernel<<<grid, 256, 0, s>>>(idx, n, K, cnt, rank);
+    }
     VQB_CHECK_LAUNCH("rank_kernel");
-    offsets_kernel<<<1, 1024, 0, s>>>(cnt, K, offs, item_off, n_items, hist);
+    VQB_CUDA(launch_pdl(offsets_kernel, dim3(1), dim3(1024), 0, s, (const int*)cnt, K, offs, item_off, n_items, hist));
     VQB_CHECK_LAUNCH("offsets_kernel");
-    permute_kernel<<<grid, 256, 0, s>>>(idx, n, K, offs, rank, perm);
+    VQB_CUDA(launch_pdl(permute_kernel, dim3(grid), dim3(256), 0, s, idx, n, K, (const int*)offs, (const int*)rank, perm));
     VQB_CHECK_LAUNCH("permute_kernel");
     const long long scap = (long long)sm_count() * 8;
     const unsigned sgrid = (unsigned)(ceil_div((long long)m, 8) < scap ? ceil_div((long long)m, 8) : scap);
     const int D4 = D / 4;
-#define VQB_SS(L, V) segsum_kernel<L, V><<<sgrid, 256, 0, s>>>(g, perm, cnt, offs, item_off, n_items, K, D, dtable)
+#define VQB_SS(L, V) VQB_CUDA(launch_pdl(segsum_kernel<L, V>, dim3(sgrid), dim3(256), 0, s, g, (const int*)perm, (const int*)cnt, \
+                                         (const int*)offs, (const int*)item_off, (const int*)n_items, K, D, dtable))
     if (D4 <= 4) VQB_SS(4, 1); else if (D4 <= 8) VQB_SS(8, 1); else if (D4 <= 16) VQB_SS(16, 1);
     else if (D4 <= 32) VQB_SS(32, 1); else if (D4 <= 64) VQB_SS(32, 2); else VQB_SS(32, 4);
 #undef VQB_SS
     VQB_CHECK_LAUNCH("segsum_kernel");
-    VQB_CUDA(cudaFreeAsync(ws, s));
+    kernel_event_end(s);
     return VQB_OK;
 }
 
+// per-warp private copies only pay off while 8 warps of them fit (small codebooks, e.g. K=43: 11 KB each)
+static bool scatter_fits_smem(int64_t K, int64_t D) { return (size_t)K * D * 4 * 8 <= 96 * 1024; }
+
+size_t scatter_workspace_bytes(int64_t n, int64_t K, int64_t D) {
+    return (!scatter_fits_smem(K, D) && n >= 65536) ? sorted_ws_bytes(n, K) : 0;
+}
+
 int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K, int64_t D, float* dtable,
-                       int64_t* hist, cudaStream_t s) {
+                       int64_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     if (n == 0) return VQB_OK;
     if (D % 4 != 0) return invalid("scatter_add: D must be a multiple of 4 (got %lld)", (long long)D);
     // per-warp private copies only pay off while 8 warps of them fit (small codebooks, e.g. K=43: 11 KB each);
@@ -334,8 +399,9 @@ int launch_scatter_add(const int64_t* idx, int64_t n, const float* g, int64_t K,
     // large tables: ticket + permutation + one gather-sum per code (no atomics per row).  Short inputs stay on the
     // direct 128-bit global reductions: four extra launches would cost more than they save.
     static const bool direct = getenv("VQB_SCATTER_DIRECT") != nullptr;       // developer switch (A/B)
-    if (g && !direct && n >= 65536)
-        return launch_scatter_sorted((const long long*)idx, n, g, (int)K, (int)D, dtable, (unsigned long long*)hist, s);
+    const size_t need = scatter_workspace_bytes(n, K, D);
+    if (g && !direct && need && workspace && workspace_bytes >= need)
+        return launch_scatter_sorted((const long long*)idx, n, g, (int)K, (int)D, dtable, (unsigned long long*)hist, workspace, s);
     return launch_scatter_v<false>((const long long*)idx, n, g, (int)K, (int)D, dtable,
                                    (unsigned long long*)hist, 8, 0, s);
 }
@@ -389,12 +455,18 @@ extern "C" int vqb_inference_gather(const int64_t* txt, int64_t n_tokens, const 
     return VQB_OK;
 }
 
+extern "C" int vqb_scatter_workspace(int64_t n_tokens, int64_t n_codes, int64_t dim, size_t* bytes) {
+    if (!bytes) return invalid("vqb_scatter_workspace: bytes is NULL");
+    *bytes = (n_tokens > 0 && n_codes > 0 && dim > 0) ? scatter_workspace_bytes(n_tokens, n_codes, dim) : 0;
+    return VQB_OK;
+}
+
 extern "C" int vqb_scatter_add(const int64_t* txt, int64_t n_tokens, const float* g, int64_t n_codes, int64_t dim,
-                               float* dtable, int64_t* hist, void* stream) {
+                               float* dtable, int64_t* hist, void* workspace, size_t workspace_bytes, void* stream) {
     if (n_tokens == 0) return VQB_OK;
     if (!txt || (g && !dtable)) return invalid("vqb_scatter_add: NULL pointer");
     if (g && (!aligned16(g) || !aligned16(dtable))) return invalid("vqb_scatter_add: pointers must be 16-byte aligned");
-    return launch_scatter_add(txt, n_tokens, g, n_codes, dim, dtable, hist, (cudaStream_t)stream);
+    return launch_scatter_add(txt, n_tokens, g, n_codes, dim, dtable, hist, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int vqb_loss_backward(const float* x, const float* table, const int64_t* idx, int64_t n_rows, int64_t dim,

@@ -401,7 +401,10 @@ class _Lookup(torch.autograd.Function):
         g2 = _g32(g).view(-1, D)
         dtab = torch.zeros(K, D, device=g2.device, dtype=torch.float32)
         with torch.cuda.device(g2.device):
-            _lib.check(lib.vqb_scatter_add(ptr(t), t.numel(), ptr(g2), K, D, ptr(dtab), None, _stream(g2)))
+            nb = ctypes.c_size_t(0)
+            _lib.check(lib.vqb_scatter_workspace(t.numel(), K, D, ctypes.byref(nb)))
+            ws = torch.empty(nb.value, device=g2.device, dtype=torch.uint8) if nb.value else None
+            _lib.check(lib.vqb_scatter_add(ptr(t), t.numel(), ptr(g2), K, D, ptr(dtab), None, ptr(ws), nb.value, _stream(g2)))
         d_learn, d_pw, d_pb = _table_backward(dtab, None, None, phn_attr, ctx.Da)
         return None, d_learn, None, d_pw, d_pb
 

@@ -403,7 +403,11 @@ def test_large_table_scatter_add_sorted_path(N, K, D, skew):
     hist = torch.full((K,), 5, dtype=torch.int64, device="cuda")
     ti, tg = torch.from_numpy(idx).cuda(), torch.from_numpy(g).cuda()
     sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    V._lib.check(lib.vqb_scatter_add(ti.data_ptr(), N, tg.data_ptr(), K, D, dt.data_ptr(), hist.data_ptr(), sp))
+    nb = ctypes.c_size_t(0)
+    V._lib.check(lib.vqb_scatter_workspace(N, K, D, ctypes.byref(nb)))
+    assert nb.value > 0
+    ws = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+    V._lib.check(lib.vqb_scatter_add(ti.data_ptr(), N, tg.data_ptr(), K, D, dt.data_ptr(), hist.data_ptr(), ws.data_ptr(), nb.value, sp))
     torch.cuda.synchronize()
     assert rel_err(dt.cpu().numpy(), want) < 1e-6
     assert np.array_equal(hist.cpu().numpy() - 5, np.bincount(idx, minlength=K))

@@ -19,11 +19,17 @@ def main():
     tf32_peak = peaks["bf16_tflops"] / 2.0          # kind::tf32 runs at half the dense bf16 rate
     lib = _lib.load()
     out = []
+    only = os.environ.get("VQB_SWEEP_POINTS")                  # e.g. "256x64,8192x256" (K x D)
+    only = {tuple(int(v) for v in t.split("x")) for t in only.split(",")} if only else None
     for D in (64, 256):
+        if only and not any(d == D for _, d in only):
+            continue
         g = torch.Generator().manual_seed(D)
         xs = [torch.randn(N, D, generator=g).cuda() for _ in range(2)]          # 2 x (N*D*4) >= 512 MB > L2
         gq = torch.randn(N, D, generator=g).cuda()
         for K in (256, 1024, 4096, 8192):
+            if only and (K, D) not in only:
+                continue
             e = torch.randn(K, D, generator=g).cuda()
             tab, enorm, _ = VF.assemble_table(e)
             temp = torch.ones(1, device="cuda")
@@ -55,11 +61,14 @@ def main():
             st = (stats.cpu().float() / iters).tolist()
             # scatter-add backward (codebook gradient + histogram), idx from the last forward
             dtab = torch.zeros(K, D, device="cuda"); hist = torch.zeros(K, dtype=torch.int64, device="cuda")
+            nbs = ctypes.c_size_t(0)
+            _lib.check(lib.vqb_scatter_workspace(N, K, D, ctypes.byref(nbs)))
+            wss = torch.empty(max(nbs.value, 1), dtype=torch.uint8, device="cuda")
             for _ in range(2):
-                _lib.check(lib.vqb_scatter_add(idx.data_ptr(), N, gq.data_ptr(), K, D, dtab.data_ptr(), hist.data_ptr(), sp))
+                _lib.check(lib.vqb_scatter_add(idx.data_ptr(), N, gq.data_ptr(), K, D, dtab.data_ptr(), hist.data_ptr(), wss.data_ptr(), nbs.value, sp))
             torch.cuda.synchronize(); ev0.record()
             for _ in range(iters):
-                _lib.check(lib.vqb_scatter_add(idx.data_ptr(), N, gq.data_ptr(), K, D, dtab.data_ptr(), hist.data_ptr(), sp))
+                _lib.check(lib.vqb_scatter_add(idx.data_ptr(), N, gq.data_ptr(), K, D, dtab.data_ptr(), hist.data_ptr(), wss.data_ptr(), nbs.value, sp))
             ev1.record(); torch.cuda.synchronize()
             bwd_ms = ev0.elapsed_time(ev1) / iters
             flops = 2.0 * N * K * D
