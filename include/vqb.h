@@ -141,13 +141,14 @@ VQB_API int vqb_forward(const vqb_fwd_args* args, void* stream);
  *   With a tail, d_score_w and colsum are scratch: they are overwritten (no pre-zeroing) and hold this GPU's table
  *   gradient / column sums afterwards.
  * Exchange buffer of each rank (peer-mapped, e.g. torch symmetric memory), vqb_exchange_bytes(n_flat, world) bytes,
- * zero-filled once before the first call:  [world x uint32 flags, padded to 128 B | slot 0: n_flat fp32 | slot 1].
+ * zero-filled once before the first call:  [world x uint32 flags, padded to 128 B | slot 0: n_flat fp32, padded to a
+ * multiple of 4 | slot 1].
  * Flags carry a call counter (`epoch`), so the buffers need no reset between calls or CUDA-graph replays; all ranks
  * must make the same sequence of calls. */
 typedef struct vqb_bwd_tail {
     const float* phn_attr;       /* [K,A] or NULL (then n_attr = dim_attr = 0 and d_flat = d_learnable only) */
     int64_t n_attr, dim_attr;
-    float* d_flat;               /* [K*D_l + D_a*A + D_a] = d_learnable | d_proj_w | d_proj_b, overwritten */
+    float* d_flat;               /* [K*D_l + D_a*A + D_a] = d_learnable | d_proj_w | d_proj_b, overwritten; 16-byte aligned */
     uint32_t* counter;           /* [2] device words, zero before the first call: [0] block ticket (left zero),
                                     [1] epoch of the exchange (incremented by every call with world > 1) */
     int32_t world, rank;         /* world <= 1: no exchange */

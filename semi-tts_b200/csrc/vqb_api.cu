@@ -227,7 +227,8 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
         const vqb_bwd_tail* tl = a->tail;
         if (!l2 || want_tf32 || !backward_h2_supported(a))
             return invalid("vqb_backward: the fused tail needs the L2 score on the vqb_bwd_h2_kernel route (see vqb_backward_kernel_name)");
-        if (!tl->d_flat || !tl->counter) return invalid("vqb_backward: tail.d_flat and tail.counter are required");
+        if (!tl->d_flat || !tl->counter || !aligned16(tl->d_flat))
+            return invalid("vqb_backward: tail.d_flat (16-byte aligned) and tail.counter are required");
         if (tl->phn_attr ? (tl->n_attr <= 0 || tl->n_attr > 120 || tl->dim_attr <= 0 || tl->dim_attr >= a->dim) : (tl->n_attr != 0 || tl->dim_attr != 0))
             return invalid("vqb_backward: tail.phn_attr / n_attr / dim_attr are inconsistent");
         if (tl->world > 1 && (!tl->peer_bufs || tl->rank < 0 || tl->rank >= tl->world || tl->world > VQB_MAX_WORLD))

@@ -693,8 +693,10 @@ struct TailP {
     float* d_flat;
     unsigned int* counter;    // [0] ticket, [1] epoch
     void* const* peer_bufs;   // device array [world]
+    unsigned long long* dbg;  // optional timeline buffer (developer hook), slots 100..
     int A, Da, world, rank;
 };
+#define VQB_TTL(slot) do { if (t.dbg && tid == 0) t.dbg[100 + (slot)] = globaltimer_ns(); } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     unsigned int v;
@@ -710,6 +712,30 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
     return v;
 }
 
+// d_flat[i] = sum_r slot[r][i] in rank order.  W peers' 16-byte pieces are requested back to back before the first add
+// (compile-time W keeps the batch in registers under the 64-register cap of a 1024-thread block); world > W runs in
+// groups of W, still in rank order.
+template <int W>
+__device__ __forceinline__ void sum_peers(const float* const* s_slot, int world, int n_flat, int tid, float* __restrict__ d_flat) {
+    for (int i = 4 * tid; i < n_flat; i += 4 * 1024) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r0 = 0; r0 < world; r0 += W) {
+            float4 v[W];
+#pragma unroll
+            for (int r = 0; r < W; ++r) {
+                v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + r < world)
+                    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w) : "l"(s_slot[r0 + r] + i) : "memory");
+            }
+#pragma unroll
+            for (int r = 0; r < W; ++r) if (r0 + r < world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+        }
+        if (i + 3 < n_flat) *reinterpret_cast<float4*>(d_flat + i) = a;        // d_flat is 16-byte aligned (checked by the host)
+        else { d_flat[i] = a.x; if (i + 1 < n_flat) d_flat[i + 1] = a.y; if (i + 2 < n_flat) d_flat[i + 2] = a.z; }
+    }
+}
+
 constexpr int EXCH_FLAG_BYTES = 128;      // world (<= VQB_MAX_WORLD) x uint32, padded
 
 __global__ void __launch_bounds__(1024)
@@ -719,7 +745,9 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
     __shared__ unsigned int s_flag;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * 32 + tx;
+    if (t.dbg && tid == 0 && blockIdx.x == 0) t.dbg[100] = globaltimer_ns();
     pdl_wait();                                                     // the main backward kernel has completed
+    if (t.dbg && tid == 0 && blockIdx.x == 0) t.dbg[101] = globaltimer_ns();
     {
         const int n_kd = K * 64;
         const int o = blockIdx.x * 32 + tx;                         // output index over [n_kd | K column sums]
@@ -748,6 +776,7 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
     __syncthreads();
     if (!s_flag) return;
     __threadfence();
+    VQB_TTL(2);
 
     // ---- phase 2: parameter gradients from the table gradient (all reads through L2: written by other blocks) ----
     const int Dl = 64 - t.Da;
@@ -757,7 +786,8 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
     float* out = t.d_flat;
     if (exchange) {
         epoch = t.counter[1] + 1u;
-        out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(t.peer_bufs[t.rank]) + EXCH_FLAG_BYTES) + (size_t)(epoch & 1u) * n_flat;
+        out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(t.peer_bufs[t.rank]) + EXCH_FLAG_BYTES) +
+              (size_t)(epoch & 1u) * ((n_flat + 3) & ~3);
     }
     // stage eff = dW + 2 * table * colsum ([K][64]) and the attribute table ([K][A]) in shared memory with one round of
     // independent, coalesced loads, then form every output from shared memory (one thread per output)
@@ -783,11 +813,13 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
         out[n_l + o] = acc;
     }
     if (tid == 0) t.counter[0] = 0u;                                // ticket ready for the next call
+    VQB_TTL(3);
     if (!exchange) return;
 
     // ---- phase 3: one-shot all-reduce over peer memory ---------------------------------------------------------
     __threadfence_system();                                         // my slot is visible system-wide ...
     __syncthreads();
+    VQB_TTL(4);
     if (tid < t.world)                                              // ... before any peer sees my flag
         st_release_sys(reinterpret_cast<unsigned int*>(t.peer_bufs[tid]) + t.rank, epoch);
     if (tid < t.world) {
@@ -798,30 +830,19 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
         }
     }
     __syncthreads();
-    // all peers' values of an element are requested before the first one is consumed (one NVLink round trip per element,
-    // not `world` of them); the sum itself runs in rank order on every GPU
+    VQB_TTL(5);
+    // all peers' values of an element are requested before the first one is consumed (one NVLink round trip per
+    // batch, not `world` of them), as 16-byte loads; the sum itself runs in rank order on every GPU
     __shared__ const float* s_slot[VQB_MAX_WORLD];
+    const int n_pad = (n_flat + 3) & ~3;                            // slot stride: keeps every slot 16-byte aligned
     if (tid < t.world)
         s_slot[tid] = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(t.peer_bufs[tid]) + EXCH_FLAG_BYTES) +
-                      (size_t)(epoch & 1u) * n_flat;
+                      (size_t)(epoch & 1u) * n_pad;
     __syncthreads();
-    for (int i0 = tid; i0 < n_flat; i0 += 2 * 1024) {
-        const int i1 = i0 + 1024;
-        float v0[VQB_MAX_WORLD], v1[VQB_MAX_WORLD];
-#pragma unroll
-        for (int r = 0; r < VQB_MAX_WORLD; ++r) {
-            v0[r] = 0.f; v1[r] = 0.f;
-            if (r < t.world) {
-                v0[r] = ld_relaxed_sys_f32(s_slot[r] + i0);
-                if (i1 < n_flat) v1[r] = ld_relaxed_sys_f32(s_slot[r] + i1);
-            }
-        }
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int r = 0; r < VQB_MAX_WORLD; ++r) if (r < t.world) { a0 += v0[r]; a1 += v1[r]; }
-        t.d_flat[i0] = a0;
-        if (i1 < n_flat) t.d_flat[i1] = a1;
-    }
+    if (t.world <= 2) sum_peers<2>(s_slot, t.world, n_flat, tid, t.d_flat);
+    else if (t.world <= 4) sum_peers<4>(s_slot, t.world, n_flat, tid, t.d_flat);
+    else sum_peers<8>(s_slot, t.world, n_flat, tid, t.d_flat);
+    VQB_TTL(6);
     if (tid == 0) t.counter[1] = epoch;
 }
 
@@ -830,7 +851,7 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
 
-size_t exchange_bytes(int64_t n_flat, int world) { return (size_t)EXCH_FLAG_BYTES + 2 * (size_t)n_flat * 4 + 0 * (size_t)world; }
+size_t exchange_bytes(int64_t n_flat, int world) { (void)world; return (size_t)EXCH_FLAG_BYTES + 2 * (size_t)((n_flat + 3) & ~3ll) * 4; }
 
 bool backward_h2_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
@@ -883,7 +904,7 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
         const vqb_bwd_tail* tl = a->tail;
         TailP t;
         t.table = a->gather_table; t.attr = tl->phn_attr; t.d_flat = tl->d_flat; t.counter = tl->counter;
-        t.peer_bufs = tl->peer_bufs; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
+        t.peer_bufs = tl->peer_bufs; t.dbg = p.dbg; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
         const int n_out = (int)(K * 64 + K);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)ceil_div(n_out, 32)); cfg.blockDim = dim3(32, 32); cfg.stream = s;

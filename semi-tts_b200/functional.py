@@ -151,8 +151,9 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
         A = phn_attr.shape[1] if phn_attr is not None else 0
         Da = Da if phn_attr is not None else 0
         n_flat = K * (D - Da) + Da * A + Da
-        zeros = torch.empty(K * D + K + 4 + n_flat, device=dev, dtype=torch.float32)
-        flat = zeros[K * D + K + 4:]
+        n_pad = (n_flat + 3) & ~3                         # the flat gradient comes first: 16-byte aligned for the kernel
+        whole = torch.empty(n_pad + K * D + K + 4, device=dev, dtype=torch.float32)
+        flat, zeros = whole[:n_flat], whole[n_pad:]
         tl = _lib.BwdTail()
         tl.phn_attr, tl.n_attr, tl.dim_attr, tl.d_flat = ptr(phn_attr), A, Da, ptr(flat)
         tl.counter = ptr(tail.counter_for(dev))
