@@ -134,21 +134,20 @@ VQB_API int vqb_forward(const vqb_fwd_args* args, void* stream);
  * ------------------------------------------------------------------------------------------- */
 /* Optional fused tail of vqb_backward (L2 score, tensor-core route): the fixed-order sum of the per-CTA partial
  * gradients, the backward of the table assembly (vqb_table_backward) and -- in data-parallel runs -- the sum of the
- * result over all GPUs run as ONE kernel behind the main backward kernel, instead of three launches and an NCCL
- * call.  The cross-GPU step is a one-shot all-reduce over NVLink peer memory: every rank stores its flat gradient
- * into its own exchange buffer, raises a flag in every peer's buffer, waits for the peers' flags and adds the
- * world buffers in rank order (so all ranks obtain bit-identical sums).
- *   With a tail, d_score_w and colsum are scratch: they are overwritten (no pre-zeroing) and hold this GPU's table
- *   gradient / column sums afterwards.
+ * result over all GPUs run as ONE block-parallel kernel behind the main backward kernel, instead of three launches,
+ * a fill and an NCCL call.  Every block finishes a few outputs of the flat gradient on its own, pushes them into every
+ * peer's exchange buffer over NVLink as 8-byte (value, epoch) words -- the data carries its own flag, so there is no
+ * fence and no separate signal -- polls its own buffer for the peers' words of the same outputs and adds them in rank
+ * order (all ranks obtain bit-identical sums).
+ *   With a tail, d_score_w and colsum are not used and may be NULL.
  * Exchange buffer of each rank (peer-mapped, e.g. torch symmetric memory), vqb_exchange_bytes(n_flat, world) bytes,
- * zero-filled once before the first call:  [world x uint32 flags, padded to 128 B | slot 0: n_flat fp32, padded to a
- * multiple of 4 | slot 1].
- * Flags carry a call counter (`epoch`), so the buffers need no reset between calls or CUDA-graph replays; all ranks
- * must make the same sequence of calls. */
+ * zero-filled once before the first call:  [2 slots][world senders][n_flat padded to a multiple of 4] 8-byte words.
+ * Words carry a call counter (`epoch`, never 0) and the slots alternate with its parity, so the buffers need no reset
+ * between calls or CUDA-graph replays; all ranks must make the same sequence of calls. */
 typedef struct vqb_bwd_tail {
-    const float* phn_attr;       /* [K,A] or NULL (then n_attr = dim_attr = 0 and d_flat = d_learnable only) */
+    const float* phn_attr;       /* [K,A], A <= 63, or NULL (then n_attr = dim_attr = 0 and d_flat = d_learnable only) */
     int64_t n_attr, dim_attr;
-    float* d_flat;               /* [K*D_l + D_a*A + D_a] = d_learnable | d_proj_w | d_proj_b, overwritten; 16-byte aligned */
+    float* d_flat;               /* [K*D_l + D_a*A + D_a] = d_learnable | d_proj_w | d_proj_b, overwritten */
     uint32_t* counter;           /* [2] device words, zero before the first call: [0] block ticket (left zero),
                                     [1] epoch of the exchange (incremented by every call with world > 1) */
     int32_t world, rank;         /* world <= 1: no exchange */
@@ -241,6 +240,17 @@ VQB_API int vqb_segment_mean(const float* latent, const int32_t* seg_start, cons
 /* dlatent[B,T,D] = g_out[b, slot, :] / count(slot), 0 for blank frames (autograd of the means) */
 VQB_API int vqb_segment_mean_backward(const float* g_out, const int32_t* slot_of_row, const int32_t* seg_count,
                      int64_t n_utts, int64_t n_frames, int64_t dim, int64_t max_len, float* dlatent, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC input preparation  (replaces `(p_code + EPS).transpose(0,1).log()`, bin/train_vqvae.py:430-432 and :236,
+ * EPS = 1e-10: the only consumer of p_code in training)
+ *   out[s,b,:] = log(p_code[b,s,:] + eps)            contiguous [S,B,K]
+ *   g_p[b,s,k] (+)= g_out[s,b,k] / (p_code[b,s,k] + eps)      (accumulate != 0 adds into g_p)
+ * ------------------------------------------------------------------------------------------- */
+VQB_API int vqb_ctc_logp(const float* p_code, int64_t n_utts, int64_t n_frames, int64_t n_codes, float eps, float* out,
+                 void* stream);
+VQB_API int vqb_ctc_logp_backward(const float* g_out, const float* p_code, int64_t n_utts, int64_t n_frames,
+                 int64_t n_codes, float eps, float* g_p, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

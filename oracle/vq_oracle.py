@@ -336,6 +336,24 @@ def mean_forward_backward(idx, g_out, max_frames_per_phn):
 
 
 # --------------------------------------------------------------------------------------
+# CTC input preparation                              (bin/train_vqvae.py:430-432, :236)
+# --------------------------------------------------------------------------------------
+CTC_EPS = 1e-10          # EPS of bin/train_vqvae.py:19
+
+
+def ctc_input(p_code, eps=CTC_EPS, dtype=np.float64):
+    """ctc_input = (model_output + EPS).transpose(0, 1).log(): [B,S,K] -> [S,B,K]."""
+    p = np.asarray(p_code, dtype=dtype)
+    return np.log(p + dtype(eps)).transpose(1, 0, 2)
+
+
+def ctc_input_backward(p_code, g_out, eps=CTC_EPS, dtype=np.float64):
+    """d/dp of the above: g_p[b,s,k] = g_out[s,b,k] / (p[b,s,k] + eps)."""
+    p = np.asarray(p_code, dtype=dtype)
+    return np.asarray(g_out, dtype=dtype).transpose(1, 0, 2) / (p + dtype(eps))
+
+
+# --------------------------------------------------------------------------------------
 # helpers for parity reports
 # --------------------------------------------------------------------------------------
 def top2_rel_gap(dist):

@@ -9,9 +9,9 @@ from . import _lib
 from .functional import (vq_l2, vq_linear, codebook_lookup, assemble_table, vq_search)
 from .embed import L2Embedding, SeperateEmbedding, read_phn_attr
 from .usage import UsageHistogram
-from .segment import mean_forward, row_argmax
+from .segment import mean_forward, row_argmax, ctc_log_probs
 from .patch import install_into_reference
 from . import dist
 
 __all__ = ["L2Embedding", "SeperateEmbedding", "read_phn_attr", "vq_l2", "vq_linear", "vq_search",
-           "codebook_lookup", "assemble_table", "UsageHistogram", "mean_forward", "row_argmax", "install_into_reference", "dist", "_lib"]
+           "codebook_lookup", "assemble_table", "UsageHistogram", "mean_forward", "row_argmax", "ctc_log_probs", "install_into_reference", "dist", "_lib"]

@@ -47,7 +47,7 @@ class BwdArgs(ctypes.Structure):
 EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
            "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_scatter_workspace", "vqb_loss_backward",
-           "vqb_row_argmax", "vqb_segment_plan", "vqb_segment_mean", "vqb_segment_mean_backward"]
+           "vqb_row_argmax", "vqb_segment_plan", "vqb_segment_mean", "vqb_segment_mean_backward", "vqb_ctc_logp", "vqb_ctc_logp_backward"]
 
 _lib = None
 _lock = threading.Lock()
@@ -85,6 +85,8 @@ def load():
         lib.vqb_segment_plan.argtypes = [_p, i64, i64, i64, _p, _p, _p, _p, _p]
         lib.vqb_segment_mean.argtypes = [_p, _p, _p, _p, i64, i64, i64, i64, _p, _p]
         lib.vqb_segment_mean_backward.argtypes = [_p, _p, _p, i64, i64, i64, i64, _p, _p]
+        lib.vqb_ctc_logp.argtypes = [_p, i64, i64, i64, ctypes.c_float, _p, _p]
+        lib.vqb_ctc_logp_backward.argtypes = [_p, _p, i64, i64, i64, ctypes.c_float, _p, ctypes.c_int, _p]
         lib.vqb_forward_kernel_name.argtypes = [ctypes.POINTER(FwdArgs)]
         lib.vqb_backward_kernel_name.argtypes = [ctypes.POINTER(BwdArgs)]
         for name in EXPORTS:

@@ -213,13 +213,13 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
         return launch_scatter_add(a->idx, a->n_rows, a->g_q, a->n_codes, a->dim, dst, nullptr, a->workspace, a->workspace_bytes, s);
     }
 
-    if (!a->x || !a->score_w || !a->gather_table || !a->p_code || !a->dx || !a->d_score_w || !a->colsum)
+    if (!a->x || !a->score_w || !a->gather_table || !a->p_code || !a->dx || (!a->tail && (!a->d_score_w || !a->colsum)))
         return invalid("vqb_backward: x, score_w, gather_table, p_code, dx, d_score_w and colsum are required for the p_code route");
     if (l2 && !a->temp) return invalid("vqb_backward: temp is required for the L2 score");
     if ((a->flags & VQB_TEMP_GRAD) && (!a->d_temp || !a->score_b)) return invalid("vqb_backward: VQB_TEMP_GRAD needs d_temp and score_b");
     if (!l2 && a->g_q && !a->d_gather) return invalid("vqb_backward: d_gather is required for the LINEAR score when g_q is given");
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->dx) ||
-        !aligned16(a->d_score_w) || (a->g_q && !aligned16(a->g_q)) || (a->d_gather && !aligned16(a->d_gather)))
+        (a->d_score_w && !aligned16(a->d_score_w)) || (a->g_q && !aligned16(a->g_q)) || (a->d_gather && !aligned16(a->d_gather)))
         return invalid("vqb_backward: tensor pointers must be 16-byte aligned");
     const char* pick = getenv("VQB_BWD_KERNEL");                    // developer override: "tf32" = first-generation kernel
     const bool want_tf32 = pick && strcmp(pick, "tf32") == 0;
@@ -227,9 +227,8 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
         const vqb_bwd_tail* tl = a->tail;
         if (!l2 || want_tf32 || !backward_h2_supported(a))
             return invalid("vqb_backward: the fused tail needs the L2 score on the vqb_bwd_h2_kernel route (see vqb_backward_kernel_name)");
-        if (!tl->d_flat || !tl->counter || !aligned16(tl->d_flat))
-            return invalid("vqb_backward: tail.d_flat (16-byte aligned) and tail.counter are required");
-        if (tl->phn_attr ? (tl->n_attr <= 0 || tl->n_attr > 120 || tl->dim_attr <= 0 || tl->dim_attr >= a->dim) : (tl->n_attr != 0 || tl->dim_attr != 0))
+        if (!tl->d_flat || !tl->counter) return invalid("vqb_backward: tail.d_flat and tail.counter are required");
+        if (tl->phn_attr ? (tl->n_attr <= 0 || tl->n_attr > 63 || tl->dim_attr <= 0 || tl->dim_attr >= a->dim) : (tl->n_attr != 0 || tl->dim_attr != 0))
             return invalid("vqb_backward: tail.phn_attr / n_attr / dim_attr are inconsistent");
         if (tl->world > 1 && (!tl->peer_bufs || tl->rank < 0 || tl->rank >= tl->world || tl->world > VQB_MAX_WORLD))
             return invalid("vqb_backward: tail.world=%d rank=%d needs peer_bufs and world <= %d", tl->world, tl->rank, VQB_MAX_WORLD);

@@ -679,13 +679,20 @@ reduce_partials_h2_kernel(const float* __restrict__ partial, int n_cta, int K, f
 }
 
 // -----------------------------------------------------------------------------------------------------------
-// Fused tail (vqb_bwd_tail, L2 score): partial sums -> table gradient -> parameter gradients -> sum over GPUs.
-//   phase 1 (every block)   same fixed-order sum as reduce_partials_h2_kernel, but the result OVERWRITES dW / colsum
-//   phase 2 (last block)    backward of the table assembly (src/embed.py:109-112): d_learnable | d_proj_w | d_proj_b
-//   phase 3 (last block)    one-shot all-reduce over NVLink peer memory (see vqb.h); the world buffers are added in
-//                           rank order, so every GPU ends with the same bits
-// The last block is elected with a ticket counter (threadfence reduction pattern); no grid-wide barrier, no atomics on
-// data.  Peer waits are bounded (2 s) and trap, so a lost peer fails the launch instead of wedging the GPU.
+// Fused tail (vqb_bwd_tail, L2 score): partial sums -> parameter gradients -> sum over GPUs, block-parallel.
+//
+// Every block owns a few outputs of the flat gradient  d_learnable | d_proj_w | d_proj_b  and finishes them alone:
+//   learnable blocks (32 consecutive outputs (k, d < D_l)):   fixed-order sum over the CTAs' partial records of
+//       dE[k][d] and of the column sum cs[k];  out = dE + 2 E[k][d] cs[k]                     (src/embed.py:109-112, :211)
+//   projection blocks (one per projected column j):  eff[k] = dE[k][D_l+j] + 2 E[k][D_l+j] cs[k] for all k, then
+//       d_proj_w[j][a] = sum_k eff[k] attr[k][a],  d_proj_b[j] = sum_k eff[k]
+// Data-parallel runs: the block then PUSHES its outputs into every peer's exchange buffer over NVLink as 8-byte
+// (value, epoch) words -- the data carries its own flag (NCCL's "LL" idea), so there is no fence and no separate
+// signal -- and polls its own buffer until the same outputs of every peer have arrived; the sum runs in rank order, so
+// all GPUs end with the same bits.  No block waits for another block of its own GPU, remote blocks push before they
+// poll: no deadlock whatever the residency.  Two slots alternate by epoch parity (a rank cannot run two exchanges
+// ahead of a peer, because each exchange needs that peer's data of the same epoch).  Waits are bounded (2 s) and trap.
+// The last block to finish (ticket counter) hands the ticket back and publishes the epoch for the next call.
 // -----------------------------------------------------------------------------------------------------------
 struct TailP {
     const float* table;       // [K][64]
@@ -694,156 +701,139 @@ struct TailP {
     unsigned int* counter;    // [0] ticket, [1] epoch
     void* const* peer_bufs;   // device array [world]
     unsigned long long* dbg;  // optional timeline buffer (developer hook), slots 100..
-    int A, Da, world, rank;
+    int A, Da, world, rank, n_learn_blocks;
 };
-#define VQB_TTL(slot) do { if (t.dbg && tid == 0) t.dbg[100 + (slot)] = globaltimer_ns(); } while (0)
+#define VQB_TTL(slot) do { if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100 + (slot)] = globaltimer_ns(); } while (0)
 
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_relaxed_sys_b64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_b64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
-// d_flat[i] = sum_r slot[r][i] in rank order.  W peers' 16-byte pieces are requested back to back before the first add
-// (compile-time W keeps the batch in registers under the 64-register cap of a 1024-thread block); world > W runs in
-// groups of W, still in rank order.
-template <int W>
-__device__ __forceinline__ void sum_peers(const float* const* s_slot, int world, int n_flat, int tid, float* __restrict__ d_flat) {
-    for (int i = 4 * tid; i < n_flat; i += 4 * 1024) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r0 = 0; r0 < world; r0 += W) {
-            float4 v[W];
-#pragma unroll
-            for (int r = 0; r < W; ++r) {
-                v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r0 + r < world)
-                    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                 : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w) : "l"(s_slot[r0 + r] + i) : "memory");
-            }
-#pragma unroll
-            for (int r = 0; r < W; ++r) if (r0 + r < world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
-        }
-        if (i + 3 < n_flat) *reinterpret_cast<float4*>(d_flat + i) = a;        // d_flat is 16-byte aligned (checked by the host)
-        else { d_flat[i] = a.x; if (i + 1 < n_flat) d_flat[i + 1] = a.y; if (i + 2 < n_flat) d_flat[i + 2] = a.z; }
-    }
-}
-
-constexpr int EXCH_FLAG_BYTES = 128;      // world (<= VQB_MAX_WORLD) x uint32, padded
+// exchange buffer of one rank: [2 slots][world senders][n_pad] 8-byte words (value | epoch << 32)
+__host__ __device__ inline size_t exch_words(int64_t n_flat, int world) { return 2 * (size_t)world * (size_t)((n_flat + 3) & ~3ll); }
 
 __global__ void __launch_bounds__(1024)
-bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* __restrict__ dW,
-                   float* __restrict__ colsum, TailP t) {
-    __shared__ float red[32][33];
-    __shared__ unsigned int s_flag;
+bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
+    __shared__ float red[32][33], red2[32][33];
+    __shared__ float s_eff[64];
+    __shared__ float s_out[64];              // this block's finished outputs
+    __shared__ int s_idx[64];                // their positions in the flat gradient
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * 32 + tx;
-    if (t.dbg && tid == 0 && blockIdx.x == 0) t.dbg[100] = globaltimer_ns();
-    pdl_wait();                                                     // the main backward kernel has completed
-    if (t.dbg && tid == 0 && blockIdx.x == 0) t.dbg[101] = globaltimer_ns();
-    {
-        const int n_kd = K * 64;
-        const int o = blockIdx.x * 32 + tx;                         // output index over [n_kd | K column sums]
-        const float* src = nullptr;
-        float* dst = nullptr;
-        if (o < n_kd) { src = partial + o; dst = dW + o; }
-        else if (o - n_kd < K) { src = partial + 2 * H_KD + (o - n_kd); dst = colsum + (o - n_kd); }
-        float a = 0.f;
-        if (src) {
-#pragma unroll 5
-            for (int cta = ty; cta < n_cta; cta += 32) a += __ldg(src + (size_t)cta * H_PARTIAL_FLOATS);
-        }
-        red[ty][tx] = a;
-        __syncthreads();
-        if (ty == 0 && dst) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s += red[j][tx];
-            __stcg(dst, s);
-        }
-    }
-    // ---- elect the last block -------------------------------------------------------------------------------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_flag = atomicAdd(t.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (!s_flag) return;
-    __threadfence();
-    VQB_TTL(2);
-
-    // ---- phase 2: parameter gradients from the table gradient (all reads through L2: written by other blocks) ----
     const int Dl = 64 - t.Da;
     const int n_l = K * Dl, n_w = t.Da * t.A, n_flat = n_l + n_w + t.Da;
     const bool exchange = t.world > 1;
-    unsigned int epoch = 0;
-    float* out = t.d_flat;
-    if (exchange) {
-        epoch = t.counter[1] + 1u;
-        out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(t.peer_bufs[t.rank]) + EXCH_FLAG_BYTES) +
-              (size_t)(epoch & 1u) * ((n_flat + 3) & ~3);
-    }
-    // stage eff = dW + 2 * table * colsum ([K][64]) and the attribute table ([K][A]) in shared memory with one round of
-    // independent, coalesced loads, then form every output from shared memory (one thread per output)
-    extern __shared__ float s_tail[];
-    float* s_eff = s_tail;                                          // [K][64]
-    float* s_attr = s_tail + K * 64;                                // [K][A]
-    for (int i = tid; i < K * 64; i += 1024)
-        s_eff[i] = fmaf(2.f * __ldg(t.table + i), __ldcg(colsum + (i >> 6)), __ldcg(dW + i));
-    for (int i = tid; i < K * t.A; i += 1024) s_attr[i] = __ldg(t.attr + i);
-    __syncthreads();
-    for (int i = tid; i < n_l; i += 1024) {
-        const int k = i / Dl, d = i - k * Dl;
-        out[i] = s_eff[k * 64 + d];
-    }
-    for (int o = tid; o < n_w + t.Da; o += 1024) {                  // d_proj_w[j][a] = sum_k eff[k][Dl+j] attr[k][a]; d_proj_b[j]
-        const int j = o < n_w ? o / t.A : o - n_w;
-        const int a = o < n_w ? o - j * t.A : -1;
-        float acc = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float v = s_eff[k * 64 + Dl + j];
-            acc = a >= 0 ? fmaf(v, s_attr[k * t.A + a], acc) : acc + v;
-        }
-        out[n_l + o] = acc;
-    }
-    if (tid == 0) t.counter[0] = 0u;                                // ticket ready for the next call
-    VQB_TTL(3);
-    if (!exchange) return;
+    if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100] = globaltimer_ns();
+    pdl_wait();                                                     // the main backward kernel has completed
+    VQB_TTL(1);
+    const unsigned int epoch = exchange ? *reinterpret_cast<volatile unsigned int*>(t.counter + 1) + 1u : 0u;
+    int n_mine = 0;                                                 // outputs finished by this block (block-uniform)
 
-    // ---- phase 3: one-shot all-reduce over peer memory ---------------------------------------------------------
-    __threadfence_system();                                         // my slot is visible system-wide ...
-    __syncthreads();
-    VQB_TTL(4);
-    if (tid < t.world)                                              // ... before any peer sees my flag
-        st_release_sys(reinterpret_cast<unsigned int*>(t.peer_bufs[tid]) + t.rank, epoch);
-    if (tid < t.world) {
-        const unsigned int* mine = reinterpret_cast<const unsigned int*>(t.peer_bufs[t.rank]) + tid;
-        const unsigned long long t0 = globaltimer_ns();
-        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-            if (globaltimer_ns() - t0 > 2000000000ull) { printf("libvqb200: rank %d timed out waiting for rank %d (epoch %u)\n", t.rank, tid, epoch); __trap(); }
+    if ((int)blockIdx.x < t.n_learn_blocks) {
+        // ---- 32 consecutive learnable outputs --------------------------------------------------------------------
+        const int i = blockIdx.x * 32 + tx;
+        const bool live = i < n_l;
+        const int k = live ? i / Dl : 0, d = live ? i - k * Dl : 0;
+        float a = 0.f, c = 0.f;
+        if (live) {
+#pragma unroll 5
+            for (int cta = ty; cta < n_cta; cta += 32) {
+                const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
+                a += __ldg(rec + k * 64 + d);
+                c += __ldg(rec + 2 * H_KD + k);
+            }
         }
+        red[ty][tx] = a; red2[ty][tx] = c;
+        __syncthreads();
+        if (ty == 0) {
+            float sa = 0.f, sc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { sa += red[j][tx]; sc += red2[j][tx]; }
+            s_out[tx] = live ? fmaf(2.f * __ldg(t.table + k * 64 + d), sc, sa) : 0.f;
+            s_idx[tx] = live ? i : -1;
+        }
+        n_mine = 32;
+    } else {
+        // ---- one projected column j: eff[k] for all codes, then its A weights and its bias ------------------------
+        const int j = blockIdx.x - t.n_learn_blocks;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + tx;
+            float a = 0.f, c = 0.f;
+            if (k < K) {
+#pragma unroll 5
+                for (int cta = ty; cta < n_cta; cta += 32) {
+                    const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
+                    a += __ldg(rec + k * 64 + Dl + j);
+                    c += __ldg(rec + 2 * H_KD + k);
+                }
+            }
+            red[ty][tx] = a; red2[ty][tx] = c;
+            __syncthreads();
+            if (ty == 0 && k < K) {
+                float sa = 0.f, sc = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) { sa += red[jj][tx]; sc += red2[jj][tx]; }
+                s_eff[k] = fmaf(2.f * __ldg(t.table + k * 64 + Dl + j), sc, sa);
+            }
+            __syncthreads();
+        }
+        if (tid <= t.A) {                                           // tid < A: weight (j, a = tid);  tid == A: bias j
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k) acc = tid < t.A ? fmaf(s_eff[k], __ldg(t.attr + (size_t)k * t.A + tid), acc) : acc + s_eff[k];
+            s_out[tid] = acc;
+            s_idx[tid] = tid < t.A ? n_l + j * t.A + tid : n_l + n_w + j;
+        }
+        n_mine = t.A + 1;                                           // A <= 63 (checked by the host)
     }
     __syncthreads();
-    VQB_TTL(5);
-    // all peers' values of an element are requested before the first one is consumed (one NVLink round trip per
-    // batch, not `world` of them), as 16-byte loads; the sum itself runs in rank order on every GPU
-    __shared__ const float* s_slot[VQB_MAX_WORLD];
-    const int n_pad = (n_flat + 3) & ~3;                            // slot stride: keeps every slot 16-byte aligned
-    if (tid < t.world)
-        s_slot[tid] = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(t.peer_bufs[tid]) + EXCH_FLAG_BYTES) +
-                      (size_t)(epoch & 1u) * n_pad;
+    VQB_TTL(2);
+
+    if (!exchange) {
+        if (tid < n_mine && s_idx[tid] >= 0) t.d_flat[s_idx[tid]] = s_out[tid];
+        return;
+    }
+
+    // ---- push to every peer (own buffer included), then gather the peers' words of the same outputs ---------------
+    const int n_pad = (n_flat + 3) & ~3;
+    const size_t slot_off = (size_t)(epoch & 1u) * t.world * n_pad;
+    for (int w = tid; w < n_mine * t.world; w += 1024) {
+        const int o = w % n_mine, r = w / n_mine;                   // consecutive threads: consecutive words of one peer
+        const int i = s_idx[o];
+        if (i >= 0) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(t.peer_bufs[r]) + slot_off + (size_t)t.rank * n_pad + i;
+            st_relaxed_sys_b64(dst, ((unsigned long long)epoch << 32) | __float_as_uint(s_out[o]));
+        }
+    }
+    VQB_TTL(3);
+    if (tid < n_mine && s_idx[tid] >= 0) {
+        const int i = s_idx[tid];
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(t.peer_bufs[t.rank]) + slot_off + i;
+        float sum = 0.f;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int r = 0; r < t.world; ++r) {                         // rank order: identical bits on every GPU
+            unsigned long long w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+            while ((unsigned int)(w >> 32) != epoch) {
+                if (globaltimer_ns() - t0 > 2000000000ull) {
+                    printf("libvqb200: rank %d timed out waiting for rank %d (epoch %u, output %d)\n", t.rank, r, epoch, i);
+                    __trap();
+                }
+                w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+            }
+            sum += __uint_as_float((unsigned int)w);
+        }
+        t.d_flat[i] = sum;
+    }
+    VQB_TTL(4);
+    // ---- housekeeping: the last block hands the ticket back and publishes the epoch ----------------------------------
     __syncthreads();
-    if (t.world <= 2) sum_peers<2>(s_slot, t.world, n_flat, tid, t.d_flat);
-    else if (t.world <= 4) sum_peers<4>(s_slot, t.world, n_flat, tid, t.d_flat);
-    else sum_peers<8>(s_slot, t.world, n_flat, tid, t.d_flat);
-    VQB_TTL(6);
-    if (tid == 0) t.counter[1] = epoch;
+    if (tid == 0) {
+        if (atomicAdd(t.counter, 1u) == gridDim.x - 1) { t.counter[0] = 0u; t.counter[1] = epoch; }
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -851,7 +841,7 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, float* _
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
 
-size_t exchange_bytes(int64_t n_flat, int world) { (void)world; return (size_t)EXCH_FLAG_BYTES + 2 * (size_t)((n_flat + 3) & ~3ll) * 4; }
+size_t exchange_bytes(int64_t n_flat, int world) { return exch_words(n_flat, world) * 8; }
 
 bool backward_h2_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
@@ -905,14 +895,15 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
         TailP t;
         t.table = a->gather_table; t.attr = tl->phn_attr; t.d_flat = tl->d_flat; t.counter = tl->counter;
         t.peer_bufs = tl->peer_bufs; t.dbg = p.dbg; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
-        const int n_out = (int)(K * 64 + K);
+        const int Dl = 64 - t.Da;
+        t.n_learn_blocks = (int)ceil_div(K * Dl, 32);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)ceil_div(n_out, 32)); cfg.blockDim = dim3(32, 32); cfg.stream = s;
-        cfg.dynamicSmemBytes = (size_t)K * (64 + t.A) * 4;          // <= 64 * (64 + A) * 4: under 48 KB for A <= 128
+        cfg.gridDim = dim3((unsigned)(t.n_learn_blocks + t.Da)); cfg.blockDim = dim3(32, 32); cfg.stream = s;
+        cfg.dynamicSmemBytes = 0;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = getenv("VQB_NO_PDL") ? 0 : 1;
-        VQB_CUDA(cudaLaunchKernelEx(&cfg, bwd_tail_h2_kernel, (const float*)p.partial, grid, (int)K, a->d_score_w, a->colsum, t));
+        VQB_CUDA(cudaLaunchKernelEx(&cfg, bwd_tail_h2_kernel, (const float*)p.partial, grid, (int)K, t));
         VQB_CHECK_LAUNCH("bwd_tail_h2_kernel");
         return VQB_OK;
     }

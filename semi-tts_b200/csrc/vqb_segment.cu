@@ -219,3 +219,63 @@ extern "C" int vqb_segment_mean_backward(const float* g_out, const int32_t* slot
     VQB_CHECK_LAUNCH("segment_mean_backward_kernel");
     return VQB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTC input preparation (reference: bin/train_vqvae.py:430-432 and :236): ctc_input = (p_code + EPS).transpose(0,1).log()
+// -- the only consumer of p_code in training.  One pass: out[s,b,:] = log(p[b,s,:] + eps), contiguous [S,B,K] as
+// nn.CTCLoss wants it; consecutive threads walk consecutive OUTPUT elements, so reads and writes are both whole
+// K-float runs.  Backward: g_p[b,s,k] (+)= g_out[s,b,k] / (p[b,s,k] + eps).
+// ---------------------------------------------------------------------------------------------------------------
+namespace vqb {
+
+__global__ void __launch_bounds__(256)
+ctc_logp_kernel(const float* __restrict__ p, int B, int S, int K, float eps, float* __restrict__ out) {
+    const long long n = (long long)B * S * K;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
+        const long long row = o / K;                       // = s * B + b
+        const int k = (int)(o - row * K);
+        const int s = (int)(row / B), b = (int)(row - (long long)s * B);
+        out[o] = logf(__ldg(p + ((long long)b * S + s) * K + k) + eps);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ctc_logp_backward_kernel(const float* __restrict__ g_out, const float* __restrict__ p, int B, int S, int K, float eps,
+                         float* __restrict__ g_p, int accumulate) {
+    const long long n = (long long)B * S * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / K;                       // = b * S + s
+        const int k = (int)(i - row * K);
+        const int b = (int)(row / S), s = (int)(row - (long long)b * S);
+        const float g = __ldg(g_out + ((long long)s * B + b) * K + k) / (__ldg(p + i) + eps);
+        g_p[i] = accumulate ? g_p[i] + g : g;
+    }
+}
+
+}  // namespace vqb
+
+extern "C" int vqb_ctc_logp(const float* p_code, int64_t n_utts, int64_t n_frames, int64_t n_codes, float eps, float* out,
+                            void* stream) {
+    const int64_t n = n_utts * n_frames * n_codes;
+    if (n == 0) return VQB_OK;
+    if (!p_code || !out) return invalid("vqb_ctc_logp: NULL pointer");
+    if (n_utts >= (1ll << 31) || n_frames >= (1ll << 31) || n_codes >= (1ll << 31)) return invalid("vqb_ctc_logp: shape too large");
+    const int64_t blocks = ceil_div(n, 256), cap = (int64_t)sm_count() * 16;
+    ctc_logp_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(p_code, (int)n_utts, (int)n_frames,
+                                                                                              (int)n_codes, eps, out);
+    VQB_CHECK_LAUNCH("ctc_logp_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_ctc_logp_backward(const float* g_out, const float* p_code, int64_t n_utts, int64_t n_frames, int64_t n_codes,
+                                     float eps, float* g_p, int accumulate, void* stream) {
+    const int64_t n = n_utts * n_frames * n_codes;
+    if (n == 0) return VQB_OK;
+    if (!g_out || !p_code || !g_p) return invalid("vqb_ctc_logp_backward: NULL pointer");
+    if (n_utts >= (1ll << 31) || n_frames >= (1ll << 31) || n_codes >= (1ll << 31)) return invalid("vqb_ctc_logp_backward: shape too large");
+    const int64_t blocks = ceil_div(n, 256), cap = (int64_t)sm_count() * 16;
+    ctc_logp_backward_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        g_out, p_code, (int)n_utts, (int)n_frames, (int)n_codes, eps, g_p, accumulate);
+    VQB_CHECK_LAUNCH("ctc_logp_backward_kernel");
+    return VQB_OK;
+}

@@ -151,9 +151,8 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
         A = phn_attr.shape[1] if phn_attr is not None else 0
         Da = Da if phn_attr is not None else 0
         n_flat = K * (D - Da) + Da * A + Da
-        n_pad = (n_flat + 3) & ~3                         # the flat gradient comes first: 16-byte aligned for the kernel
-        whole = torch.empty(n_pad + K * D + K + 4, device=dev, dtype=torch.float32)
-        flat, zeros = whole[:n_flat], whole[n_pad:]
+        flat = torch.empty(n_flat, device=dev, dtype=torch.float32)
+        zeros = None
         tl = _lib.BwdTail()
         tl.phn_attr, tl.n_attr, tl.dim_attr, tl.d_flat = ptr(phn_attr), A, Da, ptr(flat)
         tl.counter = ptr(tail.counter_for(dev))
@@ -163,10 +162,13 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     else:
         # one zero-filled buffer (one fill kernel) carved into the accumulation targets
         zeros = torch.zeros(K * D + n_g + K + 4, device=dev, dtype=torch.float32)
-    d_w = zeros[:K * D].view(K, D)
-    d_gather = zeros[K * D:K * D + n_g].view(K, D) if separate_gather else None
-    colsum = zeros[K * D + n_g:K * D + n_g + K]
-    d_temp = zeros[K * D + n_g + K:K * D + n_g + K + 1] if flags & _lib.TEMP_GRAD else None
+    if zeros is not None:
+        d_w = zeros[:K * D].view(K, D)
+        d_gather = zeros[K * D:K * D + n_g].view(K, D) if separate_gather else None
+        colsum = zeros[K * D + n_g:K * D + n_g + K]
+        d_temp = zeros[K * D + n_g + K:K * D + n_g + K + 1] if flags & _lib.TEMP_GRAD else None
+    else:
+        d_w = d_gather = colsum = d_temp = None           # the fused tail writes the parameter gradients directly
     dx = torch.empty(N, D, device=dev, dtype=torch.float32) if want_dx_buffer else None
     a.dx, a.d_score_w, a.colsum, a.d_gather, a.d_temp = ptr(dx), ptr(d_w), ptr(colsum), ptr(d_gather), ptr(d_temp)
     with torch.cuda.device(dev):

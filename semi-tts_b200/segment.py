@@ -84,3 +84,38 @@ def mean_forward(p_code, latent, max_frames_per_phn, idx=None):
 def vqvae_mean_forward(self, p_code, latent):
     """Method form, installed over src.vqvae.VQVAE.mean_forward by patch.install_into_reference()."""
     return mean_forward(p_code, latent, self.max_frames_per_phn)
+
+
+class _CtcLogp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p_code, eps):
+        _require(p_code, "p_code")
+        lib = _lib.load()
+        B, S, K = p_code.shape
+        p = _c(p_code.detach())
+        out = torch.empty(S, B, K, device=p.device, dtype=torch.float32)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.vqb_ctc_logp(ptr(p), B, S, K, float(eps), ptr(out), _stream(p)))
+        ctx.eps = float(eps)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(p)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None:
+            return None, None
+        (p,) = ctx.saved_tensors
+        B, S, K = p.shape
+        lib = _lib.load()
+        g = _g32(g)
+        gp = torch.empty(B, S, K, device=p.device, dtype=torch.float32)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.vqb_ctc_logp_backward(ptr(g), ptr(p), B, S, K, ctx.eps, ptr(gp), 0, _stream(p)))
+        return gp, None
+
+
+def ctc_log_probs(p_code, eps=1e-10):
+    """`(p_code + EPS).transpose(0, 1).log()` of bin/train_vqvae.py:430-432 / :236 in one pass: p_code[B,S,K] ->
+    contiguous [S,B,K] log-probabilities for nn.CTCLoss, differentiable w.r.t. p_code."""
+    return _CtcLogp.apply(p_code, eps)

@@ -79,3 +79,20 @@ def test_row_argmax_first_index_on_ties():
     p[::7, 20] = 2.0                                                    # tied maxima: the first index wins (:223 on CPU)
     got = V.row_argmax(p.cuda().view(10, 100, 43)).cpu()
     assert torch.equal(got.view(-1), p.argmax(-1))
+
+
+@pytest.mark.parametrize("B,S,K", [(4, 50, 43), (64, 800, 43), (3, 7, 300), (1, 1, 5)])
+def test_ctc_log_probs_vs_oracle(B, S, K):
+    """ctc_log_probs == (p_code + 1e-10).transpose(0,1).log() (bin/train_vqvae.py:430-432) and its gradient."""
+    import semi_tts_b200 as V
+    rng = np.random.default_rng(B * S + K)
+    logits = rng.standard_normal((B, S, K)) * 6.0                         # peaky rows: some p underflow towards EPS
+    p = np.exp(logits - logits.max(-1, keepdims=True)); p /= p.sum(-1, keepdims=True)
+    p32 = p.astype(np.float32)
+    pt = torch.from_numpy(p32).cuda().requires_grad_(True)
+    out = V.ctc_log_probs(pt)
+    assert out.shape == (S, B, K) and out.is_contiguous()
+    assert rel_err(out.detach().cpu().numpy(), O.ctc_input(p32.astype(np.float64))) < 1e-6
+    go = rng.standard_normal((S, B, K)).astype(np.float32)
+    out.backward(torch.from_numpy(go).cuda())
+    assert rel_err(pt.grad.cpu().numpy(), O.ctc_input_backward(p32.astype(np.float64), go.astype(np.float64))) < 1e-6

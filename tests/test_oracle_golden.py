@@ -166,3 +166,16 @@ def test_mean_forward_segments_and_backward_are_consistent(tag):
     go = np.random.default_rng(7).standard_normal(out.shape)
     out.backward(torch.from_numpy(go))
     assert np.allclose(lt.grad.numpy(), O.mean_forward_backward(idx, go, mfp), atol=1e-12)
+
+
+def test_ctc_input_oracle_matches_the_reference_expression():
+    """oracle.ctc_input restates `(model_output+EPS).transpose(0,1).log()` (bin/train_vqvae.py:430-432), evaluated here
+    by torch on the CPU exactly as the reference writes it, including its autograd."""
+    import torch
+    g = load_golden("l2_attr_stopgrad")
+    p = torch.from_numpy(g["p_code"].astype(np.float64)).requires_grad_(True)
+    ref = (p + 1e-10).transpose(0, 1).log()
+    assert np.allclose(ref.detach().numpy(), O.ctc_input(g["p_code"]), rtol=1e-12, atol=1e-12)
+    go = np.random.default_rng(11).standard_normal(ref.shape)
+    ref.backward(torch.from_numpy(go))
+    assert np.allclose(p.grad.numpy(), O.ctc_input_backward(g["p_code"], go), rtol=1e-12)

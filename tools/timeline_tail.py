@@ -34,15 +34,14 @@ for it in range(6):
     torch.cuda.synchronize()
 lib.vqb_debug_set_timeline(None)
 raw = buf.cpu().tolist()
-names = ["tail block 0 entry", "block 0 past pdl_wait", "last block elected", "phase 2 done (own gradient ready)",
-         "fence.sys done", "peer flags seen", "sum over GPUs stored"]
-main = [int(t) & ((1 << 56) - 1) for t in raw[:40] if t != 0 and ((int(t) >> 56) & 0xFF) == 13]
-t0 = main[0] if main else raw[100]
+names = ["tail block entry", "past pdl_wait (main kernel complete)", "own outputs finished", "pushed to all peers",
+         "peers' words gathered, sum stored"]
+t0 = raw[100]
 for r in range(world):
     if world > 1:
         dist.barrier()
     if r == rank:
-        print("rank %d (t = 0: main backward kernel's CTA 0 has written its partial record)" % rank)
+        print("rank %d (last block of the tail kernel; t = 0 at its entry)" % rank)
         prev = t0
         for i, nme in enumerate(names):
             t = raw[100 + i]
