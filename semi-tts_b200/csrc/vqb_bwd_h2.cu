@@ -719,8 +719,9 @@ __host__ __device__ inline size_t exch_words(int64_t n_flat, int world) { return
 
 __global__ void __launch_bounds__(1024)
 bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
-    __shared__ float red[32][33], red2[32][33];
-    __shared__ float s_eff[64];
+    __shared__ float red[32][33], red2[32][33], red3[32][33], red4[32][33];
+    __shared__ float s_eff[64], s_tab[64];
+    extern __shared__ float s_attr[];        // [K][A] (projection blocks)
     __shared__ float s_out[64];              // this block's finished outputs
     __shared__ int s_idx[64];                // their positions in the flat gradient
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -729,6 +730,18 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t)
     const int n_l = K * Dl, n_w = t.Da * t.A, n_flat = n_l + n_w + t.Da;
     const bool exchange = t.world > 1;
     if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100] = globaltimer_ns();
+    if ((int)blockIdx.x >= t.n_learn_blocks) {
+        // constants of a projection block (frozen attribute table, this step's codebook column): fetched while the main
+        // backward kernel is still running -- neither is written by it
+        const int j = blockIdx.x - t.n_learn_blocks;
+        for (int i = tid; i < K * t.A; i += 1024) s_attr[i] = __ldg(t.attr + i);
+        if (tid < K) s_tab[tid] = __ldg(t.table + tid * 64 + Dl + j);
+    }
+    // learnable blocks: output tx of this block and its codebook entry (a constant of this step), also ahead of the wait
+    const int li = blockIdx.x * 32 + tx;
+    const bool live = (int)blockIdx.x < t.n_learn_blocks && li < n_l;
+    const int lk = live ? li / Dl : 0, ld = live ? li - lk * Dl : 0;
+    const float ltab = live ? __ldg(t.table + lk * 64 + ld) : 0.f;
     pdl_wait();                                                     // the main backward kernel has completed
     VQB_TTL(1);
     const unsigned int epoch = exchange ? *reinterpret_cast<volatile unsigned int*>(t.counter + 1) + 1u : 0u;
@@ -736,9 +749,7 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t)
 
     if ((int)blockIdx.x < t.n_learn_blocks) {
         // ---- 32 consecutive learnable outputs --------------------------------------------------------------------
-        const int i = blockIdx.x * 32 + tx;
-        const bool live = i < n_l;
-        const int k = live ? i / Dl : 0, d = live ? i - k * Dl : 0;
+        const int i = li, k = lk, d = ld;
         float a = 0.f, c = 0.f;
         if (live) {
 #pragma unroll 5
@@ -754,37 +765,41 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t)
             float sa = 0.f, sc = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { sa += red[j][tx]; sc += red2[j][tx]; }
-            s_out[tx] = live ? fmaf(2.f * __ldg(t.table + k * 64 + d), sc, sa) : 0.f;
+            s_out[tx] = live ? fmaf(2.f * ltab, sc, sa) : 0.f;
             s_idx[tx] = live ? i : -1;
         }
         n_mine = 32;
     } else {
         // ---- one projected column j: eff[k] for all codes, then its A weights and its bias ------------------------
         const int j = blockIdx.x - t.n_learn_blocks;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + tx;
-            float a = 0.f, c = 0.f;
+        float a[2] = {0.f, 0.f}, c[2] = {0.f, 0.f};                  // codes tx and tx + 32 (K <= 64)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = tx + 32 * h;
             if (k < K) {
 #pragma unroll 5
                 for (int cta = ty; cta < n_cta; cta += 32) {
                     const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
-                    a += __ldg(rec + k * 64 + Dl + j);
-                    c += __ldg(rec + 2 * H_KD + k);
+                    a[h] += __ldg(rec + k * 64 + Dl + j);
+                    c[h] += __ldg(rec + 2 * H_KD + k);
                 }
             }
-            red[ty][tx] = a; red2[ty][tx] = c;
-            __syncthreads();
-            if (ty == 0 && k < K) {
+        }
+        red[ty][tx] = a[0]; red2[ty][tx] = c[0]; red3[ty][tx] = a[1]; red4[ty][tx] = c[1];
+        __syncthreads();
+        if (ty < 2) {
+            const int k = tx + 32 * ty;
+            if (k < K) {
                 float sa = 0.f, sc = 0.f;
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) { sa += red[jj][tx]; sc += red2[jj][tx]; }
-                s_eff[k] = fmaf(2.f * __ldg(t.table + k * 64 + Dl + j), sc, sa);
+                for (int jj = 0; jj < 32; ++jj) { sa += (ty ? red3 : red)[jj][tx]; sc += (ty ? red4 : red2)[jj][tx]; }
+                s_eff[k] = fmaf(2.f * s_tab[k], sc, sa);
             }
-            __syncthreads();
         }
+        __syncthreads();
         if (tid <= t.A) {                                           // tid < A: weight (j, a = tid);  tid == A: bias j
             float acc = 0.f;
-            for (int k = 0; k < K; ++k) acc = tid < t.A ? fmaf(s_eff[k], __ldg(t.attr + (size_t)k * t.A + tid), acc) : acc + s_eff[k];
+            for (int k = 0; k < K; ++k) acc = tid < t.A ? fmaf(s_eff[k], s_attr[k * t.A + tid], acc) : acc + s_eff[k];
             s_out[tid] = acc;
             s_idx[tid] = tid < t.A ? n_l + j * t.A + tid : n_l + n_w + j;
         }
@@ -899,7 +914,7 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
         t.n_learn_blocks = (int)ceil_div(K * Dl, 32);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(t.n_learn_blocks + t.Da)); cfg.blockDim = dim3(32, 32); cfg.stream = s;
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = (size_t)K * t.A * 4;                  // <= 64 * 63 * 4 B
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = getenv("VQB_NO_PDL") ? 0 : 1;
