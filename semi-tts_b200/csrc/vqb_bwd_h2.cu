@@ -47,7 +47,8 @@ constexpr int HM = 128;                 // rows per tile
 constexpr int HBLK = HM * 128;          // one [128 rows][128 B] block = 16 KB
 constexpr int H_THREADS = 256;
 constexpr int H_KD = 64 * 64;
-constexpr int H_PARTIAL_FLOATS = 2 * H_KD + 64;   // [0] d_score_w part, [1] scatter part (LINEAR), [2] column sums
+constexpr int H_PARTIAL_FLOATS = 2 * H_KD + 64;   // [0] d_score_w part, [1] scatter part (LINEAR) / transposed projected
+                                                  // columns (L2 with the fused tail), [2] column sums
 
 struct BwdH2P {
     const float* p;
@@ -59,6 +60,7 @@ struct BwdH2P {
     float* partial;           // [grid][H_PARTIAL_FLOATS]
     unsigned long long* dbg;  // optional timeline buffer (developer hook)
     int N, K, n_real, num_tiles;
+    int t_first;              // L2 + fused tail: columns d >= t_first are also stored transposed (record plane 1), else 64
     unsigned flags;
 };
 
@@ -625,7 +627,10 @@ vqb_bwd_h2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if (k < K) {
                     const float v = acc[k] + sXch[k * 64 + r];
                     if (l2) {
-                        part[k * 64 + r] = fmaf(-2.f, v, sAcc[k * 64 + r]);
+                        const float e = fmaf(-2.f, v, sAcc[k * 64 + r]);
+                        part[k * 64 + r] = e;
+                        // projected columns once more, column-major: the tail's projection blocks read them coalesced
+                        if (r >= p.t_first) part[H_KD + r * 64 + k] = e;
                     } else {
                         part[k * 64 + r] = v;
                         part[H_KD + k * 64 + r] = sAcc[k * 64 + r];
@@ -780,7 +785,7 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t)
 #pragma unroll 5
                 for (int cta = ty; cta < n_cta; cta += 32) {
                     const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
-                    a[h] += __ldg(rec + k * 64 + Dl + j);
+                    a[h] += __ldg(rec + H_KD + (Dl + j) * 64 + k);   // column-major copy: lanes read consecutive codes
                     c[h] += __ldg(rec + 2 * H_KD + k);
                 }
             }
@@ -892,6 +897,7 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
     p.N = (int)N; p.K = (int)K; p.n_real = (int)(a->n_real_rows > 0 && a->n_real_rows < N ? a->n_real_rows : 0);
     p.num_tiles = (int)ceil_div(N, HM);
     p.flags = a->flags;
+    p.t_first = (a->tail && l2) ? 64 - (int)a->tail->dim_attr : 64;
 
     const int stage_bytes = (int)((HM * K * 4 + 127) & ~127);
     const size_t smem = (size_t)2 * 2 * HBLK + 2 * HBLK + 2 * HBLK + 2 * 64 * 128 + 2 * (size_t)stage_bytes + 64 * 64 * 4 +
