@@ -120,14 +120,18 @@ __device__ __forceinline__ float exact_score(const uint8_t* sXt, int r, float xx
 
 #define VQB_TL(tag) do { if (p.dbg && et == 0 && wg == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG>
+// NOAUG (streamed 1xTF32 search at D = 256 only): the |e|^2 term is not folded into the GEMM as an extra K-step but
+// added by the epilogue from a per-chunk copy of enorm in shared memory; this frees the 16 KB A block and one piece
+// per chunk, which buys a fifth ring slot where shared memory is otherwise full.
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG, bool NOAUG>
 __global__ void __launch_bounds__(64 + 128 * NWG, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
-    constexpr int PIECES = PASSES == 3 ? 2 * KB + 1 : KB + 1;     // per chunk: hi/lo per K-block + the bias block
+    constexpr int PIECES = PASSES == 3 ? 2 * KB + 1 : (NOAUG ? KB : KB + 1);   // per chunk: hi/lo per K-block + the bias block
+    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT && !PCODE && NWG == 1), "NOAUG: streamed 1xTF32 search only");
     constexpr int TMEM_COLS = 2 * BN;
-    constexpr int CAP = 16;                                       // per-row candidate list capacity (SEARCH)
+    constexpr int CAP = NOAUG ? 15 : 16;                          // per-row candidate list capacity (SEARCH); 15: fits 227 KB
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
     static_assert(!PCODE || BN == 64, "the p_code epilogue keeps one 64-column accumulator in registers");
     // NWG epilogue warpgroups work on alternate tiles (tile t -> group t % NWG, x slot t % XS, TMEM buffer t & 1,
@@ -143,7 +147,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sX = smem;                                                        // [XS][KB][16 KB]
     uint8_t* sXlo = sX + (size_t)XS * KB * XBLK;                               // [XS][KB][16 KB]  (PASSES == 3)
     uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0);        // [16 KB] A block [1,1,1,0,...]
-    uint8_t* sB = sAug + XBLK;                                                 // [BS][PIECE]
+    uint8_t* sB = sAug + (NOAUG ? 0 : XBLK);                                   // [BS][PIECE]
     float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65] p_code staging (PCODE)
     uint2* sCand = reinterpret_cast<uint2*>(sP);                               // [CAP][128] (value, code)  (SEARCH)
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * SP_FLOATS * 4 : CAP * BM * 8));
@@ -173,11 +177,12 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
-    for (int i = threadIdx.x; i < XBLK / 16; i += NTHREADS)
-        reinterpret_cast<float4*>(sAug)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!NOAUG)
+        for (int i = threadIdx.x; i < XBLK / 16; i += NTHREADS)
+            reinterpret_cast<float4*>(sAug)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[121] = globaltimer_ns();
-    if (threadIdx.x < BM)
+    if (!NOAUG && threadIdx.x < BM)
         *reinterpret_cast<float4*>(sAug + sw128_offset(threadIdx.x, 0)) = make_float4(1.f, 1.f, 1.f, 0.f);
     fence_proxy_async_smem();
     tcgen05_fence_before();
@@ -278,7 +283,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                             mbar_wait(&b_full[bs], bph);
                             tcgen05_fence_after();
                             const uint64_t b = umma_desc_sw128(sB + (size_t)bs * PIECE);
-                            const bool is_aug = j == PIECES - 1;
+                            const bool is_aug = !NOAUG && j == PIECES - 1;
                             const bool is_lo = PASSES == 3 && !is_aug && (j & 1);
                             const int kb = PASSES == 3 ? (j >> 1) : j;
                             if (is_aug) {
@@ -437,8 +442,19 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 float mn = INFINITY, thr = INFINITY;
                 int cnt = 0;
                 bool overflow = false;
+                // NOAUG: |e|^2 of the chunk's codes, staged by the row threads themselves (thread et <-> code), double-buffered;
+                // the value of the next chunk is fetched one iteration ahead.  Codes beyond K get +1e30 (never the minimum).
+                float* sEn = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);     // [2][BN]
+                float en_next = 0.f;
+                if (NOAUG) en_next = et < p.K ? __ldg(p.bias + et) : 1e30f;
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
                     const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                    if (NOAUG) {
+                        sEn[(chunk & 1) * BN + et] = en_next;
+                        const int nk = (chunk + 1) * BN + et;
+                        en_next = (chunk + 1 < p.num_chunks && nk < p.K) ? __ldg(p.bias + nk) : 1e30f;
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // chunk's enorm visible; the buffer written
+                    }                                                                  // now was last read two chunks ago
                     mbar_wait(&t_full[buf], tph);
                     tcgen05_fence_after();
 #pragma unroll 1
@@ -446,6 +462,14 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         float v[32];
                         tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
+                        if (NOAUG) {
+                            const float4* en4 = reinterpret_cast<const float4*>(sEn + (chunk & 1) * BN + c * 32);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 e4 = en4[j4];                  // same address in every lane: a broadcast
+                                v[4 * j4] += e4.x; v[4 * j4 + 1] += e4.y; v[4 * j4 + 2] += e4.z; v[4 * j4 + 3] += e4.w;
+                            }
+                        }
                         float bm = v[0];
 #pragma unroll
                         for (int j = 1; j < 32; ++j) bm = fminf(bm, v[j]);
@@ -690,14 +714,15 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1, bool NOAUG = false>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s, bool pdl) {
     constexpr int XLS = NWG == 2 ? 1 : XS;
-    const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + XBLK + (size_t)BS * BN * 128 +
-                        (PCODE ? NWG * BM * 65 * 4 : 16 * BM * 8) + 1024 + 256 + 2 * BM * 4;
+    const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
+                        (size_t)BS * BN * 128 + (PCODE ? NWG * BM * 65 * 4 : (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
+                        (NOAUG ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     // PDL (only when the caller vouches for the predecessor, VQB_AFTER_ASSEMBLE, or when this call itself has just
@@ -773,15 +798,18 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
             if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, tq, p, s, pdl);
             if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, tq, p, s, pdl);
         }
-        if (D == 32) return launch_tc<1, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
+        // The codebook ring is as deep as shared memory allows: the streamed search is bound by the bytes in flight
+        // from L2 (one 16 KB piece per slot; the tensor pipe consumes ~100 GB/s per SM at the tf32 peak, i.e. needs
+        // ~150 KB in flight at ~1.5 us of loaded L2 latency -- profiles/r1e_ncu_full_search.csv: nothing else is busy).
+        if (D == 32) return launch_tc<1, 128, 2, 8, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
     }
     switch (D) {
-        case 32:  return launch_tc<1, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
-        case 64:  return launch_tc<2, 128, 2, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
-        case 128: return launch_tc<4, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
-        default:  return launch_tc<8, 128, 1, 4, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        case 32:  return launch_tc<1, 128, 2, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        case 64:  return launch_tc<2, 128, 2, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        case 128: return launch_tc<4, 128, 1, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);
+        default:  return launch_tc<8, 128, 1, 5, 1, false, false, 1, true>(tx, th, tl, tq, p, s, pdl);
     }
 }
 

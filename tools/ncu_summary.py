@@ -60,6 +60,8 @@ def main():
             per.setdefault(kn, []).append((rd + wr, rd, wr, t_us))
         for kn, v in per.items():
             n = len(v)
+            if name not in ("fwd", "bwd", "tail"):
+                kn = "%s@%s" % (kn, name)                   # captures of other workloads never shadow the bench kernels
             traffic[kn] = {"dram_bytes_per_launch": sum(x[0] for x in v) / n, "dram_read": sum(x[1] for x in v) / n,
                            "dram_write": sum(x[2] for x in v) / n, "ncu_time_us": sum(x[3] for x in v) / n, "launches": n,
                            "source": "%s_ncu_full_%s.csv (ncu --set full --clock-control none, bench.py workload)" % (rnd, name)}
