@@ -375,13 +375,12 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 VQB_TL(5);
                 float v[64];
                 {
-                    float t[32];
-                    tmem_ld_32x32(tmem_base + lane_addr + buf * BN, t);
+                    float t0[32], t1[32];                            // both halves in flight, one wait
+                    tmem_ld_32x32_nowait(tmem_base + lane_addr + buf * BN, t0);
+                    tmem_ld_32x32_nowait(tmem_base + lane_addr + buf * BN + 32, t1);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = t[j];
-                    tmem_ld_32x32(tmem_base + lane_addr + buf * BN + 32, t);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[32 + j] = t[j];
+                    for (int j = 0; j < 32; ++j) { v[j] = t0[j]; v[32 + j] = t1[j]; }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
@@ -457,18 +456,10 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     }                                                                  // now was last read two chunks ago
                     mbar_wait(&t_full[buf], tph);
                     tcgen05_fence_after();
-                    // the whole accumulator row of this chunk is requested at once (one TMEM round trip, not BN / 32),
-                    // then scanned 32 columns at a time with a tree-shaped minimum
-                    float vv[BN / 32][32];
-#pragma unroll
-                    for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32_nowait(tmem_base + lane_addr + buf * BN + c * 32, vv[c]);
-                    tmem_ld_wait();
-                    tcgen05_fence_before();                          // the row is in registers: hand the accumulator back
-                    __syncwarp();                                    // before scanning it, so the next MMA overlaps the scan
-                    if (lane == 0) mbar_arrive(&t_empty[buf]);
-#pragma unroll
+#pragma unroll 1
                     for (int c = 0; c < BN / 32; ++c) {
-                        float (&v)[32] = vv[c];
+                        float v[32];
+                        tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
                         if (NOAUG) {
                             const float4* en4 = reinterpret_cast<const float4*>(sEn + (chunk & 1) * BN + c * 32);
@@ -478,14 +469,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 v[4 * j4] += e4.x; v[4 * j4 + 1] += e4.y; v[4 * j4 + 2] += e4.z; v[4 * j4 + 3] += e4.w;
                             }
                         }
-                        float t16[16];
+                        float bm = v[0];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) t16[j] = fminf(v[j], v[j + 16]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) t16[j] = fminf(t16[j], t16[j + 8]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) t16[j] = fminf(t16[j], t16[j + 4]);
-                        const float bm = fminf(fminf(t16[0], t16[1]), fminf(t16[2], t16[3]));
+                        for (int j = 1; j < 32; ++j) bm = fminf(bm, v[j]);
                         if (bm <= thr) {
                             mn = fminf(mn, bm);
                             thr = mn + W;
@@ -507,6 +493,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                             }
                         }
                     }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[buf]);
                     ++c_it;
                 }
                 // survivors of the final window -> exact fp32 re-rank (same expression / fmaf order as the SIMT kernel)
