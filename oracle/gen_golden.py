@@ -39,8 +39,16 @@ def _state(mod):
 
 def _run_case(name, mod, B, S, seed, first_n_real_mel=0, train=False, want_gp=True, want_gq=True):
     g = torch.Generator().manual_seed(seed)
-    D, K = mod.latent_dim, mod.vocab_size
-    x = torch.randn(B, S, D, generator=g).requires_grad_(True)
+    x = torch.randn(B, S, mod.latent_dim, generator=g)
+    _run_case_x(name, mod, x, seed, first_n_real_mel, train, want_gp, want_gq, g)
+
+
+def _run_case_x(name, mod, x, seed, first_n_real_mel=0, train=False, want_gp=True, want_gq=True, g=None):
+    """Runs the reference module on a given enc_embs tensor and saves inputs, outputs and gradients."""
+    g = g if g is not None else torch.Generator().manual_seed(seed)
+    B, S, D = x.shape
+    K = mod.vocab_size
+    x = x.requires_grad_(True)
     g_p = torch.randn(B, S, K, generator=g) if want_gp else None
     g_q = torch.randn(B, S, D, generator=g) if want_gq else None
     mod.train(train)

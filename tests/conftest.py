@@ -31,7 +31,9 @@ def rel_err(a, b):
 L2_CASES = ["l2_attr_stopgrad", "l2_attr_stopgrad_gq_only", "l2_attr_first_n", "l2_attr_st_onehot",
             "l2_attr_st_onehot_first_n", "l2_attr_learn_temp", "l2_attr_temp_quarter",
             "l2_noattr_k37_d32", "l2_noattr_k300_d128", "l2_attr_skip_train", "l2_attr_ragged",
-            "l2_attr_ragged_b3_s37", "l2_config1_16x200"]
+            "l2_attr_ragged_b3_s37", "l2_config1_16x200",
+            # enc_embs produced by the reference's own CTC encoder (oracle/gen_golden_realistic.py)
+            "l2_realistic_a", "l2_realistic_b"]
 SEP_CASES = ["sep_attr_stopgrad", "sep_attr_st_onehot", "sep_noattr_k29_d48", "sep_noattr_st_onehot",
              "sep_config1_16x200"]
 # cases whose reference module was built with stop_grad=False
