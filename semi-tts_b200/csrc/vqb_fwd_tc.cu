@@ -547,7 +547,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const bool skip = (p.flags & VQB_SKIP) != 0;
                 // L2 score with the codebook resident in shared memory: e = -(hi + lo) / 2 exactly (hi + lo == -2 e)
                 constexpr bool SMEM_GATHER = RESIDENT && PASSES == 3;
-                const bool from_smem = SMEM_GATHER && !linear;
+                // (VQB_GATHER_LDG=1 in the environment, developer A/B: read the codeword from the L1-resident fp32 table with
+                //  one 128-bit load instead of reconstructing it from the two operand pieces in shared memory)
+                const bool from_smem = SMEM_GATHER && !linear && !(p.flags & 0x80000000u);
                 const bool want_se = p.sqerr != nullptr;
                 constexpr int D4 = KB * 8;                          // 16-byte chunks per row
                 constexpr int ITER = BM * D4 / 128;                 // chunks per thread
@@ -785,6 +787,7 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     p.N = (int)N; p.K = (int)K; p.D = (int)D;
     p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
     p.flags = a->flags;
+    { static const bool ldg = getenv("VQB_GATHER_LDG") != nullptr; if (ldg) p.flags |= 0x80000000u; }
 
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     //                      KB  BN  XS BS PASSES RESIDENT PCODE
