@@ -180,6 +180,7 @@ extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
         backward_h2_workspace(a, &b2);
         *bytes = b1 > b2 ? b1 : b2;
         if (!a->g_p && (a->flags & VQB_STOP_GRAD)) *bytes = scatter_workspace_bytes(a->n_rows, a->n_codes, a->dim);
+        else if (backward_generic_needed(a)) *bytes = backward_generic_workspace(a);
     }
     return VQB_OK;
 }
@@ -235,6 +236,7 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
     }
     if (!want_tf32 && backward_h2_supported(a)) return launch_backward_h2(a, s);
     if (backward_tensor_supported(a)) return launch_backward_tensor(a, s);
+    if (backward_generic_needed(a)) return launch_backward_generic(a, s);
     return launch_backward_simt(a, s);
 }
 
@@ -245,6 +247,7 @@ extern "C" const char* vqb_backward_kernel_name(const vqb_bwd_args* a) {
     const bool want_tf32 = pick && strcmp(pick, "tf32") == 0;
     if (!want_tf32 && backward_h2_supported(a)) return "vqb_bwd_h2_kernel";
     if (backward_tensor_supported(a)) return "vqb_bwd_tc_kernel";
+    if (backward_generic_needed(a)) return "bwdg_dx_kernel";
     return "vqb_bwd_simt_kernel";
 }
 

@@ -108,5 +108,9 @@ bool backward_h2_supported(const vqb_bwd_args* a);
 int backward_h2_workspace(const vqb_bwd_args* a, size_t* bytes);
 int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s);
 size_t exchange_bytes(int64_t n_flat, int world);
+// any-K p_code-route backward through a coefficient matrix in the workspace (vqb_bwd_generic.cu)
+bool backward_generic_needed(const vqb_bwd_args* a);
+size_t backward_generic_workspace(const vqb_bwd_args* a);
+int launch_backward_generic(const vqb_bwd_args* a, cudaStream_t s);
 
 }  // namespace vqb

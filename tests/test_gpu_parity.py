@@ -36,8 +36,6 @@ def _grad(p):
 @pytest.mark.parametrize("name", L2_CASES)
 def test_l2_module_vs_reference_and_oracle(name, tc):
     g = load_golden(name)
-    if name == "l2_noattr_k300_d128":
-        pytest.skip("p_code-route backward for K > 64 is not built yet (forward covered by test_generic_large_k...)")
     stop_grad = name not in ST_ONEHOT
     learn_temp = "grad.temp" in g
     skip_case = name == "l2_attr_skip_train"
@@ -214,7 +212,9 @@ def test_fused_mode_matches_parity_mode_and_scatter_only_backward():
     assert rel_err(ref_dpw.cpu().numpy(), t64["d_proj_w"]) < TOL
 
 
-def test_generic_large_k_forward_and_unsupported_backward_is_loud():
+def test_generic_large_k_backward_and_unsupported_variant_is_loud():
+    """K = 300, D = 128 (beyond the register-tiled kernels): the any-K p_code-route backward (coefficient matrix in the
+    workspace + two tiled contractions) against the reference's gradients; the ST-onehot variant stays a loud error."""
     g = load_golden("l2_noattr_k300_d128")
     m = build_module(g, "l2")
     x = _cuda(g["x"]).requires_grad_(True)
@@ -223,13 +223,61 @@ def test_generic_large_k_forward_and_unsupported_backward_is_loud():
     rep = O.index_mismatch_report(m.last_idx.cpu().numpy(), g["idx"], f64["dist"])
     assert rep["hard_mismatches"] == 0, rep
     assert rel_err(p.detach().cpu().numpy(), f64["p_code"]) < TOL
-    with pytest.raises(RuntimeError, match="K <= 64"):
-        p.backward(_cuda(g["g_p"]), retain_graph=True)                   # loud, not silent
-    q.backward(_cuda(g["g_q"]))                                          # scatter route works for any K
+    torch.autograd.backward([p, q], [_cuda(g["g_p"]), _cuda(g["g_q"])])
+    assert rel_err(x.grad.cpu().numpy(), g["dx"]) < TOL_REF
+    assert rel_err(m.learnable_table.grad.cpu().numpy(), g["grad.learnable_table"]) < TOL_REF
+    # scatter route alone works for any K as before
+    m2 = build_module(g, "l2")
+    x2 = _cuda(g["x"]).requires_grad_(True)
+    _, q2, _, _ = m2(x2)
+    q2.backward(_cuda(g["g_q"]))
     E64 = g["sd.learnable_table"].astype(np.float64)
     dtab = np.zeros_like(E64)
-    np.add.at(dtab, m.last_idx.cpu().numpy().reshape(-1), g["g_q"].astype(np.float64).reshape(-1, 128))
-    assert rel_err(m.learnable_table.grad.cpu().numpy(), dtab) < TOL
+    np.add.at(dtab, m2.last_idx.cpu().numpy().reshape(-1), g["g_q"].astype(np.float64).reshape(-1, 128))
+    assert rel_err(m2.learnable_table.grad.cpu().numpy(), dtab) < TOL
+    # ST-onehot (stop_grad=False) at this size is not served: it must fail loudly, not silently
+    m3 = build_module(g, "l2", stop_grad=False)
+    x3 = _cuda(g["x"]).requires_grad_(True)
+    p3, q3, _, _ = m3(x3)
+    with pytest.raises(RuntimeError, match="generic p_code-route backward"):
+        torch.autograd.backward([p3, q3], [_cuda(g["g_p"]), _cuda(g["g_q"])])
+
+
+@pytest.mark.parametrize("bone,B,S,K,D,first_n", [("l2", 3, 100, 200, 256, 1), ("l2", 2, 77, 65, 64, 0), ("l2", 4, 64, 1000, 20, 2),
+                                                  ("sep", 3, 50, 100, 48, 0), ("sep", 2, 33, 513, 136, 0)])
+def test_generic_backward_vs_oracle(bone, B, S, K, D, first_n):
+    """Any-K backward through the functional API (no phoneme attributes) against the fp64 oracle: L2 with a real/fake
+    split and a temperature, and the linear score of the separate quantizer."""
+    import semi_tts_b200 as V
+    rng = np.random.default_rng(K * 7 + D)
+    x = rng.standard_normal((B, S, D)).astype(np.float32)
+    gp = rng.standard_normal((B, S, K)).astype(np.float32)
+    gq = rng.standard_normal((B, S, D)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    if bone == "l2":
+        table = (rng.standard_normal((K, D)) * 0.7).astype(np.float32)
+        tt = torch.from_numpy(table).cuda().requires_grad_(True)
+        temp = torch.tensor([0.8], device="cuda")
+        p, q, idx, _, _ = V.vq_l2(xt, tt, None, None, None, temp, stop_grad=True, n_real_rows=first_n * S)
+        torch.autograd.backward([p, q], [torch.from_numpy(gp).cuda(), torch.from_numpy(gq).cuda()])
+        f = O.l2_forward(x, table.astype(np.float64), 0.8)
+        assert rel_err(p.detach().cpu().numpy(), f["p_code"]) < TOL
+        b = O.l2_backward(x, table.astype(np.float64), 0.8, f["p_code"], idx.cpu().numpy(), gp, gq, first_n_real_rows=first_n * S)
+        assert rel_err(xt.grad.cpu().numpy(), b["dx"]) < TOL
+        assert rel_err(tt.grad.cpu().numpy(), b["dtable"]) < TOL
+    else:
+        w = (rng.standard_normal((K, D)) * 0.3).astype(np.float32)
+        bias = rng.standard_normal(K).astype(np.float32)
+        emb = rng.standard_normal((K, D)).astype(np.float32)
+        wt, bt, et = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (w, bias, emb))
+        p, q, idx = V.vq_linear(xt, wt, bt, et, None, None, None, stop_grad=True)
+        torch.autograd.backward([p, q], [torch.from_numpy(gp).cuda(), torch.from_numpy(gq).cuda()])
+        f = O.separate_forward(x, emb.astype(np.float64), w.astype(np.float64), bias.astype(np.float64))
+        assert rel_err(p.detach().cpu().numpy(), f["p_code"]) < TOL
+        b = O.separate_backward(x, emb.astype(np.float64), w.astype(np.float64), f["p_code"], idx.cpu().numpy(), gp, gq)
+        assert rel_err(xt.grad.cpu().numpy(), b["dx"]) < TOL
+        for got, key in ((wt.grad, "d_asr_w"), (bt.grad, "d_asr_b"), (et.grad, "dtable")):
+            assert rel_err(got.cpu().numpy(), b[key]) < TOL, key
 
 
 def test_loss_extensions_vs_oracle():
