@@ -374,6 +374,56 @@ def test_config2_size_against_cpu_port_and_properties():
         assert torch.equal(m.last_idx.cpu(), idx)
 
 
+def test_config5_encode_path_one_rank_share():
+    """BASELINE configs[4] (--gen-specgram encode path: no-grad search + gather, and the text-side lookup) at one
+    rank's share of the 10 000 utterances (1 250 x 400 frames, K=43, D=64), through size-independent properties:
+    the p_code-free fused search picks the same codes as the parity-mode forward and as the exact fp32 CUDA-core
+    search, new_latent is the straight-through value of the picked codeword, quantising the output again is
+    idempotent, the usage histogram is the bincount of the indices, and inference(txt) is the table gather."""
+    import semi_tts_b200 as V
+    g = load_golden("l2_attr_stopgrad")
+    m = build_module(g, "l2").eval()
+    gen = torch.Generator().manual_seed(5)
+    U, S, D, K = 1250, 400, 64, 43
+    x = torch.randn(U, S, D, generator=gen).cuda()
+    txt = torch.randint(0, K, (64, 67), generator=gen).cuda()
+    with torch.no_grad():
+        tab = m.embedding.weight.data
+        m.usage.reset()
+        p, q, vq, commit = m(x)                                  # parity mode (src/vqvae.py:119 under :343's no_grad)
+        idx_p = m.last_idx.clone()
+        assert vq == 0 and commit == 0 and not q.requires_grad
+        assert torch.equal(idx_p, p.argmax(-1))
+        assert torch.equal(m.usage.counts, torch.bincount(idx_p.flatten(), minlength=K))
+        m.fused_search = True
+        m.usage.reset()
+        p2, q2, _, _ = m(x)                                      # fused mode: tensor-core search, no p_code
+        assert p2 is None
+        idx_f = m.last_idx.clone()
+        m.fused_search = False
+        idx_e, q_e = V.vq_search(x, tab, search_tensor=False)    # exact fp32 CUDA-core search
+        assert torch.equal(idx_f, idx_e) and torch.equal(q2, q_e)
+        # argmax over p_code vs argmin over the exact fp32 distances: bit-exact except rows whose top-2 gap is
+        # below 1e-6 relative (north_star); the count is reported
+        d64 = O.l2_distance(x.cpu().numpy().reshape(-1, D), _table64(g))
+        rep = O.index_mismatch_report(idx_p.cpu().numpy(), idx_f.cpu().numpy(), d64)
+        rep5 = O.index_mismatch_report(idx_p.cpu().numpy(), idx_f.cpu().numpy(), d64, rel_gap=1e-5)
+        print("config5 index report (parity mode vs fused search):", rep)
+        # the fused search is exact (asserted above); the parity-mode scores are 3xTF32 (|err| <= 3 * 2^-20 * 2|x||e|,
+        # i.e. up to 2.9e-6 of a distance of ~128), so at half a million rows a row whose gap lies just above 1e-6 may
+        # legitimately flip: none may flip above 1e-5, and at most a couple in between
+        assert rep5["hard_mismatches"] == 0 and rep["hard_mismatches"] <= 2, (rep, rep5)
+        same = idx_p == idx_f
+        assert torch.equal(q[same], q2[same])
+        c = tab[idx_f]
+        assert torch.equal(q2, (x + c) - x)                      # src/embed.py:145
+        assert int(m.usage.counts.sum().item()) == U * S
+        idx_again, _ = V.vq_search(q2, tab, search_tensor=True)
+        assert torch.equal(idx_again, idx_f)                     # idempotent
+        out = m.inference(txt)                                   # src/vqvae.py:147
+        assert torch.equal(out, tab[txt])
+
+
 @pytest.mark.parametrize("B,S,first_n", [(4, 128, 2), (3, 256, 1), (5, 77, 0), (2, 128, 2), (4, 100, 1), (1, 50, 0),
                                           (40, 400, 7)])
 def test_tensor_core_backward_vs_oracle_and_simt(B, S, first_n):
