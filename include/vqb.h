@@ -128,6 +128,10 @@ VQB_API int vqb_forward(const vqb_fwd_args* args, void* stream);
  *           d_score_w = -2 Gd*^T @ x + scatter_add(idx, g_q) ; colsum = colsum(Gd*)   (Gd* = rows < n_real_rows)
  *           d_temp = sum Gs * (-dist) * [temp > 0]
  *   LINEAR: dx = Gs@W;  d_score_w = Gs^T @ x;  colsum = colsum(Gs);  d_gather = scatter_add(idx, g_q)
+ * Routes (vqb_backward_kernel_name): K <= 64 with D = 64 and STOP_GRAD runs on the tensor cores; K <= 64 with
+ * D % 8 == 0, D <= 128 on the register-tiled exact-fp32 kernel (all flag combinations); every other shape (any K,
+ * D % 4 == 0, D <= 512) on the any-K route, which keeps the N x K coefficient matrix in the workspace
+ * (vqb_backward_workspace grows by 4 N K bytes) and serves the same flag combinations.
  * All outputs are ACCUMULATED into (+=): the caller zeroes d_score_w, colsum, d_gather, d_temp first.
  * dx is overwritten.  If g_p == NULL, STOP_GRAD and L2, only the scatter route runs and dx may be
  * NULL (the caller aliases dx = g_q: the straight-through identity costs zero bytes).

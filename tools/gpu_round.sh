@@ -14,6 +14,7 @@ timeout 200 python tools/timeline_fwd.py > gpurun_out/timeline_fwd.txt 2>&1
 timeout 200 python tools/timeline_bwd.py > gpurun_out/timeline_bwd.txt 2>&1
 timeout 200 python tools/timeline_tail.py 2>&1 | grep -v "^W\|OMP_NUM" > gpurun_out/timeline_tail_n1.txt
 timeout 300 python tools/sweep_c3.py > gpurun_out/sweep_c3.jsonl 2> gpurun_out/sweep_c3.err
+timeout 120 python tools/encode_c5.py > gpurun_out/encode_c5_n1.json 2> gpurun_out/encode_c5.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 4 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
 grep -E "passed|failed" gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log | cut -c1-300; cut -c1-700 gpurun_out/bench.json; tail -2 gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_ref.json
