@@ -118,6 +118,41 @@ __device__ __forceinline__ float exact_score(const uint8_t* sXt, int r, float xx
     return tau * (-dist);
 }
 
+// PIPE (see the kernel): |x|^2 in the exact kernel's fmaf order and x_lo = x - trunc_tf32(x), the operand of the third
+// MMA pass, for the tile with per-CTA counter `it`; returns |x|^2 of this thread's row `r`.  Same statements as the
+// in-loop form of the kernel (streamed 3xTF32 search, one epilogue warpgroup: x_lo slot == x slot).
+template <int KB, int XS>
+__device__ __forceinline__ float prep_tile(const uint8_t* sX, uint8_t* sXlo, uint64_t* x_full, uint64_t* xlo_full, int r, int lane,
+                                           uint32_t it) {
+    const uint32_t xs = it % XS, xph = (it / XS) & 1;
+    const uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
+    uint8_t* sXl = sXlo + (size_t)xs * KB * XBLK;
+    mbar_wait(&x_full[xs], xph);
+    float xx = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < KB; ++kb) {
+        float4 xv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(sXt + kb * XBLK + sw128_offset(r, c));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            xx = fmaf(xv[c].x, xv[c].x, xx); xx = fmaf(xv[c].y, xv[c].y, xx);
+            xx = fmaf(xv[c].z, xv[c].z, xx); xx = fmaf(xv[c].w, xv[c].w, xx);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float4 lo;
+            lo.x = xv[c].x - tf32_trunc(xv[c].x); lo.y = xv[c].y - tf32_trunc(xv[c].y);
+            lo.z = xv[c].z - tf32_trunc(xv[c].z); lo.w = xv[c].w - tf32_trunc(xv[c].w);
+            *reinterpret_cast<float4*>(sXl + kb * XBLK + sw128_offset(r, c)) = lo;
+        }
+    }
+    fence_proxy_async_smem();                                       // generic writes -> tcgen05.mma operand reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&xlo_full[xs]);
+    return xx;
+}
+
 #define VQB_TL(tag) do { if (p.dbg && et == 0 && wg == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
 
 // NOAUG (streamed 1xTF32 search at D = 256 only): the |e|^2 term is not folded into the GEMM as an extra K-step but
@@ -324,13 +359,33 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         float se_acc = 0.f;
         int tl_n = 0;
         VQB_TL(1);
+        // PIPE (streamed 3xTF32 search with two x / x_lo slots; VQB_SEARCH_PIPE): x_lo of the NEXT tile is produced
+        // before the epilogue of the current one, so the MMA warp -- which cannot start a streamed tile without x_lo --
+        // runs tile t+1 while these warps scan, re-rank, gather and store tile t.  Slot (t+1) % 2 is free by then: its
+        // previous user, tile t-1, was drained (x slot: x_empty -> TMA refill -> x_full; x_lo slot: every MMA of t-1 had
+        // retired before the last t_full of t-1 was consumed).
+        constexpr bool PIPE_OK = !PCODE && !RESIDENT && PASSES == 3 && XS == 2 && NWG == 1;
+        const bool pipe = PIPE_OK && (p.flags & 0x40000000u) != 0;
+        float xx_next = 0.f;
+        if constexpr (PIPE_OK) {
+            if (pipe && (int)blockIdx.x < p.num_tiles) xx_next = prep_tile<KB, XS>(sX, sXlo, x_full, xlo_full, r, lane, x_it);
+        }
         for (int tile = blockIdx.x + wg * gridDim.x; tile < p.num_tiles; tile += NWG * gridDim.x) {
             const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
             const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
             uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
             uint8_t* sXl = sXlo + (size_t)xls * KB * XBLK;
             VQB_TL(2);
-            mbar_wait(&x_full[xs], xph);
+            float xx_pipe = 0.f;
+            bool prepped = false;
+            if constexpr (PIPE_OK) {
+                if (pipe) {
+                    xx_pipe = xx_next;                              // this tile was prepared one iteration ago
+                    if (tile + (int)gridDim.x < p.num_tiles) xx_next = prep_tile<KB, XS>(sX, sXlo, x_full, xlo_full, r, lane, x_it + 1);
+                    prepped = true;
+                }
+            }
+            if (!PIPE_OK || !prepped) mbar_wait(&x_full[xs], xph);
             VQB_TL(3);
             const int row0 = tile * BM;
             const int rows = min(BM, p.N - row0);
@@ -338,8 +393,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             // |x|^2 in the exact kernel's fmaf order; x_lo = x - trunc_tf32(x) for the third MMA pass
             if (NWG == 2) mbar_wait(xlo_free, xlph ^ 1);            // previous tile's third MMA pass has read x_lo
             float xx = 0.f;
+            if (PIPE_OK && prepped) xx = xx_pipe;
 #pragma unroll 1
-            for (int kb = 0; kb < KB; ++kb) {
+            for (int kb = 0; kb < ((PIPE_OK && prepped) ? 0 : KB); ++kb) {
                 float4 xv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c)                         // all loads first: the stores below may alias
@@ -359,7 +415,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     }
                 }
             }
-            if (PASSES == 3) {
+            if (PASSES == 3 && (!PIPE_OK || !prepped)) {
                 fence_proxy_async_smem();                           // generic writes -> tcgen05.mma operand reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xlo_full[xls]);
@@ -788,6 +844,8 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
     p.flags = a->flags;
     { static const bool ldg = getenv("VQB_GATHER_LDG") != nullptr; if (ldg) p.flags |= 0x80000000u; }
+    // developer A/B: software-pipelined x_lo in the streamed 3xTF32 search (see PIPE in the kernel)
+    { static const bool pipe = getenv("VQB_SEARCH_PIPE") != nullptr; if (pipe) p.flags |= 0x40000000u; }
 
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     //                      KB  BN  XS BS PASSES RESIDENT PCODE

@@ -20,7 +20,9 @@ def _case(N, K, D, seed, scale=1.0):
 
 @pytest.mark.parametrize("N,K,D", [(1, 1, 32), (200, 43, 64), (128, 128, 64), (1000, 129, 32), (3000, 300, 128),
                                    (4096, 1024, 64), (2500, 4096, 256), (777, 8192, 64),
-                                   (1500, 1000, 256), (300, 130, 256)])
+                                   (1500, 1000, 256), (300, 130, 256),
+                                   # several tiles per CTA on the streamed 3xTF32 kernels (x / x_lo slots alternate)
+                                   (60000, 256, 64), (45000, 200, 32)])
 def test_tensor_search_equals_exact_simt_search(N, K, D):
     import semi_tts_b200 as V
     x, e = _case(N, K, D, seed=N + K + D)
