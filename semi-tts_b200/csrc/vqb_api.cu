@@ -85,6 +85,11 @@ namespace vqb { void set_debug_timeline(void* p); }
 // (tag << 56 | globaltimer ns) marks; pass NULL to disable
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_timeline(void* dev_ptr) { vqb::set_debug_timeline(dev_ptr); }
 
+// undocumented developer hook (A/B): force the software-pipelined x_lo of the streamed 3xTF32 search on (1) / off (0);
+// -1 = follow the VQB_SEARCH_PIPE environment variable
+namespace vqb { void set_debug_search_pipe(int v); }
+extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_pipe(int v) { vqb::set_debug_search_pipe(v); }
+
 namespace vqb {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

@@ -742,6 +742,8 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     return VQB_OK;
 }
 
+static int g_search_pipe = -1;                 // -1: follow VQB_SEARCH_PIPE; 0 / 1: forced (vqb_debug_set_search_pipe)
+void set_debug_search_pipe(int v) { g_search_pipe = v; }
 static unsigned long long* g_timeline = nullptr;
 void set_debug_timeline(void* p) { g_timeline = reinterpret_cast<unsigned long long*>(p); }
 unsigned long long* get_debug_timeline() { return g_timeline; }
@@ -845,7 +847,7 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     p.flags = a->flags;
     { static const bool ldg = getenv("VQB_GATHER_LDG") != nullptr; if (ldg) p.flags |= 0x80000000u; }
     // developer A/B: software-pipelined x_lo in the streamed 3xTF32 search (see PIPE in the kernel)
-    { static const bool pipe = getenv("VQB_SEARCH_PIPE") != nullptr; if (pipe) p.flags |= 0x40000000u; }
+    { static const bool pipe_env = getenv("VQB_SEARCH_PIPE") != nullptr; if (g_search_pipe < 0 ? pipe_env : g_search_pipe > 0) p.flags |= 0x40000000u; }
 
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     //                      KB  BN  XS BS PASSES RESIDENT PCODE
