@@ -86,7 +86,7 @@ namespace vqb { void set_debug_timeline(void* p); }
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_timeline(void* dev_ptr) { vqb::set_debug_timeline(dev_ptr); }
 
 // undocumented developer hook (A/B): force the software-pipelined x_lo of the streamed 3xTF32 search on (1) / off (0);
-// -1 = follow the VQB_SEARCH_PIPE environment variable
+// -1 = default (on unless VQB_SEARCH_NOPIPE is set)
 namespace vqb { void set_debug_search_pipe(int v); }
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_pipe(int v) { vqb::set_debug_search_pipe(v); }
 

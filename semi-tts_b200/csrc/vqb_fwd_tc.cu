@@ -359,13 +359,17 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         float se_acc = 0.f;
         int tl_n = 0;
         VQB_TL(1);
-        // PIPE (streamed 3xTF32 search with two x / x_lo slots; VQB_SEARCH_PIPE): x_lo of the NEXT tile is produced
-        // before the epilogue of the current one, so the MMA warp -- which cannot start a streamed tile without x_lo --
-        // runs tile t+1 while these warps scan, re-rank, gather and store tile t.  Slot (t+1) % 2 is free by then: its
-        // previous user, tile t-1, was drained (x slot: x_empty -> TMA refill -> x_full; x_lo slot: every MMA of t-1 had
-        // retired before the last t_full of t-1 was consumed).
+        // PIPE (streamed 3xTF32 search with two x / x_lo slots and at most two chunks per tile, i.e. 128 < K <= 256):
+        // x_lo of the NEXT tile is produced before the epilogue of the current one, so the MMA warp -- which cannot start
+        // a streamed tile without x_lo -- runs tile t+1 (and the producer streams its codebook pieces) while these warps
+        // scan, re-rank, gather and store tile t.  Slot (t+1) % 2 is free by then: its previous user, tile t-1, was
+        // drained (x slot: x_empty -> TMA refill -> x_full; x_lo slot: every MMA of t-1 had retired before the last
+        // t_full of t-1 was consumed).  Why two chunks at most: the producer issues x(t+1) only after the last codebook
+        // piece of tile t, the ring frees slots only as the MMA consumes them, and the MMA can run two chunks ahead of
+        // the epilogue (two TMEM buffers) -- with more chunks the wait for x(t+1) at the top of tile t would close a
+        // cycle (measured: it does; B200, K = 1024).  Measured at N = 2^20, K = 256, D = 64: 0.719 -> 0.658 ms.
         constexpr bool PIPE_OK = !PCODE && !RESIDENT && PASSES == 3 && XS == 2 && NWG == 1;
-        const bool pipe = PIPE_OK && (p.flags & 0x40000000u) != 0;
+        const bool pipe = PIPE_OK && p.num_chunks <= 2 && (p.flags & 0x40000000u) != 0;
         float xx_next = 0.f;
         if constexpr (PIPE_OK) {
             if (pipe && (int)blockIdx.x < p.num_tiles) xx_next = prep_tile<KB, XS>(sX, sXlo, x_full, xlo_full, r, lane, x_it);
@@ -742,7 +746,7 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     return VQB_OK;
 }
 
-static int g_search_pipe = -1;                 // -1: follow VQB_SEARCH_PIPE; 0 / 1: forced (vqb_debug_set_search_pipe)
+static int g_search_pipe = -1;                 // -1: default (on unless VQB_SEARCH_NOPIPE); 0 / 1: forced (vqb_debug_set_search_pipe)
 void set_debug_search_pipe(int v) { g_search_pipe = v; }
 static unsigned long long* g_timeline = nullptr;
 void set_debug_timeline(void* p) { g_timeline = reinterpret_cast<unsigned long long*>(p); }
@@ -846,8 +850,9 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
     p.flags = a->flags;
     { static const bool ldg = getenv("VQB_GATHER_LDG") != nullptr; if (ldg) p.flags |= 0x80000000u; }
-    // developer A/B: software-pipelined x_lo in the streamed 3xTF32 search (see PIPE in the kernel)
-    { static const bool pipe_env = getenv("VQB_SEARCH_PIPE") != nullptr; if (g_search_pipe < 0 ? pipe_env : g_search_pipe > 0) p.flags |= 0x40000000u; }
+    // software-pipelined x_lo in the streamed 3xTF32 search (see PIPE in the kernel): on by default,
+    // VQB_SEARCH_NOPIPE=1 or vqb_debug_set_search_pipe(0) turns it off (developer A/B)
+    { static const bool nopipe_env = getenv("VQB_SEARCH_NOPIPE") != nullptr; if (g_search_pipe < 0 ? !nopipe_env : g_search_pipe > 0) p.flags |= 0x40000000u; }
 
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     //                      KB  BN  XS BS PASSES RESIDENT PCODE

@@ -62,7 +62,7 @@ def main():
             pipe_ms = None
             if os.environ.get("VQB_SWEEP_PIPE_AB"):              # A/B of the software-pipelined x_lo (streamed 3xTF32 search)
                 idx_ref = idx.clone()
-                lib.vqb_debug_set_search_pipe(1)
+                lib.vqb_debug_set_search_pipe(0)
                 for i in range(2):
                     a.x = xs[i % 2].data_ptr(); _lib.check(lib.vqb_forward(ctypes.byref(a), sp))
                 torch.cuda.synchronize(); ev0.record()
@@ -95,7 +95,7 @@ def main():
                    "scatter_hbm_frac": bwd_bytes / bwd_ms / 1e6 / peaks["hbm_gbs"],
                    "frames_per_s_fwd_bwd": N / ((fwd_ms + bwd_ms) * 1e-3)}
             if pipe_ms is not None:
-                rec["fwd_ms_search_pipe"] = pipe_ms
+                rec["fwd_ms_search_nopipe"] = pipe_ms
             print(json.dumps(rec), flush=True)
             out.append(rec)
     return out
