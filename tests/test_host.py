@@ -44,6 +44,48 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
                    ctypes.sizeof(B), B.idx.offset, B.d_temp.offset]
 
 
+def test_c_program_links_and_uses_the_abi_without_python(tmp_path):
+    """The boundary is a C ABI: a C99 program includes vqb.h, links libvqb200.so and gets the documented behaviour
+    from the host-side entry points (version, workspace sizing, argument validation with thread-local messages,
+    no-device failure) -- no torch, no Python in between."""
+    import subprocess
+    lib_dir = os.path.join(ROOT, "semi-tts_b200")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "vqb.h"
+int main(void) {
+    if (vqb_abi_version() != VQB_ABI_VERSION) { printf("version\n"); return 1; }
+    vqb_fwd_args a; memset(&a, 0, sizeof a);
+    size_t n = 123;
+    a.struct_size = 4;                                        /* wrong size -> VQB_ERR_INVALID + message */
+    if (vqb_forward_workspace(&a, &n) != VQB_ERR_INVALID || !strstr(vqb_last_error(), "struct_size")) { printf("size\n"); return 2; }
+    a.struct_size = (uint32_t)sizeof a;
+    a.flags = VQB_SCORE_L2 | VQB_SCORE_LINEAR;                /* both scores -> invalid */
+    a.n_rows = 8; a.dim = 64; a.n_codes = 43;
+    if (vqb_forward_workspace(&a, &n) != VQB_ERR_INVALID) { printf("flags\n"); return 3; }
+    a.flags = VQB_SCORE_L2 | VQB_STOP_GRAD;
+    a.dim = 62;                                               /* D must be a multiple of 4 */
+    if (vqb_forward_workspace(&a, &n) != VQB_ERR_INVALID || !strstr(vqb_last_error(), "multiple of 4")) { printf("dim\n"); return 4; }
+    a.dim = 64; a.n_rows = 0;                                 /* empty input: nothing to do, no workspace */
+    if (vqb_forward_workspace(&a, &n) != VQB_OK || n != 0) { printf("empty\n"); return 5; }
+    size_t sb = 0;                                            /* large-table scatter needs scratch, small tables none */
+    if (vqb_scatter_workspace(1 << 20, 8192, 256, &sb) != VQB_OK || sb == 0) { printf("scatter\n"); return 6; }
+    if (vqb_scatter_workspace(51200, 43, 64, &sb) != VQB_OK || sb != 0) { printf("scatter small\n"); return 7; }
+    if (vqb_exchange_bytes(2580, 8) < (size_t)2 * 8 * 2580 * 8) { printf("exchange\n"); return 8; }
+    printf("devices %d\n", vqb_device_count());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lvqb200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("devices ")
+
+
 def test_struct_size_mismatch_is_an_error_without_a_gpu():
     import semi_tts_b200 as V
     lib = V._lib.load()
