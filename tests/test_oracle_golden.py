@@ -179,3 +179,61 @@ def test_ctc_input_oracle_matches_the_reference_expression():
     go = np.random.default_rng(11).standard_normal(ref.shape)
     ref.backward(torch.from_numpy(go))
     assert np.allclose(p.grad.numpy(), O.ctc_input_backward(g["p_code"], go), rtol=1e-12)
+
+
+@pytest.mark.parametrize("bone,B,S,K,D,first_n", [("l2", 3, 40, 200, 64, 1), ("l2", 2, 33, 65, 32, 0), ("l2", 4, 16, 300, 20, 2),
+                                                  ("sep", 3, 25, 100, 48, 0), ("sep", 2, 17, 130, 36, 0)])
+@pytest.mark.parametrize("variant", ["stop_grad", "st_onehot", "st_onehot_gq_only", "learn_temp"])
+def test_oracle_backward_algebra_vs_fp64_autograd_large_k(bone, B, S, K, D, first_n, variant):
+    """The GPU tests of the any-K backward (K > 64: no golden vectors from the reference at those sizes beyond
+    l2_noattr_k300_d128) rest on the oracle's backward algebra alone; here that algebra is checked against torch
+    autograd of the reference's op sequence (oracle/torch_port.py, validated against the real modules above) in
+    float64, for every variant those tests use: stop-grad, ST-onehot with and without g_p, learnable temperature,
+    the real/fake split, both quantizers."""
+    if variant == "learn_temp" and bone == "sep":
+        pytest.skip("the separate quantizer has no temperature (src/embed.py:190)")
+    stop_grad = not variant.startswith("st_onehot")
+    with_gp = variant != "st_onehot_gq_only"
+    rng = np.random.default_rng(K * 7 + D)
+    x = rng.standard_normal((B, S, D))
+    gp = rng.standard_normal((B, S, K))
+    gq = rng.standard_normal((B, S, D))
+    t64 = lambda a, rg=False: torch.from_numpy(np.asarray(a, dtype=np.float64).copy()).requires_grad_(rg)
+    xt = t64(x, True)
+    pick = (lambda p, q: ([p, q], [t64(gp), t64(gq)])) if with_gp else (lambda p, q: ([q], [t64(gq)]))
+    if bone == "l2":
+        table = rng.standard_normal((K, D)) * 0.7
+        tval = 0.3
+        tt = t64(table, True)
+        temp = t64([tval], variant == "learn_temp")
+        p, q, idx = TP.l2_forward(xt, tt, temp, stop_grad=stop_grad, first_n_real_mel=first_n)
+        torch.autograd.backward(*pick(p, q))
+        f = O.l2_forward(x, table, tval, stop_grad=stop_grad)
+        assert np.array_equal(f["idx"], idx.numpy())
+        assert np.allclose(f["p_code"], p.detach().numpy(), rtol=1e-10, atol=1e-14)
+        assert np.allclose(f["new_latent"], q.detach().numpy(), rtol=1e-10, atol=1e-12)
+        b = O.l2_backward(x, table, tval, f["p_code"], f["idx"], gp if with_gp else None, gq, stop_grad=stop_grad,
+                          first_n_real_rows=first_n * S)
+        assert rel_err(b["dx"], xt.grad.numpy()) < 1e-12
+        assert rel_err(b["dtable"], tt.grad.numpy()) < 1e-12
+        if variant == "learn_temp":
+            assert abs(float(b["dtemp"]) - temp.grad.item()) < 1e-10 * max(1.0, abs(temp.grad.item()))
+            # the identity the CUDA kernel uses: sum Gs * (-dist) == (1/tau) sum Gs * log P  (sum_k Gs_k = 0)
+            P = f["p_code"].reshape(-1, K)
+            G = gp.reshape(-1, K)
+            Gs = P * (G - (G * P).sum(-1, keepdims=True))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                alt = np.where(P > 0, Gs * np.log(P), 0.0).sum() / tval
+            assert abs(alt - float(b["dtemp"])) < 1e-9 * max(1.0, abs(float(b["dtemp"])))
+    else:
+        w, bias, emb = rng.standard_normal((K, D)) * 0.3, rng.standard_normal(K), rng.standard_normal((K, D))
+        wt, bt, et = t64(w, True), t64(bias, True), t64(emb, True)
+        p, q, idx = TP.separate_forward(xt, wt, bt, et, stop_grad=stop_grad)
+        torch.autograd.backward(*pick(p, q))
+        f = O.separate_forward(x, emb, w, bias, stop_grad=stop_grad, emb_weight=emb)
+        assert np.array_equal(f["idx"], idx.numpy())
+        b = O.separate_backward(x, emb, w, f["p_code"], f["idx"], gp if with_gp else None, gq, stop_grad=stop_grad)
+        assert rel_err(b["dx"], xt.grad.numpy()) < 1e-12
+        assert rel_err(b["d_asr_w"], wt.grad.numpy()) < 1e-12
+        assert rel_err(b["d_asr_b"], bt.grad.numpy()) < 1e-12
+        assert rel_err(b["dtable"], et.grad.numpy()) < 1e-12
