@@ -153,13 +153,17 @@ __device__ __forceinline__ float prep_tile(const uint8_t* sX, uint8_t* sXlo, uin
     return xx;
 }
 
-#define VQB_TL(tag) do { if (p.dbg && et == 0 && wg == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
+#define VQB_TL(tag) do { if (p.dbg && et == 0 && wg == 0 && cg == 0 && blockIdx.x == 0 && tl_n < 120) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
 
 // NOAUG (streamed 1xTF32 search at D = 256 only): the |e|^2 term is not folded into the GEMM as an extra K-step but
 // added by the epilogue from a per-chunk copy of enorm in shared memory; this frees the 16 KB A block and one piece
 // per chunk, which buys a fifth ring slot where shared memory is otherwise full.
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG, bool NOAUG>
-__global__ void __launch_bounds__(64 + 128 * NWG, 1)
+// CS = 2 (experimental, streamed 1xTF32 search, selected only by vqb_debug_set_search_cs2 / VQB_SEARCH_CS2): a second
+// epilogue warpgroup takes the other half of every chunk's columns (same TMEM lanes, i.e. the same rows) with its own
+// running minimum and candidate list; the two are merged after the last chunk with the threshold of the smaller minimum
+// (each list is a superset of what that threshold admits from its columns, so the re-rank sees every admissible code).
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG, bool NOAUG, int CS>
+__global__ void __launch_bounds__(64 + 128 * NWG * CS, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
@@ -173,7 +177,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // its own p_code staging); with NWG = 2 the x_lo tile is single-buffered (XLS = 1) and handed back by the
     // MMA warp through xlo_free as soon as the third MMA pass of a tile has been issued.
     static_assert(NWG == 1 || (PCODE && XS == 2 && RESIDENT && PASSES == 3), "two warpgroups: p_code mode only");
-    constexpr int NTHREADS = 64 + 128 * NWG;
+    static_assert(CS == 1 || (CS == 2 && !PCODE && !RESIDENT && PASSES == 1 && !NOAUG && NWG == 1), "column split: streamed 1xTF32 search only");
+    constexpr int NTHREADS = 64 + 128 * NWG * CS;
     constexpr int XLS = NWG == 2 ? 1 : XS;                        // x_lo slots
     constexpr int SP_FLOATS = BM * 65;
 
@@ -185,7 +190,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sB = sAug + (NOAUG ? 0 : XBLK);                                   // [BS][PIECE]
     float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65] p_code staging (PCODE)
     uint2* sCand = reinterpret_cast<uint2*>(sP);                               // [CAP][128] (value, code)  (SEARCH)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * SP_FLOATS * 4 : CAP * BM * 8));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * SP_FLOATS * 4 : CS * CAP * BM * 8));
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
     uint64_t* xlo_full = x_empty + XS;
@@ -207,7 +212,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_prefetch_desc(&tm_q);
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * CS); }
         mbar_init(xlo_free, 1);
         fence_barrier_init();
     }
@@ -347,7 +352,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // =============================== epilogue (thread = row) ==========================================
         const int q4 = warp & 3;                                    // TMEM lane quadrant this warp may read
         const int r = q4 * 32 + lane;                               // row within the tile == TMEM lane
-        const int wg = (warp - 2) >> 2;                             // epilogue warpgroup (0 .. NWG-1)
+        const int wg = CS == 2 ? 0 : (warp - 2) >> 2;               // epilogue warpgroup for the tile rotation (0 .. NWG-1)
+        const int cg = CS == 2 ? (warp - 2) >> 2 : 0;               // column group of this warpgroup (CS == 2)
         const int et = ((warp - 2) & 3) * 32 + lane;                // 0..127 within the warpgroup
         const uint32_t bar_id = 1 + wg;                             // named barrier of this warpgroup
         float* sPg = sP + (PCODE ? wg * SP_FLOATS : 0);
@@ -501,6 +507,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 float mn = INFINITY, thr = INFINITY;
                 int cnt = 0;
                 bool overflow = false;
+                uint2* sCandG = sCand + (CS == 2 ? cg * CAP * BM : 0);     // this warpgroup's list
                 // NOAUG: |e|^2 of the chunk's codes, staged by the row threads themselves (thread et <-> code), double-buffered;
                 // the value of the next chunk is fetched one iteration ahead.  Codes beyond K get +1e30 (never the minimum).
                 float* sEn = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);     // [2][BN]
@@ -517,7 +524,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     mbar_wait(&t_full[buf], tph);
                     tcgen05_fence_after();
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
+                    for (int c = cg * (BN / 32 / CS); c < (cg + 1) * (BN / 32 / CS); ++c) {
                         float v[32];
                         tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
@@ -539,15 +546,15 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 // make room: drop entries that fell out of the (tighter) window
                                 int kept = 0;
                                 for (int c2 = 0; c2 < cnt; ++c2) {
-                                    const uint2 e = sCand[c2 * BM + r];
-                                    if (__uint_as_float(e.x) <= thr) sCand[(kept++) * BM + r] = e;
+                                    const uint2 e = sCandG[c2 * BM + r];
+                                    if (__uint_as_float(e.x) <= thr) sCandG[(kept++) * BM + r] = e;
                                 }
                                 cnt = kept;
                             }
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 if (v[j] <= thr) {
-                                    if (cnt < CAP) sCand[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
+                                    if (cnt < CAP) sCandG[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
                                     else overflow = true;
                                 }
                             }
@@ -558,12 +565,33 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                     ++c_it;
                 }
+                int cnt_o = 0;                                      // entries of the other warpgroup's list (CS == 2)
+                if constexpr (CS == 2) {
+                    // merge the two column groups: group 1 publishes (minimum, count | overflow); group 0 tightens the
+                    // window to the smaller minimum and re-ranks over both lists; group 1 goes on to the next tile once
+                    // group 0 has finished reading its list (barrier 4)
+                    float* sMn = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);   // [BM]
+                    int* sCo = reinterpret_cast<int*>(sMn + BM);                                               // [BM]
+                    if (cg == 1) { sMn[r] = mn; sCo[r] = cnt | (overflow ? 0x10000 : 0); }
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (cg == 1) {
+                        asm volatile("bar.sync 4, 256;" ::: "memory");
+                        x_it += NWG;
+                        continue;
+                    }
+                    mn = fminf(mn, sMn[r]);
+                    thr = mn + W;
+                    const int co = sCo[r];
+                    cnt_o = co & 0xFFFF;
+                    overflow = overflow || (co & 0x10000) != 0;
+                }
+                const int ctot = cnt + cnt_o;
                 // survivors of the final window -> exact fp32 re-rank (same expression / fmaf order as the SIMT kernel)
                 int ncand = 0;
                 float bs_ = -INFINITY;
                 int first = 0;
-                for (int c2 = 0; c2 < cnt; ++c2) {
-                    const uint2 e = sCand[c2 * BM + r];
+                for (int c2 = 0; c2 < ctot; ++c2) {
+                    const uint2 e = sCand[((CS == 2 && c2 >= cnt) ? CAP + (c2 - cnt) : c2) * BM + r];
                     if (__uint_as_float(e.x) <= thr) { if (ncand == 0) first = (int)e.y; ++ncand; }
                 }
                 const bool full_scan = valid && overflow;
@@ -575,8 +603,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         if (sc > bs_) { bs_ = sc; best = k; }
                     }
                 } else if (rerank) {
-                    for (int c2 = 0; c2 < cnt; ++c2) {
-                        const uint2 e = sCand[c2 * BM + r];
+                    for (int c2 = 0; c2 < ctot; ++c2) {
+                        const uint2 e = sCand[((CS == 2 && c2 >= cnt) ? CAP + (c2 - cnt) : c2) * BM + r];
                         if (__uint_as_float(e.x) <= thr) {
                             const int k = (int)e.y;
                             const float sc = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
@@ -591,6 +619,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         if (m2) atomicAdd(p.stats + 1, (unsigned)__popc(m2));
                     }
                 }
+                if constexpr (CS == 2) asm volatile("bar.sync 4, 256;" ::: "memory");   // group 1 may reuse its list / merge words
             }
 
             VQB_TL(6);
@@ -748,6 +777,8 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 static int g_search_pipe = -1;                 // -1: default (on unless VQB_SEARCH_NOPIPE); 0 / 1: forced (vqb_debug_set_search_pipe)
 void set_debug_search_pipe(int v) { g_search_pipe = v; }
+static int g_search_cs2 = 0;                   // experimental column-split epilogue of the streamed 1xTF32 search (off)
+void set_debug_search_cs2(int v) { g_search_cs2 = v; }
 static unsigned long long* g_timeline = nullptr;
 void set_debug_timeline(void* p) { g_timeline = reinterpret_cast<unsigned long long*>(p); }
 unsigned long long* get_debug_timeline() { return g_timeline; }
@@ -777,22 +808,22 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1, bool NOAUG = false>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1, bool NOAUG = false, int CS = 1>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s, bool pdl) {
     constexpr int XLS = NWG == 2 ? 1 : XS;
     const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
-                        (size_t)BS * BN * 128 + (PCODE ? NWG * BM * 65 * 4 : (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
-                        (NOAUG ? 2 * BN * 4 : 0);
+                        (size_t)BS * BN * 128 + (PCODE ? NWG * BM * 65 * 4 : CS * (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
+                        ((NOAUG || CS == 2) ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG, CS>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     // PDL (only when the caller vouches for the predecessor, VQB_AFTER_ASSEMBLE, or when this call itself has just
     // launched build_operands_kernel): the prologue and the first x tile overlap the operand-preparation kernel
     kernel_event_begin(s);
-    if (pdl) VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG), smem, s, tx, th, tl, tq, p));
-    else kern<<<grid, 64 + 128 * NWG, smem, s>>>(tx, th, tl, tq, p);
+    if (pdl) VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG * CS), smem, s, tx, th, tl, tq, p));
+    else kern<<<grid, 64 + 128 * NWG * CS, smem, s>>>(tx, th, tl, tq, p);
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
@@ -871,6 +902,15 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
         if (D == 32) return launch_tc<1, 128, 2, 8, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
+    }
+    if (g_search_cs2 > 0 && D <= 128) {
+        // experimental (vqb_debug_set_search_cs2): two epilogue warpgroups, each on half of every chunk's columns; one ring
+        // slot less where the second candidate list needs the room
+        switch (D) {
+            case 32:  return launch_tc<1, 128, 2, 8, 1, false, false, 1, false, 2>(tx, th, tl, tq, p, s, pdl);
+            case 64:  return launch_tc<2, 128, 2, 7, 1, false, false, 1, false, 2>(tx, th, tl, tq, p, s, pdl);
+            default:  return launch_tc<4, 128, 1, 7, 1, false, false, 1, false, 2>(tx, th, tl, tq, p, s, pdl);
+        }
     }
     switch (D) {
         case 32:  return launch_tc<1, 128, 2, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);

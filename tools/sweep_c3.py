@@ -59,19 +59,26 @@ def main():
             ev1.record(); torch.cuda.synchronize()
             fwd_ms = ev0.elapsed_time(ev1) / iters
             st = (stats.cpu().float() / iters).tolist()
-            pipe_ms = None
-            if os.environ.get("VQB_SWEEP_PIPE_AB"):              # A/B of the software-pipelined x_lo (streamed 3xTF32 search)
-                idx_ref = idx.clone()
-                lib.vqb_debug_set_search_pipe(0)
+            def timed_fwd():
                 for i in range(2):
                     a.x = xs[i % 2].data_ptr(); _lib.check(lib.vqb_forward(ctypes.byref(a), sp))
                 torch.cuda.synchronize(); ev0.record()
                 for i in range(iters):
                     a.x = xs[i % 2].data_ptr(); _lib.check(lib.vqb_forward(ctypes.byref(a), sp))
                 ev1.record(); torch.cuda.synchronize()
-                pipe_ms = ev0.elapsed_time(ev1) / iters
+                return ev0.elapsed_time(ev1) / iters
+            ab = {}
+            idx_ref = idx.clone()
+            if os.environ.get("VQB_SWEEP_PIPE_AB"):              # software-pipelined x_lo (streamed 3xTF32 search) forced off
+                lib.vqb_debug_set_search_pipe(0)
+                ab["fwd_ms_search_nopipe"] = timed_fwd()
                 lib.vqb_debug_set_search_pipe(-1)
-                assert torch.equal(idx, idx_ref), "pipelined search changed the indices"
+                assert torch.equal(idx, idx_ref), "the pipelined search and the plain one disagree"
+            if os.environ.get("VQB_SWEEP_CS2_AB"):               # experimental column-split epilogue (streamed 1xTF32 search, D <= 128)
+                lib.vqb_debug_set_search_cs2(1)
+                ab["fwd_ms_search_cs2"] = timed_fwd()
+                lib.vqb_debug_set_search_cs2(0)
+                assert torch.equal(idx, idx_ref), "the column-split search changed the indices"
             # scatter-add backward (codebook gradient + histogram), idx from the last forward
             dtab = torch.zeros(K, D, device="cuda"); hist = torch.zeros(K, dtype=torch.int64, device="cuda")
             nbs = ctypes.c_size_t(0)
@@ -94,8 +101,7 @@ def main():
                    "scatter_ms": bwd_ms, "scatter_gbs": bwd_bytes / bwd_ms / 1e6,
                    "scatter_hbm_frac": bwd_bytes / bwd_ms / 1e6 / peaks["hbm_gbs"],
                    "frames_per_s_fwd_bwd": N / ((fwd_ms + bwd_ms) * 1e-3)}
-            if pipe_ms is not None:
-                rec["fwd_ms_search_nopipe"] = pipe_ms
+            rec.update(ab)
             print(json.dumps(rec), flush=True)
             out.append(rec)
     return out
