@@ -162,7 +162,13 @@ __device__ __forceinline__ float prep_tile(const uint8_t* sX, uint8_t* sXlo, uin
 // epilogue warpgroup takes the other half of every chunk's columns (same TMEM lanes, i.e. the same rows) with its own
 // running minimum and candidate list; the two are merged after the last chunk with the threshold of the smaller minimum
 // (each list is a superset of what that threshold admits from its columns, so the re-rank sees every admissible code).
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG, bool NOAUG, int CS>
+// MC = 2 (experimental, streamed 1xTF32 search, selected only by vqb_debug_set_search_mc2): launched as thread-block
+// clusters of two.  CTA (piece & 1) of the pair loads a codebook piece ONCE with TMA multicast into the same ring slot of
+// both CTAs; each CTA arms its own b_full with the full piece size; b_empty counts the tcgen05.commit of BOTH MMA warps
+// (multicast arrive), so a slot is refilled only when both consumers have retired it.  Both CTAs run the same number of
+// tiles (a tile index >= num_tiles is an empty tile: TMA zero-fills its load and clips its store).  Every SM then requests
+// half of the codebook bytes for the same MMA work -- the streamed search at D = 256 is bound by the bytes in flight.
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG, bool NOAUG, int CS, int MC>
 __global__ void __launch_bounds__(64 + 128 * NWG * CS, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
@@ -178,6 +184,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // MMA warp through xlo_free as soon as the third MMA pass of a tile has been issued.
     static_assert(NWG == 1 || (PCODE && XS == 2 && RESIDENT && PASSES == 3), "two warpgroups: p_code mode only");
     static_assert(CS == 1 || (CS == 2 && !PCODE && !RESIDENT && PASSES == 1 && !NOAUG && NWG == 1), "column split: streamed 1xTF32 search only");
+    static_assert(MC == 1 || (MC == 2 && !PCODE && !RESIDENT && PASSES == 1 && NWG == 1 && CS == 1), "multicast pair: streamed 1xTF32 search only");
     constexpr int NTHREADS = 64 + 128 * NWG * CS;
     constexpr int XLS = NWG == 2 ? 1 : XS;                        // x_lo slots
     constexpr int SP_FLOATS = BM * 65;
@@ -211,7 +218,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (PASSES == 3) tma_prefetch_desc(&tm_lo);
         tma_prefetch_desc(&tm_q);
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
-        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], MC); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * CS); }
         mbar_init(xlo_free, 1);
         fence_barrier_init();
@@ -228,6 +235,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    if constexpr (MC == 2) cluster_sync_all();                     // the peer's barriers are initialised before anything is multicast
+    // one past the last tile index of this CTA; MC == 2: every CTA runs ceil(num_tiles / grid) tiles, the surplus ones empty
+    const int tile_end = MC == 2 ? (int)(blockIdx.x + ((p.num_tiles + gridDim.x - 1) / gridDim.x) * gridDim.x) : p.num_tiles;
     const uint32_t tmem_base = *tmem_slot;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[122] = globaltimer_ns();
     constexpr uint32_t IDESC = umma_idesc(2u, BM, BN);
@@ -242,7 +252,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (lane == 0) {
             uint32_t x_it = 0, b_it = 0;
             bool resident_loaded = false;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
                 const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
                 mbar_wait(&x_empty[xs], xph ^ 1);
                 mbar_arrive_expect_tx(&x_full[xs], KB * XBLK);
@@ -259,6 +269,10 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         mbar_arrive_expect_tx(&b_full[bs], PIECE);
                         const bool is_lo = PASSES == 3 && j < 2 * KB && (j & 1);
                         const int kb = PASSES == 3 ? (j >> 1) : j;                 // the bias block has kb == KB
+                        if constexpr (MC == 2) {
+                            if ((b_it & 1u) == cluster_ctarank())
+                                tma_load_2d_mc(sB + (size_t)bs * PIECE, &tm_hi, kb * 32, chunk * BN, &b_full[bs], (uint16_t)3);
+                        } else
                         tma_load_2d(sB + (size_t)bs * PIECE, is_lo ? &tm_lo : &tm_hi, kb * 32, chunk * BN, &b_full[bs]);
                         ++b_it;
                     }
@@ -270,7 +284,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (lane == 0) {
             uint32_t x_it = 0, b_it = 0, c_it = 0;
             bool resident_ready = false;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
                 const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
                 const uint8_t* xt = sX + (size_t)xs * KB * XBLK;
                 const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
@@ -338,6 +352,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                     for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + 2 * k, b + 2 * k, IDESC, true);
                                 }
                             }
+                            if constexpr (MC == 2) umma_commit_mc(&b_empty[bs], (uint16_t)3);   // ... in both CTAs of the pair
+                            else
                             umma_commit(&b_empty[bs]);              // frees the ring slot when these MMAs retire
                             ++b_it;
                         }
@@ -380,7 +396,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if constexpr (PIPE_OK) {
             if (pipe && (int)blockIdx.x < p.num_tiles) xx_next = prep_tile<KB, XS>(sX, sXlo, x_full, xlo_full, r, lane, x_it);
         }
-        for (int tile = blockIdx.x + wg * gridDim.x; tile < p.num_tiles; tile += NWG * gridDim.x) {
+        for (int tile = blockIdx.x + wg * gridDim.x; tile < tile_end; tile += NWG * gridDim.x) {
             const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
             const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
             uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
@@ -738,6 +754,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ---- teardown ----------------------------------------------------------------------------------------
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (MC == 2) cluster_sync_all();                     // no CTA leaves while its peer may still signal its barriers
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[123] = globaltimer_ns();
 }
@@ -777,6 +794,8 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 static int g_search_pipe = -1;                 // -1: default (on unless VQB_SEARCH_NOPIPE); 0 / 1: forced (vqb_debug_set_search_pipe)
 void set_debug_search_pipe(int v) { g_search_pipe = v; }
+static int g_search_mc2 = 0;                   // experimental cluster-of-2 multicast codebook stream (off)
+void set_debug_search_mc2(int v) { g_search_mc2 = v; }
 static int g_search_cs2 = 0;                   // experimental column-split epilogue of the streamed 1xTF32 search (off)
 void set_debug_search_cs2(int v) { g_search_cs2 = v; }
 static unsigned long long* g_timeline = nullptr;
@@ -808,7 +827,7 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1, bool NOAUG = false, int CS = 1>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1, bool NOAUG = false, int CS = 1, int MC = 1>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s, bool pdl) {
     constexpr int XLS = NWG == 2 ? 1 : XS;
@@ -816,9 +835,25 @@ static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtenso
                         (size_t)BS * BN * 128 + (PCODE ? NWG * BM * 65 * 4 : CS * (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
                         ((NOAUG || CS == 2) ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG, CS>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG, CS, MC>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    if (MC == 2) {
+        // clusters of two: an even grid (a CTA whose tile indices all lie beyond num_tiles runs empty tiles only)
+        grid = (grid + 1) & ~1;
+        if (grid > sm_count()) grid = sm_count() & ~1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * NWG * CS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        kernel_event_begin(s);
+        VQB_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, th, tl, tq, p));
+        kernel_event_end(s);
+        VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
+        return VQB_OK;
+    }
     // PDL (only when the caller vouches for the predecessor, VQB_AFTER_ASSEMBLE, or when this call itself has just
     // launched build_operands_kernel): the prologue and the first x tile overlap the operand-preparation kernel
     kernel_event_begin(s);
@@ -902,6 +937,11 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
         if (D == 32) return launch_tc<1, 128, 2, 8, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
+    }
+    if (g_search_mc2 > 0 && D >= 128) {
+        // experimental (vqb_debug_set_search_mc2): clusters of two with the codebook pieces multicast into both CTAs
+        if (D == 128) return launch_tc<4, 128, 1, 8, 1, false, false, 1, false, 1, 2>(tx, th, tl, tq, p, s, pdl);
+        return launch_tc<8, 128, 1, 5, 1, false, false, 1, true, 1, 2>(tx, th, tl, tq, p, s, pdl);
     }
     if (g_search_cs2 > 0 && D <= 128) {
         // experimental (vqb_debug_set_search_cs2): two epilogue warpgroups, each on half of every chunk's columns; one ring

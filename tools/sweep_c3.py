@@ -74,6 +74,11 @@ def main():
                 ab["fwd_ms_search_nopipe"] = timed_fwd()
                 lib.vqb_debug_set_search_pipe(-1)
                 assert torch.equal(idx, idx_ref), "the pipelined search and the plain one disagree"
+            if os.environ.get("VQB_SWEEP_MC2_AB") and D >= 128 and (K > 1024 or D == 256):   # experimental cluster-of-2 multicast stream
+                lib.vqb_debug_set_search_mc2(1)
+                ab["fwd_ms_search_mc2"] = timed_fwd()
+                lib.vqb_debug_set_search_mc2(0)
+                assert torch.equal(idx, idx_ref), "the multicast search changed the indices"
             if os.environ.get("VQB_SWEEP_CS2_AB"):               # experimental column-split epilogue (streamed 1xTF32 search, D <= 128)
                 lib.vqb_debug_set_search_cs2(1)
                 ab["fwd_ms_search_cs2"] = timed_fwd()
