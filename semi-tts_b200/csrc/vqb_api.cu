@@ -87,7 +87,10 @@ extern "C" __attribute__((visibility("default"))) void vqb_debug_set_timeline(vo
 
 // undocumented developer hook (A/B): force the software-pipelined x_lo of the streamed 3xTF32 search on (1) / off (0);
 // -1 = default (on unless VQB_SEARCH_NOPIPE is set)
-namespace vqb { void set_debug_search_pipe(int v); void set_debug_search_cs2(int v); void set_debug_search_mc2(int v); }
+namespace vqb { void set_debug_search_pipe(int v); void set_debug_search_cs2(int v); void set_debug_search_mc2(int v); void set_debug_fwd_x3(int v); }
+// undocumented developer hook: 1 = run the parity-mode (p_code) tensor-core forward with three x slots (bias added by the
+// epilogue, staging sized by K) (experimental, not yet measured on hardware; off by default)
+extern "C" __attribute__((visibility("default"))) void vqb_debug_set_fwd_x3(int v) { vqb::set_debug_fwd_x3(v); }
 // undocumented developer hook: 1 = run the streamed 1xTF32 search (D >= 128) as clusters of two CTAs that share every codebook
 // piece through TMA multicast (experimental, not yet measured on hardware; off by default)
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_mc2(int v) { vqb::set_debug_search_mc2(v); }

@@ -173,8 +173,13 @@ __global__ void __launch_bounds__(64 + 128 * NWG * CS, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
-    constexpr int PIECES = PASSES == 3 ? 2 * KB + 1 : (NOAUG ? KB : KB + 1);   // per chunk: hi/lo per K-block + the bias block
-    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT && !PCODE && NWG == 1), "NOAUG: streamed 1xTF32 search only");
+    constexpr int PIECES = (PASSES == 3 ? 2 * KB : KB) + (NOAUG ? 0 : 1);      // per chunk: hi/lo per K-block + the bias block
+    // NOAUG with PCODE (experimental, vqb_debug_set_fwd_x3): the bias is added by the epilogue from a 64-float copy in shared
+    // memory, which frees the 16 KB A block and the bias piece; with the p_code staging sized by K instead of 64 that
+    // leaves room for a THIRD x slot, so the load of a CTA's third tile no longer waits for its first tile to drain
+    // (profiles/r1e_timeline_fwd.txt: 3.5 us of x_full wait on the third tile)
+    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT && !PCODE && NWG == 1) || (PCODE && RESIDENT && PASSES == 3),
+                  "NOAUG: streamed 1xTF32 search, or the resident p_code kernel");
     constexpr int TMEM_COLS = 2 * BN;
     constexpr int CAP = NOAUG ? 15 : 16;                          // per-row candidate list capacity (SEARCH); 15: fits 227 KB
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
@@ -182,7 +187,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // NWG epilogue warpgroups work on alternate tiles (tile t -> group t % NWG, x slot t % XS, TMEM buffer t & 1,
     // its own p_code staging); with NWG = 2 the x_lo tile is single-buffered (XLS = 1) and handed back by the
     // MMA warp through xlo_free as soon as the third MMA pass of a tile has been issued.
-    static_assert(NWG == 1 || (PCODE && XS == 2 && RESIDENT && PASSES == 3), "two warpgroups: p_code mode only");
+    static_assert(NWG == 1 || (PCODE && XS >= 2 && RESIDENT && PASSES == 3), "two warpgroups: p_code mode only");
     static_assert(CS == 1 || (CS == 2 && !PCODE && !RESIDENT && PASSES == 1 && !NOAUG && NWG == 1), "column split: streamed 1xTF32 search only");
     static_assert(MC == 1 || (MC == 2 && !PCODE && !RESIDENT && PASSES == 1 && NWG == 1 && CS == 1), "multicast pair: streamed 1xTF32 search only");
     constexpr int NTHREADS = 64 + 128 * NWG * CS;
@@ -197,7 +202,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sB = sAug + (NOAUG ? 0 : XBLK);                                   // [BS][PIECE]
     float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65] p_code staging (PCODE)
     uint2* sCand = reinterpret_cast<uint2*>(sP);                               // [CAP][128] (value, code)  (SEARCH)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * SP_FLOATS * 4 : CS * CAP * BM * 8));
+    const int sp_floats = (PCODE && NOAUG) ? BM * (p.K | 1) : SP_FLOATS;      // staging of one warpgroup
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * sp_floats * 4 : CS * CAP * BM * 8));
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
     uint64_t* xlo_full = x_empty + XS;
@@ -311,6 +317,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                             for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, (kb | k) != 0);
                         }
+                        if constexpr (!NOAUG)
                         umma_tf32(d_tmem, umma_desc_sw128(sAug), umma_desc_sw128(sB + (size_t)(PIECES - 1) * PIECE), IDESC, true);
                         if (PASSES == 3) {
 #pragma unroll
@@ -372,7 +379,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int cg = CS == 2 ? (warp - 2) >> 2 : 0;               // column group of this warpgroup (CS == 2)
         const int et = ((warp - 2) & 3) * 32 + lane;                // 0..127 within the warpgroup
         const uint32_t bar_id = 1 + wg;                             // named barrier of this warpgroup
-        float* sPg = sP + (PCODE ? wg * SP_FLOATS : 0);
+        float* sPg = sP + (PCODE ? wg * sp_floats : 0);
         const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
         const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
         const float emax = PCODE ? 0.f : __ldg(p.emax);
@@ -390,6 +397,12 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // piece of tile t, the ring frees slots only as the MMA consumes them, and the MMA can run two chunks ahead of
         // the epilogue (two TMEM buffers) -- with more chunks the wait for x(t+1) at the top of tile t would close a
         // cycle (measured: it does; B200, K = 1024).  Measured at N = 2^20, K = 256, D = 64: 0.719 -> 0.658 ms.
+        float* sBias = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);   // [64] (PCODE && NOAUG)
+        if constexpr (PCODE && NOAUG) {
+            // both warpgroups write the same values; each waits for its own copy pass only
+            if (et < 64) sBias[et] = et < p.K ? __ldg(p.bias + et) : (linear ? -1e30f : 1e30f);
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
         constexpr bool PIPE_OK = !PCODE && !RESIDENT && PASSES == 3 && XS == 2 && NWG == 1;
         const bool pipe = PIPE_OK && p.num_chunks <= 2 && (p.flags & 0x40000000u) != 0;
         float xx_next = 0.f;
@@ -477,7 +490,9 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int k = 0; k < 64; ++k) {
-                    const float s2 = mul * (add + v[k]);            // padded codes: acc = +-1e30 -> s2 = -huge
+                    // NOAUG: acc = -2 x.e (or x.w) only; (|x|^2 + |e|^2) - 2 x.e in the reference's own association (:210-212)
+                    const float s2 = (PCODE && NOAUG) ? mul * ((add + sBias[k]) + v[k])
+                                                      : mul * (add + v[k]);            // padded codes: acc = +-1e30 -> s2 = -huge
                     v[k] = s2;
                     m4[k & 3] = fmaxf(m4[k & 3], s2);
                 }
@@ -794,10 +809,15 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 static int g_search_pipe = -1;                 // -1: default (on unless VQB_SEARCH_NOPIPE); 0 / 1: forced (vqb_debug_set_search_pipe)
 void set_debug_search_pipe(int v) { g_search_pipe = v; }
-static int g_search_mc2 = 0;                   // experimental cluster-of-2 multicast codebook stream (off)
+// experimental kernel variants, all OFF unless a developer asks for them: -1 = follow the environment variable named
+// below (unset = off), 0 / 1 = forced by the matching vqb_debug_set_* hook
+static int g_fwd_x3 = -1;                      // VQB_FWD_X3: three-slot p_code forward
+void set_debug_fwd_x3(int v) { g_fwd_x3 = v; }
+static int g_search_mc2 = -1;                  // VQB_SEARCH_MC2: cluster-of-2 multicast codebook stream
 void set_debug_search_mc2(int v) { g_search_mc2 = v; }
-static int g_search_cs2 = 0;                   // experimental column-split epilogue of the streamed 1xTF32 search (off)
+static int g_search_cs2 = -1;                  // VQB_SEARCH_CS2: column-split epilogue of the streamed 1xTF32 search
 void set_debug_search_cs2(int v) { g_search_cs2 = v; }
+static bool experiment_on(int forced, const char* env) { return forced < 0 ? getenv(env) != nullptr : forced > 0; }
 static unsigned long long* g_timeline = nullptr;
 void set_debug_timeline(void* p) { g_timeline = reinterpret_cast<unsigned long long*>(p); }
 unsigned long long* get_debug_timeline() { return g_timeline; }
@@ -832,7 +852,7 @@ static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtenso
                      cudaStream_t s, bool pdl) {
     constexpr int XLS = NWG == 2 ? 1 : XS;
     const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
-                        (size_t)BS * BN * 128 + (PCODE ? NWG * BM * 65 * 4 : CS * (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
+                        (size_t)BS * BN * 128 + (PCODE ? NWG * BM * ((PCODE && NOAUG) ? (p.K | 1) : 65) * 4 : CS * (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
                         ((NOAUG || CS == 2) ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
     auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG, CS, MC>;
@@ -922,6 +942,16 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
 
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     //                      KB  BN  XS BS PASSES RESIDENT PCODE
+    if (mode == TC_PCODE && experiment_on(g_fwd_x3, "VQB_FWD_X3")) {
+        // experimental (vqb_debug_set_fwd_x3): bias added by the epilogue (no A block, no bias piece), staging sized by K,
+        // three x slots.  Taken only when it fits: K = 64 at D = 64 is 768 bytes over and stays on the default kernel.
+        const size_t need = (size_t)3 * (D / 32) * XBLK + (size_t)(D / 32) * XBLK + (size_t)2 * (D / 32) * 64 * 128 +
+                            (size_t)2 * BM * (K | 1) * 4 + 1024 + 256 + 2 * BM * 4 + 2 * 64 * 4;
+        if ((int)need <= max_optin_smem()) {
+            if (D == 32) return launch_tc<1, 64, 3, 2, 3, true, true, 2, true>(tx, th, tl, tq, p, s, pdl);
+            return launch_tc<2, 64, 3, 4, 3, true, true, 2, true>(tx, th, tl, tq, p, s, pdl);
+        }
+    }
     if (mode == TC_PCODE) {
         if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true, 2>(tx, th, tl, tq, p, s, pdl);
         return launch_tc<2, 64, 2, 5, 3, true, true, 2>(tx, th, tl, tq, p, s, pdl);
@@ -938,12 +968,12 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
         if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
         return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
     }
-    if (g_search_mc2 > 0 && D >= 128) {
+    if (experiment_on(g_search_mc2, "VQB_SEARCH_MC2") && D >= 128) {
         // experimental (vqb_debug_set_search_mc2): clusters of two with the codebook pieces multicast into both CTAs
         if (D == 128) return launch_tc<4, 128, 1, 8, 1, false, false, 1, false, 1, 2>(tx, th, tl, tq, p, s, pdl);
         return launch_tc<8, 128, 1, 5, 1, false, false, 1, true, 1, 2>(tx, th, tl, tq, p, s, pdl);
     }
-    if (g_search_cs2 > 0 && D <= 128) {
+    if (experiment_on(g_search_cs2, "VQB_SEARCH_CS2") && D <= 128) {
         // experimental (vqb_debug_set_search_cs2): two epilogue warpgroups, each on half of every chunk's columns; one ring
         // slot less where the second candidate list needs the room
         switch (D) {

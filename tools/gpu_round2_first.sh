@@ -1,8 +1,8 @@
 #!/bin/bash
 # First GPU visit of round 2: what round 1 could no longer run.
 #   1. the whole GPU suite (includes the tests added after the last full run of round 1)
-#   2. the experimental search variants written blind at the end of round 1 (column-split second epilogue warpgroup,
-#      cluster-of-2 multicast codebook stream): correctness first, each under its own timeout (their mbarrier waits are
+#   2. the experimental variants written blind at the end of round 1 (three-slot p_code forward, column-split second epilogue
+#      warpgroup, cluster-of-2 multicast codebook stream): correctness first, each under its own timeout (their mbarrier waits are
 #      bounded: a protocol bug traps after 4 s instead of hanging), then the A/B timings of the config-3 sweep
 #   3. bench + config-5 tool
 mkdir -p gpurun_out
@@ -11,6 +11,10 @@ grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/pytest_gpu.log | cut -c1-300 |
 VQB_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_tensor_search.py -q --tb=short -k "column_split" > gpurun_out/exp_cs2.log 2>&1; echo "exit $?" >> gpurun_out/exp_cs2.log
 VQB_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_tensor_search.py -q --tb=short -k "multicast_pair" > gpurun_out/exp_mc2.log 2>&1; echo "exit $?" >> gpurun_out/exp_mc2.log
 tail -5 gpurun_out/exp_cs2.log | cut -c1-300; tail -5 gpurun_out/exp_mc2.log | cut -c1-300
+# the three-slot p_code forward: the module parity tests and the bench with the variant switched on by the environment
+VQB_FWD_X3=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q --tb=short -k "module_vs_reference or config2 or config5 or no_grad" > gpurun_out/exp_x3.log 2>&1; echo "exit $?" >> gpurun_out/exp_x3.log
+tail -5 gpurun_out/exp_x3.log | cut -c1-300
+VQB_FWD_X3=1 timeout 300 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_x3.json 2> gpurun_out/bench_x3.err; cut -c1-400 gpurun_out/bench_x3.json
 VQB_SWEEP_PIPE_AB=1 VQB_SWEEP_CS2_AB=1 timeout 300 python tools/sweep_c3.py > gpurun_out/sweep_ab_cs2.jsonl 2> gpurun_out/sweep_ab_cs2.err
 VQB_SWEEP_MC2_AB=1 VQB_SWEEP_POINTS="4096x256,8192x256" timeout 300 python tools/sweep_c3.py > gpurun_out/sweep_ab_mc2.jsonl 2> gpurun_out/sweep_ab_mc2.err
 python - <<'PY'
