@@ -78,3 +78,15 @@ def test_model_notices_a_wrong_barrier_count():
         assert failed
     finally:
         PS.Cta.__init__ = real_init
+
+
+def test_model_notices_an_x_lo_slot_rewritten_under_the_mma():
+    """Two warpgroups share ONE x_lo tile; without the xlo_free hand-back the second warpgroup rewrites it while the third
+    MMA pass of the previous tile may still read it."""
+    cfg = dict(SHIPPED["p_code D=64 (two warpgroups, resident codebook)"], tiles=8, grid=2, BUG_skip_xlo_free=True)
+    failed = False
+    try:
+        failed = PS.check(cfg, seeds=40) is not None
+    except AssertionError as e:
+        failed = "x_lo slot" in str(e)
+    assert failed

@@ -58,6 +58,11 @@ class Cta:
         self.nb3, self.nb4 = NamedBar(2), NamedBar(2)
         self.rank = rank
         self.slot_busy = [False] * c["BS"]         # ring slot holds a piece the MMA of THIS CTA has not retired yet
+        self.xlo_reading = [False] * c["XS"]       # the MMA's third pass may still read this x_lo slot
+
+    def write_xlo(self, xls):                      # the epilogue warps overwrite an x_lo slot, then arrive on xlo_full
+        assert not self.xlo_reading[xls], "x_lo slot %d of CTA %d rewritten under the MMA's third pass" % (xls, self.rank)
+        self.xlo_full[xls].arrive(4)
 
     def land(self, bs):                            # TMA bytes of a codebook piece arrive in ring slot bs
         assert not self.slot_busy[bs], "ring slot %d of CTA %d overwritten while its MMA may still read it" % (bs, self.rank)
@@ -132,12 +137,14 @@ class Sim:
         resident_ready = False
         commits = []                                                     # tcgen05.commit arrivals retire in issue order
 
-        def commit(*bars, frees=None):
+        def commit(*bars, frees=None, xlo_done=None):
             due = max([self.now] + [d for d, _ in commits]) + self.rng.randint(1, 6)
 
-            def fn(bs=bars, fr=frees):
+            def fn(bs=bars, fr=frees, xd=xlo_done):
                 if fr is not None and not c["RESIDENT"]:
                     k.slot_busy[fr] = False
+                if xd is not None:
+                    k.xlo_reading[xd] = False
                 for b in bs:
                     b.arrive(1)
             commits.append((due, fn))
@@ -149,7 +156,8 @@ class Sim:
             yield ("wait", k.x_full[xs], xph)
             if c["PASSES"] == 3 and not c["RESIDENT"]:
                 yield ("wait", k.xlo_full[xls], xlph)
-            for _chunk in range(c["chunks"]):
+                k.xlo_reading[xls] = True
+            for chunk_i in range(c["chunks"]):
                 buf, tph = c_it & 1, (c_it >> 1) & 1
                 yield ("wait", k.t_empty[buf], tph ^ 1)
                 if c["RESIDENT"]:
@@ -159,8 +167,9 @@ class Sim:
                         resident_ready = True
                     if c["PASSES"] == 3:
                         yield ("wait", k.xlo_full[xls], xlph)
+                        k.xlo_reading[xls] = True
                         if c["NWG"] == 2:
-                            commit(k.xlo_free)
+                            commit(k.xlo_free, xlo_done=xls)
                 else:
                     for _j in range(c["PIECES"]):
                         bs, bph = b_it % c["BS"], (b_it // c["BS"]) & 1
@@ -170,7 +179,8 @@ class Sim:
                         else:
                             commit(k.b_empty[bs], frees=bs)
                         b_it += 1
-                commit(k.t_full[buf])
+                last = chunk_i == c["chunks"] - 1 and c["PASSES"] == 3 and c["NWG"] != 2
+                commit(k.t_full[buf], xlo_done=xls if last else None)
                 c_it += 1
             x_it += 1
 
@@ -184,7 +194,7 @@ class Sim:
         def prep(it):                                                    # prep_tile<KB, XS>
             xs, xph = it % c["XS"], (it // c["XS"]) & 1
             yield ("wait", k.x_full[xs], xph)
-            k.xlo_full[xs].arrive(4)
+            k.write_xlo(xs)
 
         if pipe and tiles:
             yield from prep(x_it)
@@ -196,10 +206,10 @@ class Sim:
                     yield from prep(x_it + 1)
             else:
                 yield ("wait", k.x_full[xs], xph)
-                if c["NWG"] == 2:
+                if c["NWG"] == 2 and not c.get("BUG_skip_xlo_free"):         # (the BUG_ key exists for the model's own test)
                     yield ("wait", k.xlo_free, xlph ^ 1)
                 if c["PASSES"] == 3:
-                    k.xlo_full[xls].arrive(4)
+                    k.write_xlo(xls)
             if c["PCODE"]:
                 buf, tph = c_it & 1, (c_it >> 1) & 1
                 yield ("wait", k.t_full[buf], tph)
