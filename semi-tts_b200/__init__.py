@@ -10,8 +10,8 @@ from .functional import (vq_l2, vq_linear, codebook_lookup, assemble_table, vq_s
 from .embed import L2Embedding, SeperateEmbedding, read_phn_attr
 from .usage import UsageHistogram
 from .segment import mean_forward, row_argmax, ctc_log_probs
-from .patch import install_into_reference
+from .patch import install_into_reference, uninstall_from_reference
 from . import dist
 
 __all__ = ["L2Embedding", "SeperateEmbedding", "read_phn_attr", "vq_l2", "vq_linear", "vq_search",
-           "codebook_lookup", "assemble_table", "UsageHistogram", "mean_forward", "row_argmax", "ctc_log_probs", "install_into_reference", "dist", "_lib"]
+           "codebook_lookup", "assemble_table", "UsageHistogram", "mean_forward", "row_argmax", "ctc_log_probs", "install_into_reference", "uninstall_from_reference", "dist", "_lib"]

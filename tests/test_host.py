@@ -243,6 +243,7 @@ def test_drop_in_into_reference_vqvae_construction():
     V_ref = ref_import.import_reference_vqvae()
     import semi_tts_b200 as V
     stock = (ref_embed.L2Embedding, ref_embed.SeperateEmbedding, V_ref.L2Embedding, V_ref.SeperateEmbedding)
+    stock_mean_forward = V_ref.VQVAE.mean_forward
     with ref_import.reference_cwd():
         cfg = yaml.load(open("config/semi-multi-spkr-paired-data.yaml"), Loader=yaml.FullLoader)
         torch.manual_seed(0)
@@ -252,7 +253,9 @@ def test_drop_in_into_reference_vqvae_construction():
             torch.manual_seed(0)
             new_model = V_ref.VQVAE(80, 1025, 43, 109, **copy.deepcopy(cfg["model"]))
         finally:
-            ref_embed.L2Embedding, ref_embed.SeperateEmbedding, V_ref.L2Embedding, V_ref.SeperateEmbedding = stock
+            V.uninstall_from_reference()
+    assert (ref_embed.L2Embedding, ref_embed.SeperateEmbedding, V_ref.L2Embedding, V_ref.SeperateEmbedding) == stock
+    assert V_ref.VQVAE.mean_forward is stock_mean_forward      # the run-length collapse is put back as well
     assert type(new_model.codebook) is V.L2Embedding
     a, b = ref_model.state_dict(), new_model.state_dict()
     assert list(a.keys()) == list(b.keys())
