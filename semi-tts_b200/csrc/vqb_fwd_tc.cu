@@ -834,6 +834,10 @@ static TcMode tc_mode(const vqb_fwd_args* a) {
     if (a->p_code) return (K <= 64 && (D == 32 || D == 64)) ? TC_PCODE : TC_NONE;
     if (!(a->flags & VQB_SCORE_L2)) return TC_NONE;
     if (D != 32 && D != 64 && D != 128 && D != 256) return TC_NONE;
+    // developer A/B (VQB_SEARCH_MODE=1): the streamed 1xTF32 search with its wider re-rank window also below K = 1024 --
+    // extrapolating the K = 4096 row of the config-3 sweep it should beat the three-pass kernel at D = 64 (unmeasured)
+    static const char* force = getenv("VQB_SEARCH_MODE");
+    if (force && force[0] == '1' && K > 128) return TC_SEARCH1;
     if (K <= 1024 && D <= 128) return TC_SEARCH3;
     return TC_SEARCH1;
 }

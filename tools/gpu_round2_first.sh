@@ -17,9 +17,13 @@ tail -5 gpurun_out/exp_x3.log | cut -c1-300
 VQB_FWD_X3=1 timeout 300 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_x3.json 2> gpurun_out/bench_x3.err; cut -c1-400 gpurun_out/bench_x3.json
 VQB_SWEEP_PIPE_AB=1 VQB_SWEEP_CS2_AB=1 timeout 300 python tools/sweep_c3.py > gpurun_out/sweep_ab_cs2.jsonl 2> gpurun_out/sweep_ab_cs2.err
 VQB_SWEEP_MC2_AB=1 VQB_SWEEP_POINTS="4096x256,8192x256" timeout 300 python tools/sweep_c3.py > gpurun_out/sweep_ab_mc2.jsonl 2> gpurun_out/sweep_ab_mc2.err
+# one-pass (1xTF32 + re-rank window) instead of three-pass search below K = 1024: search tests, then the sweep rows it changes
+VQB_SEARCH_MODE=1 timeout 120 python -m pytest tests/test_gpu_tensor_search.py -q --tb=short > gpurun_out/exp_mode1.log 2>&1; echo "exit $?" >> gpurun_out/exp_mode1.log
+tail -3 gpurun_out/exp_mode1.log | cut -c1-300
+VQB_SEARCH_MODE=1 VQB_SWEEP_POINTS="256x64,1024x64" timeout 120 python tools/sweep_c3.py > gpurun_out/sweep_mode1.jsonl 2> gpurun_out/sweep_mode1.err
 python - <<'PY'
 import json
-for f in ("gpurun_out/sweep_ab_cs2.jsonl", "gpurun_out/sweep_ab_mc2.jsonl"):
+for f in ("gpurun_out/sweep_ab_cs2.jsonl", "gpurun_out/sweep_ab_mc2.jsonl", "gpurun_out/sweep_mode1.jsonl"):
     for l in open(f):
         d = json.loads(l)
         print(f[-12:], d["K"], d["D"], {k: round(v, 4) for k, v in d.items() if k.startswith("fwd_ms")})
