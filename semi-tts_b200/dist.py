@@ -14,23 +14,6 @@ def shard_bounds(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def pack(tensors):
-    """Flatten a list of tensors (None skipped) into one fp32 buffer; returns (flat, metas)."""
-    live = [t for t in tensors if t is not None]
-    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in live]) if live else torch.zeros(0)
-    return flat
-
-
-def unpack_into(flat, tensors):
-    off = 0
-    for t in tensors:
-        if t is None:
-            continue
-        n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
-        off += n
-
-
 def _flat_view(grads):
     """If the gradients are consecutive views of one storage (as the backward of this package produces them),
     return that span as a single 1-D tensor; otherwise None."""
