@@ -90,3 +90,12 @@ def test_model_notices_an_x_lo_slot_rewritten_under_the_mma():
     except AssertionError as e:
         failed = "x_lo slot" in str(e)
     assert failed
+
+
+@pytest.mark.parametrize("chunks,BS,PIECES", [(8, 4, 5), (3, 4, 5), (8, 8, 3), (32, 4, 5), (2, 4, 5)])
+def test_design_study_late_prepared_x_lo_is_deadlock_free_for_any_chunk_count(chunks, BS, PIECES):
+    """Design study for round 2 (not in the kernel): producing x_lo of tile t+1 AFTER the chunk loop of tile t -- i.e.
+    under the re-rank, gather and store of tile t only -- has no cycle whatever the number of chunks, because by then
+    the MMA has retired every piece of tile t and the producer has moved on to x(t+1)."""
+    cfg = dict(XS=2, BS=BS, PIECES=PIECES, chunks=chunks, PASSES=3, PIPE=True, PIPE_LATE=True, tiles=9, grid=2)
+    assert PS.check(cfg, seeds=25) is None

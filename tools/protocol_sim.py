@@ -201,8 +201,9 @@ class Sim:
         for n, tile in enumerate(tiles):
             xs, xph = x_it % c["XS"], (x_it // c["XS"]) & 1
             xls, xlph = (0, x_it & 1) if c["NWG"] == 2 else (xs, xph)
+            late = pipe and c.get("PIPE_LATE")                         # design study: prepare tile t+1 AFTER the chunk loop of tile t
             if pipe:
-                if n + 1 < len(tiles):
+                if n + 1 < len(tiles) and not late:
                     yield from prep(x_it + 1)
             else:
                 yield ("wait", k.x_full[xs], xph)
@@ -222,6 +223,8 @@ class Sim:
                     yield ("step",)
                     k.t_empty[buf].arrive(4)
                     c_it += 1
+            if late and n + 1 < len(tiles):
+                yield from prep(x_it + 1)
             if c["CS"] == 2:
                 yield ("named", k.nb3)
                 if cg == 1:
