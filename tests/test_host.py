@@ -86,6 +86,44 @@ int main(void) {
     assert out.stdout.startswith("devices ")
 
 
+def test_abi_argument_validation_never_crashes_on_random_arguments():
+    """Host-side validation of the C ABI under random (mostly invalid) shapes and flags: always a return code and, on
+    failure, a non-empty message -- never a crash; and without a device the compute entry points refuse to run."""
+    import semi_tts_b200 as V
+    lib = V._lib.load()
+    rng = np.random.default_rng(7)
+    has_gpu = lib.vqb_device_count() > 0
+    for _ in range(300):
+        a = V._lib.FwdArgs()
+        a.struct_size = ctypes.sizeof(V._lib.FwdArgs) if rng.random() < 0.9 else int(rng.integers(0, 400))
+        a.flags = int(rng.integers(0, 1 << 8))
+        a.n_rows = int(rng.choice([-5, 0, 1, 127, 128, 129, 51200, 1 << 20, 1 << 31, 1 << 40]))
+        a.dim = int(rng.choice([-4, 0, 1, 3, 4, 20, 32, 62, 64, 128, 256, 512, 516, 4096]))
+        a.n_codes = int(rng.choice([-1, 0, 1, 43, 64, 65, 300, 8192, 1 << 24, 1 << 30]))
+        n = ctypes.c_size_t(12345)
+        rc = lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(n))
+        assert rc in (0, 1, 2, 3, 4)
+        if rc:
+            assert len(lib.vqb_last_error()) > 0 and n.value == 0
+        assert isinstance(lib.vqb_forward_kernel_name(ctypes.byref(a)), bytes)
+        b = V._lib.BwdArgs()
+        b.struct_size = ctypes.sizeof(V._lib.BwdArgs) if rng.random() < 0.9 else int(rng.integers(0, 400))
+        b.flags, b.n_rows, b.dim, b.n_codes = a.flags, a.n_rows, a.dim, a.n_codes
+        b.n_real_rows = int(rng.integers(-3, 1 << 20))
+        rc = lib.vqb_backward_workspace(ctypes.byref(b), ctypes.byref(n))
+        assert rc in (0, 1, 2, 3, 4)
+        assert isinstance(lib.vqb_backward_kernel_name(ctypes.byref(b)), bytes)
+        sb = ctypes.c_size_t(0)
+        assert lib.vqb_scatter_workspace(max(a.n_rows, 0), max(a.n_codes, 1), max(a.dim, 4), ctypes.byref(sb)) in (0, 1)
+        if not has_gpu:
+            # all pointers are NULL here: either the arguments are rejected, or an empty call is a no-op, or the missing
+            # device is reported -- the library never dereferences anything on this path
+            rc = lib.vqb_forward(ctypes.byref(a), None)
+            assert rc in (0, 1, 4)
+            if rc == 0:
+                assert a.n_rows == 0
+
+
 def test_struct_size_mismatch_is_an_error_without_a_gpu():
     import semi_tts_b200 as V
     lib = V._lib.load()
