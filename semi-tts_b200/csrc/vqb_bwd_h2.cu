@@ -911,11 +911,20 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
     vqb_bwd_h2_kernel<<<grid, H_THREADS, smem, s>>>(tx, tg, td, p, stage_bytes);
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_h2_kernel");
+    return launch_bwd_reduce(a, p.partial, grid, s, p.dbg);
+}
+
+// Behind either main backward kernel (vqb_bwd_h2_kernel, vqb_bwd_pcode_kernel): the per-CTA partial records -> gradients.
+// With a tail: ONE kernel (fixed-order sum, table backward, sum over GPUs), PDL-chained to the main kernel; otherwise the
+// fixed-order reduction into the caller's accumulators.
+int launch_bwd_reduce(const vqb_bwd_args* a, const float* partial, int grid, cudaStream_t s, unsigned long long* dbg) {
+    const int64_t K = a->n_codes;
+    const bool l2 = (a->flags & VQB_SCORE_L2) != 0;
     if (a->tail) {
         const vqb_bwd_tail* tl = a->tail;
         TailP t;
         t.table = a->gather_table; t.attr = tl->phn_attr; t.d_flat = tl->d_flat; t.counter = tl->counter;
-        t.peer_bufs = tl->peer_bufs; t.dbg = p.dbg; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
+        t.peer_bufs = tl->peer_bufs; t.dbg = dbg; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
         const int Dl = 64 - t.Da;
         t.n_learn_blocks = (int)ceil_div(K * Dl, 32);
         cudaLaunchConfig_t cfg = {};
@@ -924,13 +933,13 @@ int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s) {
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = getenv("VQB_NO_PDL") ? 0 : 1;
-        VQB_CUDA(cudaLaunchKernelEx(&cfg, bwd_tail_h2_kernel, (const float*)p.partial, grid, (int)K, t));
+        VQB_CUDA(cudaLaunchKernelEx(&cfg, bwd_tail_h2_kernel, partial, grid, (int)K, t));
         VQB_CHECK_LAUNCH("bwd_tail_h2_kernel");
         return VQB_OK;
     }
     float* dG = l2 ? nullptr : a->d_gather;
     const int n_out = (int)((dG ? 2 : 1) * K * 64 + K);
-    reduce_partials_h2_kernel<<<(unsigned)ceil_div(n_out, 32), dim3(32, 32), 0, s>>>(p.partial, grid, (int)K, a->d_score_w, dG,
+    reduce_partials_h2_kernel<<<(unsigned)ceil_div(n_out, 32), dim3(32, 32), 0, s>>>(partial, grid, (int)K, a->d_score_w, dG,
                                                                                   a->colsum);
     VQB_CHECK_LAUNCH("reduce_partials_h2_kernel");
     return VQB_OK;

@@ -99,15 +99,20 @@ size_t scatter_workspace_bytes(int64_t n, int64_t K, int64_t D);
 bool forward_tensor_supported(const vqb_fwd_args* a);
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
 int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
-bool backward_tensor_supported(const vqb_bwd_args* a);
-int backward_tensor_workspace(const vqb_bwd_args* a, size_t* bytes);
-int launch_backward_tensor(const vqb_bwd_args* a, cudaStream_t s);
 // fp16x2 generation of the parity-mode backward (vqb_bwd_h2.cu); VQB_BWD_KERNEL=tf32 in the environment selects the
 // first-generation tf32 kernel instead (kept as a comparator)
 bool backward_h2_supported(const vqb_bwd_args* a);
 int backward_h2_workspace(const vqb_bwd_args* a, size_t* bytes);
 int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s);
 size_t exchange_bytes(int64_t n_flat, int world);
+int launch_bwd_reduce(const vqb_bwd_args* a, const float* partial, int grid, cudaStream_t s, unsigned long long* dbg);
+// third generation of the parity-mode kernels (vqb_fwd_pc.cu, vqb_bwd_pc.cu): one tile per CTA at a time, several CTAs per SM
+bool forward_pcode_supported(const vqb_fwd_args* a);
+size_t forward_pcode_workspace(const vqb_fwd_args* a);
+int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s);
+bool backward_pcode_supported(const vqb_bwd_args* a);
+size_t backward_pcode_workspace(const vqb_bwd_args* a);
+int launch_backward_pcode(const vqb_bwd_args* a, cudaStream_t s);
 // any-K p_code-route backward through a coefficient matrix in the workspace (vqb_bwd_generic.cu)
 bool backward_generic_needed(const vqb_bwd_args* a);
 size_t backward_generic_workspace(const vqb_bwd_args* a);

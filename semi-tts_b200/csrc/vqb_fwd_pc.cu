@@ -1,0 +1,471 @@
+// Parity-mode forward of the quantizer (p_code is part of the result; K <= 64, D in {32, 64}) on tcgen05 / TMEM / TMA:
+// the whole of L2Embedding.forward (src/embed.py:105-147) or SeperateEmbedding.forward (:187-205) in one kernel.
+//
+//   scores (neg_batch_l2 :208-213 with the temperature :115, or F.linear :190)  ->  softmax (:127)  ->  argmax over the
+//   probabilities (:130)  ->  gather (:134 / :194-197)  ->  straight-through (:145)  ->  usage histogram.
+//
+// Shape of the kernel.  The path is HBM-bound with 5.5 kflop per row, so what matters is how many rows are in flight per
+// SM, not the MMA rate: a CTA is 128 threads and ONE tile of 128 rows at a time, thread = row = TMEM lane, no warp
+// specialisation -- a straight chain  TMA load -> split -> MMA -> softmax -> gather -> TMA store  per tile -- and THREE
+// CTAs are resident per SM (67 KB of shared memory, <= 168 registers), so every SM works on 384 rows at once and the
+// chain of one CTA is hidden behind the other two.  At BASELINE config 2 (51 200 rows = 400 tiles <= 444 CTA slots) the
+// whole input is requested from HBM in the first microsecond of the kernel.
+//
+// Precision.  x and the score table are carried as fp16x2 (vqb_f16x2.cuh): the row thread rescales its row by a power of
+// two and splits it IN PLACE over the raw TMA tile (x_hi | x_lo, 16 KB each), the table image comes ready-made from the
+// table assembly; acc = x_lo.e_lo + x_lo.e_hi + x_hi.e_lo + x_hi.e_hi, 4 x D/16 MMAs of kind::f16 with fp32 accumulation
+// in TMEM.  The distance is then formed in the reference's own association, (|x|^2 + |e|^2) - 2 x.e (:210-212).
+// Index exactness.  |acc - exact fp32 dot| is bounded (see `win` below); a row whose two best scores lie within that
+// window re-evaluates every code inside it in exact fp32 -- same expression and fmaf order as the CUDA-core kernel
+// (vqb_fwd_simt.cu) -- before the softmax, so p_code, its argmax and the gathered codeword agree with the exact kernel.
+#include <cudaTypedefs.h>
+#include <math.h>
+#include "vqb_common.cuh"
+#include "vqb_tc.cuh"
+#include "vqb_f16x2.cuh"
+
+namespace vqb {
+using namespace tc;
+
+constexpr int PM = 128;                 // rows per tile (UMMA M)
+constexpr int PBLK = PM * 128;          // one [128 rows][128 B] block = 16 KB
+
+struct PcP {
+    const float* x;            // [N][D] (exact re-rank only; the tiles arrive by TMA)
+    const float* table;        // [K][D] fp32 score table (exact re-rank)
+    const float* gtab;         // [K][D] fp32 gather table
+    const float* bias;         // [K]    |e|^2 (L2) or b (LINEAR)
+    const float* temp;         // [1]
+    const uint8_t* img;        // operand image of the score table (vqb_f16x2.cuh)
+    float* pcode;
+    long long* idx;
+    unsigned long long* hist;
+    double* sqerr;
+    unsigned int* stats;       // [0] += rows re-ranked in exact fp32 (may be NULL)
+    unsigned long long* dbg;   // optional timeline buffer (vqb_debug_set_timeline), NULL in production
+    int N, K, num_tiles;
+    int se_bytes;              // shared-memory bytes of the table region (image, later the fp32 gather table)
+    unsigned flags;
+};
+
+#define VQB_PTL(tag) do { if (p.dbg && threadIdx.x == 0 && blockIdx.x == 0 && tl_n < 60) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
+
+// exact fp32 score (log2 domain) of one code for one row, read from global memory: the rare re-rank path.
+// Same expression and fmaf order as vqb_fwd_simt.cu (dot_chunk + score_of).
+template <int D>
+__device__ __noinline__ float exact_s2(const float* __restrict__ xrow, const float* __restrict__ e, float xx, float b,
+                                       float mul, bool linear) {
+    float dot = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < D / 4; ++c) {
+        const float4 xv = ldg4(xrow + 4 * c), w = ldg4(e + 4 * c);
+        dot = fmaf(xv.x, w.x, dot); dot = fmaf(xv.y, w.y, dot);
+        dot = fmaf(xv.z, w.z, dot); dot = fmaf(xv.w, w.w, dot);
+    }
+    if (linear) return mul * (dot + b);
+    return mul * __fsub_rn(__fadd_rn(xx, b), 2.f * dot);
+}
+
+template <int KP, int D>
+__global__ void __launch_bounds__(PM, 3)
+vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, PcP p) {
+    constexpr int KB = D / 32;                      // raw fp32 blocks of an x tile
+    constexpr int KS = D / 16;                      // MMA K-steps
+    constexpr int DP = D + 4;                       // padded row of the fp32 gather table in shared memory
+    constexpr int TABV = (64 * D / 4 + PM - 1) / PM;   // float4 per thread that cover a [64][D] table
+    const int K = p.K;
+    const int KO = K | 1;                           // p_code staging row stride (odd: conflict-free)
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sX = smem;                                             // [2][16 KB] raw x -> x_hi | x_lo -> new_latent
+    uint8_t* sE = sX + 2 * PBLK;                                    // e_hi | e_lo image, later the fp32 gather table
+    float* sTab = reinterpret_cast<float*>(sE);
+    float* sP = reinterpret_cast<float*>(sE + p.se_bytes);          // [128][KO] p_code staging
+    float* sBias = sP + PM * KO;                                    // [64]
+    float* sRed = sBias + 64;                                       // [4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 4);
+    uint64_t* x_full = bars;
+    uint64_t* e_full = bars + 1;
+    uint64_t* mma_done = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+    int tl_n = 0;
+    if (p.dbg && r == 0 && blockIdx.x == 0) p.dbg[60] = globaltimer_ns();
+
+    if (r == 0) {
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_q);
+        mbar_init(x_full, 1); mbar_init(e_full, 1); mbar_init(mma_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    // PDL: the next kernel in the stream may begin its prologue; everything below that depends on the kernel BEFORE this
+    // one (the table assembly: image, table, bias) sits behind pdl_wait().  x is older than that kernel.
+    pdl_launch();
+    VQB_PTL(1);
+
+    const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
+    const bool skip = (p.flags & VQB_SKIP) != 0;
+    const float LOG2E = 1.4426950408889634f;
+    float mul = 0.f, uE = 1.f, win_c = 0.f, emax = 0.f;
+    float se_acc = 0.f;
+    constexpr uint32_t IDESC = umma_idesc(0u, PM, KP);
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int row0 = tile * PM;
+        const int rows = min(PM, p.N - row0);
+        const bool valid = r < rows;
+        // ---- loads: the x tile (older than the previous kernel), then -- behind pdl_wait -- the table image ---------
+        if (r == 0) {
+            mbar_arrive_expect_tx(x_full, KB * PBLK);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sX + kb * PBLK, &tm_x, kb * 32, row0, x_full);
+        }
+        if (it == 0) {
+            pdl_wait();
+            if (r < 64) sBias[r] = r < K ? __ldg(p.bias + r) : (linear ? -1e30f : 1e30f);
+            const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
+            mul = linear ? LOG2E : -tau * LOG2E;
+            uE = pow2i(__ldg(reinterpret_cast<const int*>(p.img + IMG_HDR)));
+            emax = __ldg(reinterpret_cast<const float*>(p.img + IMG_HDR + 4));
+        }
+        if (r == 0) {
+            mbar_arrive_expect_tx(e_full, 2 * KP * 128);
+            bulk_load_1d(sE, p.img, KP * 128, e_full);
+            bulk_load_1d(sE + KP * 128, p.img + IMG_PIECE, KP * 128, e_full);
+        }
+        // the fp32 gather table, on its way to shared memory through registers (it takes the image's place after the MMA)
+        float4 tv[TABV];
+#pragma unroll
+        for (int i = 0; i < TABV; ++i) {
+            const int i4 = r + PM * i;
+            tv[i] = i4 < K * (D / 4) ? ldg4(p.gtab + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        VQB_PTL(2);
+        mbar_wait(x_full, ph);
+        VQB_PTL(3);
+
+        // ---- row -> registers; |x|^2 in the exact kernel's fmaf order; rescale; fp16x2 split in place ---------------
+        float xr[D];
+        float xx = 0.f, mx = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(sX + kb * PBLK + sw128_offset(r, c));
+                xr[kb * 32 + 4 * c] = v.x; xr[kb * 32 + 4 * c + 1] = v.y; xr[kb * 32 + 4 * c + 2] = v.z; xr[kb * 32 + 4 * c + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            xx = fmaf(xr[d], xr[d], xx);
+            mx = fmaxf(mx, fabsf(xr[d]));
+        }
+        const int er = scale_exp(mx);
+        {
+            const float sx = pow2i(-er);
+#pragma unroll
+            for (int j = 0; j < D / 8; ++j) {
+                uint4 hi, lo;
+                split8(xr + 8 * j, sx, hi, lo);
+                *reinterpret_cast<uint4*>(sX + sw128_offset(r, j)) = hi;
+                *reinterpret_cast<uint4*>(sX + PBLK + sw128_offset(r, j)) = lo;
+            }
+        }
+        fence_proxy_async_smem();                   // generic writes -> tcgen05.mma operand reads
+        tcgen05_fence_before();
+        __syncthreads();
+        VQB_PTL(4);
+        if (r == 0) {
+            mbar_wait(e_full, ph);
+            tcgen05_fence_after();
+            const uint64_t ah = umma_desc_sw128(sX), al = umma_desc_sw128(sX + PBLK);
+            const uint64_t bh = umma_desc_sw128(sE), bl = umma_desc_sw128(sE + KP * 128);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {       // small terms first
+                umma_bf16(tmem_base, al + 2 * ks, bl + 2 * ks, IDESC, ks != 0);
+                umma_bf16(tmem_base, al + 2 * ks, bh + 2 * ks, IDESC, true);
+                umma_bf16(tmem_base, ah + 2 * ks, bl + 2 * ks, IDESC, true);
+                umma_bf16(tmem_base, ah + 2 * ks, bh + 2 * ks, IDESC, true);
+            }
+            umma_commit(mma_done);
+        }
+        mbar_wait(mma_done, ph);
+        tcgen05_fence_after();
+        VQB_PTL(5);
+        // the MMAs have retired: the image's shared memory is dead, the gather table takes its place
+#pragma unroll
+        for (int i = 0; i < TABV; ++i) {
+            const int i4 = r + PM * i;
+            if (i4 < K * (D / 4)) {
+                const int k = i4 / (D / 4), c = i4 - k * (D / 4);
+                *reinterpret_cast<float4*>(sTab + k * DP + 4 * c) = tv[i];
+            }
+        }
+
+        // ---- scores (log2 domain) -> softmax -> p_code, argmax over p_code -----------------------------------------
+        float v[KP];
+        tmem_ld_cols<KP>(tmem_base + lane_addr, v);
+        tcgen05_fence_before();
+        const float u1 = pow2i(er);
+        const float add = linear ? 0.f : xx;
+        float m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const float dot = v[k] * u1 * uE;
+            //   L2:     score = relu(temp) * -((|x|^2 + |e|^2) - 2 x.e)          (:115, :208-213)
+            //   LINEAR: score = x.w + b                                           (:190)
+            const float s2 = linear ? mul * (dot + sBias[k]) : mul * __fsub_rn(__fadd_rn(add, sBias[k]), 2.f * dot);
+            v[k] = s2;                              // padded codes: bias = +-1e30 -> s2 = -huge
+            m2 = fmaxf(m2, fminf(m1, s2));
+            m1 = fmaxf(m1, s2);
+        }
+        // window: |acc - exact fp32 dot| <= 5e-6 |x||e| (operand pieces 2 * 2^-22, fp32 accumulation in the tensor core and
+        // in the exact kernel's 64-term fmaf chain), twice for the two candidates, doubled in the distance; plus the rounding
+        // of (|x|^2 + |e|^2) - 2 x.e itself
+        {
+            const float xn = sqrtf(xx);
+            const float wd = linear ? 1e-5f * xn * emax : 2e-5f * xn * emax + 2.4e-7f * (xn + emax) * (xn + emax);
+            win_c = fabsf(mul) * wd;
+        }
+        if (valid && m1 - m2 <= win_c && mul != 0.f) {
+            // near-tie: every code inside the window is re-evaluated in exact fp32 (rare: a few rows per 10^5 at config 2)
+            const float thr = m1 - win_c;
+            const float* xrow = p.x + (size_t)(row0 + r) * D;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K && v[k] >= thr) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, linear);
+            m1 = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);
+            if (p.stats) atomicAdd(p.stats, 1u);
+        }
+        if (mul == 0.f) {                           // temp <= 0: uniform over the K real codes only
+#pragma unroll
+            for (int k = 0; k < KP; ++k) v[k] = k < K ? 0.f : -INFINITY;
+            m1 = 0.f;
+        }
+        // four interleaved chains (k mod 4) for the sum and for the first-index arg-max of exp(score - max)
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        float bv4[4] = {-1.f, -1.f, -1.f, -1.f};
+        int bi4[4] = {0, 1, 2, 3};
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m1));     // padded codes: ex2(-huge) = 0
+            v[k] = e;
+            s4[k & 3] += e;
+            if (e > bv4[k & 3]) { bv4[k & 3] = e; bi4[k & 3] = k; }
+        }
+        // argmax over p_code = e * inv (monotone in e), first index on ties (:130)
+        float bv = bv4[0];
+        int best = bi4[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+            if (bv4[j] > bv || (bv4[j] == bv && bi4[j] < best)) { bv = bv4[j]; best = bi4[j]; }
+        const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+        {
+            float* prow = sP + r * KO;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) prow[k] = v[k] * inv;    // softmax (:127)
+        }
+        if (valid) p.idx[row0 + r] = best;
+        if (p.hist) {
+            // warp-aggregated histogram: one atomic per distinct code per warp
+            const unsigned peers = __match_any_sync(0xffffffffu, valid ? best : -1);
+            if (valid && lane == (__ffs(peers) - 1)) atomicAdd(p.hist + best, (unsigned long long)__popc(peers));
+        }
+        __syncthreads();                            // the gather table is complete in shared memory
+        VQB_PTL(6);
+
+        // ---- gather + straight-through: the row's result replaces its (dead) operand pieces in the x tile -----------
+        {
+            const float* crow = sTab + best * DP;
+            const bool want_se = p.sqerr != nullptr;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 cv = *reinterpret_cast<const float4*>(crow + kb * 32 + 4 * c);
+                    const float x0 = xr[kb * 32 + 4 * c], x1 = xr[kb * 32 + 4 * c + 1], x2 = xr[kb * 32 + 4 * c + 2], x3 = xr[kb * 32 + 4 * c + 3];
+                    float4 o;
+                    if (linear) {
+                        o = cv;                                                         // (:194-197)
+                    } else {
+                        // new_latent = enc_embs + picked_code - enc_embs.detach()  (:145)
+                        o.x = __fsub_rn(__fadd_rn(x0, cv.x), x0); o.y = __fsub_rn(__fadd_rn(x1, cv.y), x1);
+                        o.z = __fsub_rn(__fadd_rn(x2, cv.z), x2); o.w = __fsub_rn(__fadd_rn(x3, cv.w), x3);
+                        if (skip) o = make_float4(x0, x1, x2, x3);                      // (:142)
+                    }
+                    if (want_se && valid) {
+                        const float d0 = x0 - cv.x, d1 = x1 - cv.y, d2 = x2 - cv.z, d3 = x3 - cv.w;
+                        se_acc = fmaf(d0, d0, se_acc); se_acc = fmaf(d1, d1, se_acc);
+                        se_acc = fmaf(d2, d2, se_acc); se_acc = fmaf(d3, d3, se_acc);
+                    }
+                    *reinterpret_cast<float4*>(sX + kb * PBLK + sw128_offset(r, c)) = o;
+                }
+            }
+        }
+        fence_proxy_async_smem();                   // tile / p_code writes -> bulk stores
+        __syncthreads();
+        VQB_PTL(7);
+        if (r == 0) {
+            // new_latent tile: TMA store straight from the swizzled tile (rows beyond N are clipped by TMA)
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) tma_store_2d(&tm_q, sX + kb * PBLK, kb * 32, row0);
+            if (K & 1) {
+                const uint32_t bytes = (uint32_t)(rows * K * 4) & ~15u;
+                if (bytes) bulk_store_1d(p.pcode + (size_t)row0 * K, sP, bytes);
+            }
+            tma_store_commit();
+        }
+        {
+            float* dst = p.pcode + (size_t)row0 * K;
+            const int n = rows * K;
+            if (K & 1) {
+                const int done = (int)(((uint32_t)(n * 4) & ~15u) >> 2);   // < 16 bytes of a ragged last tile
+                if (r < n - done) dst[done + r] = sP[done + r];
+            } else {
+                int rr = r / K, k = r - rr * K;                 // running (row, code) of element i
+                const int step_r = PM / K, step_k = PM - step_r * K;
+                for (int i = r; i < n; i += PM) {
+                    __stcs(dst + i, sP[rr * KO + k]);
+                    rr += step_r; k += step_k;
+                    if (k >= K) { k -= K; ++rr; }
+                }
+            }
+        }
+        if (r == 0) tma_store_wait_read();          // shared memory may be overwritten from here on
+        VQB_PTL(8);
+        if (tile + (int)gridDim.x < p.num_tiles) __syncthreads();       // another tile follows: the buffers are free
+    }
+    if (p.sqerr) {
+        se_acc = warp_sum(se_acc);
+        if (lane == 0) sRed[warp] = se_acc;
+        __syncthreads();
+        if (r == 0) atomicAdd(p.sqerr, (double)sRed[0] + (double)sRed[1] + (double)sRed[2] + (double)sRed[3]);
+    }
+    if (r == 0) tma_store_wait_all();
+    VQB_PTL(9);
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<64>(tmem_base);
+    if (p.dbg && r == 0 && blockIdx.x == 0) p.dbg[61] = globaltimer_ns();
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// operand image of a table that was not assembled by vqb_assemble_table (LINEAR score; raw C-ABI calls without a cache)
+// -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+build_image_kernel(const float* __restrict__ w, int K, int D, uint8_t* __restrict__ img) {
+    __shared__ float s_max[8], s_nrm[8];
+    pdl_launch();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gmax = 0.f, nmax = 0.f;
+    for (int k = warp; k < K; k += 8) {
+        float sq = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float v = __ldg(w + (size_t)k * D + d);
+            gmax = fmaxf(gmax, fabsf(v));
+            sq = fmaf(v, v, sq);
+        }
+        nmax = fmaxf(nmax, warp_sum(sq));
+    }
+    gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gmax)));   // non-negative floats order like uints
+    if (lane == 0) { s_max[warp] = gmax; s_nrm[warp] = nmax; }
+    __syncthreads();
+    gmax = 0.f; nmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gmax = fmaxf(gmax, s_max[i]); nmax = fmaxf(nmax, s_nrm[i]); }
+    write_image(w, D, K, D, gmax, sqrtf(nmax), img);
+}
+
+int launch_build_image(const float* w, int K, int D, void* img, cudaStream_t s) {
+    build_image_kernel<<<1, 256, 0, s>>>(w, K, D, reinterpret_cast<uint8_t*>(img));
+    VQB_CHECK_LAUNCH("build_image_kernel");
+    return VQB_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// host side
+// -----------------------------------------------------------------------------------------------------------
+unsigned long long* get_debug_timeline();
+
+bool forward_pcode_supported(const vqb_fwd_args* a) {
+    return a->p_code != nullptr && a->n_codes <= 64 && (a->dim == 32 || a->dim == 64);
+}
+
+size_t forward_pcode_workspace(const vqb_fwd_args* a) { return a->operand_cache ? 0 : (size_t)IMG_BYTES; }
+
+template <int KP, int D>
+static int launch_pc(const CUtensorMap& tx, const CUtensorMap& tq, PcP p, cudaStream_t s, bool pdl) {
+    const int tab_bytes = p.K * (D + 4) * 4, img_bytes = 2 * KP * 128;
+    p.se_bytes = ((tab_bytes > img_bytes ? tab_bytes : img_bytes) + 1023) & ~1023;
+    const size_t smem = (size_t)2 * PBLK + p.se_bytes + (size_t)PM * (p.K | 1) * 4 + 64 * 4 + 4 * 4 + 3 * 8 + 16 + 1024;
+    auto kern = vqb_fwd_pcode_kernel<KP, D>;
+    VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const int slots = 3 * sm_count();
+    const int grid = p.num_tiles < slots ? p.num_tiles : slots;
+    kernel_event_begin(s);
+    if (pdl) VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(PM), smem, s, tx, tq, p));
+    else kern<<<grid, PM, smem, s>>>(tx, tq, p);
+    kernel_event_end(s);
+    VQB_CHECK_LAUNCH("vqb_fwd_pcode_kernel");
+    return VQB_OK;
+}
+
+int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
+    const int64_t N = a->n_rows, K = a->n_codes, D = a->dim;
+    if (N == 0) return VQB_OK;
+    const bool cached = a->operand_cache != nullptr;
+    if (!cached && (!a->workspace || a->workspace_bytes < (size_t)IMG_BYTES)) {
+        set_error("vqb_forward: workspace too small (%zu < %d bytes)", a->workspace_bytes, IMG_BYTES);
+        return VQB_ERR_WORKSPACE;
+    }
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(cached ? a->operand_cache : a->workspace);
+    if (!cached) {
+        int rc = launch_build_image(a->score_w, (int)K, (int)D, a->workspace, s);
+        if (rc) return rc;
+    }
+    CUtensorMap tx, tq;
+    int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, PM);
+    if (rc) return rc;
+    if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, PM))) return rc;
+    PcP p;
+    p.x = a->x; p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.img = img;
+    p.pcode = a->p_code; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
+    p.stats = a->search_stats; p.dbg = get_debug_timeline();
+    p.N = (int)N; p.K = (int)K; p.num_tiles = (int)ceil_div(N, PM); p.se_bytes = 0; p.flags = a->flags;
+    // PDL when the kernel enqueued immediately before is ours: the image build above, or (the caller vouches,
+    // VQB_AFTER_ASSEMBLE) the table assembly
+    const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
+    const int KP = (int)((K + 15) / 16 * 16);
+    if (D == 32) {
+        switch (KP) {
+            case 16: return launch_pc<16, 32>(tx, tq, p, s, pdl);
+            case 32: return launch_pc<32, 32>(tx, tq, p, s, pdl);
+            case 48: return launch_pc<48, 32>(tx, tq, p, s, pdl);
+            default: return launch_pc<64, 32>(tx, tq, p, s, pdl);
+        }
+    }
+    switch (KP) {
+        case 16: return launch_pc<16, 64>(tx, tq, p, s, pdl);
+        case 32: return launch_pc<32, 64>(tx, tq, p, s, pdl);
+        case 48: return launch_pc<48, 64>(tx, tq, p, s, pdl);
+        default: return launch_pc<64, 64>(tx, tq, p, s, pdl);
+    }
+}
+
+}  // namespace vqb

@@ -1,63 +1,84 @@
 // Codebook table assembly and its backward (reference: src/embed.py:109-112, :87-94).
 #include <cuda_bf16.h>
 #include "vqb_common.cuh"
+#include "vqb_f16x2.cuh"
 
 namespace vqb {
 
 // One CTA per code row: table[k,:] = cat(learnable[k,:], attr[k,:] @ W^T + b); enorm[k] = |table[k,:]|^2.
-// With an operand cache the same launch also writes the tf32 hi/lo operand copies used by the tensor-core
-// kernels (forward: -2 e with |e|^2 as the bias block; backward: e), including the padded rows K..Kp-1.
+__device__ __forceinline__ float table_entry(const float* __restrict__ learnable, const float* __restrict__ attr,
+                                             const float* __restrict__ proj_w, const float* __restrict__ proj_b,
+                                             int k, int d, int Dl, int A) {
+    if (d < Dl) return learnable[(size_t)k * Dl + d];
+    const float* w = proj_w + (size_t)(d - Dl) * A;
+    const float* a = attr + (size_t)k * A;
+    float acc = 0.f;
+    for (int i = 0; i < A; ++i) acc = fmaf(a[i], w[i], acc);
+    return acc + proj_b[d - Dl];
+}
+
 __global__ void __launch_bounds__(128)
 assemble_table_kernel(const float* __restrict__ learnable, const float* __restrict__ attr,
                       const float* __restrict__ proj_w, const float* __restrict__ proj_b,
                       int K, int D, int A, int Da, float* __restrict__ table,
-                      float* __restrict__ enorm, __nv_bfloat16* __restrict__ table_bf16,
-                      float* __restrict__ f_hi, float* __restrict__ f_lo, float* __restrict__ b_hi,
-                      float* __restrict__ b_lo) {
+                      float* __restrict__ enorm, __nv_bfloat16* __restrict__ table_bf16) {
     const int k = blockIdx.x;
     const int Dl = D - Da;
     pdl_launch();                                      // the forward kernel may start its prologue (it waits before reading)
-    if (k >= K) {                                      // padded operand rows (only launched with a cache)
-        for (int d = threadIdx.x; d < D + 32; d += blockDim.x) {
-            f_hi[(size_t)k * (D + 32) + d] = d == D ? 1e30f : 0.f;
-            b_hi[(size_t)k * (D + 32) + d] = 0.f;
-            if (d < D) { f_lo[(size_t)k * D + d] = 0.f; b_lo[(size_t)k * D + d] = 0.f; }
-        }
-        return;
-    }
     float sq = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float v;
-        if (d < Dl) {
-            v = learnable[(size_t)k * Dl + d];
-        } else {
-            const float* w = proj_w + (size_t)(d - Dl) * A;
-            const float* a = attr + (size_t)k * A;
-            float acc = 0.f;
-            for (int i = 0; i < A; ++i) acc = fmaf(a[i], w[i], acc);
-            v = acc + proj_b[d - Dl];
-        }
+        const float v = table_entry(learnable, attr, proj_w, proj_b, k, d, Dl, A);
         table[(size_t)k * D + d] = v;
         if (table_bf16) table_bf16[(size_t)k * D + d] = __float2bfloat16_rn(v);
-        if (f_hi) {
-            const float m2 = -2.f * v, h = tf32_rn(m2), hb = tf32_rn(v);
-            f_hi[(size_t)k * (D + 32) + d] = h;  f_lo[(size_t)k * D + d] = m2 - h;
-            b_hi[(size_t)k * (D + 32) + d] = hb; b_lo[(size_t)k * D + d] = v - hb;
-        }
         sq = fmaf(v, v, sq);
     }
     __shared__ float red[4];
     sq = warp_sum(sq);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
     __syncthreads();
-    const float ee = (red[0] + red[1]) + (red[2] + red[3]);
-    if (threadIdx.x == 0 && enorm) enorm[k] = ee;
-    if (f_hi && threadIdx.x < 32) {                    // bias block: |e|^2 as three tf32-exact words, then zeros
-        const float b0 = tf32_trunc(ee), r1 = ee - b0, b1 = tf32_trunc(r1), b2 = r1 - b1;
-        const int j = threadIdx.x;
-        f_hi[(size_t)k * (D + 32) + D + j] = j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : 0.f));
-        b_hi[(size_t)k * (D + 32) + D + j] = 0.f;
+    if (threadIdx.x == 0 && enorm) enorm[k] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// Small tables (K <= 64, D <= 64: every semi-tts configuration) in ONE CTA: the table, |e|^2 and -- in the same launch --
+// the fp16x2 operand image (vqb_f16x2.cuh) that the parity-mode forward and backward kernels consume.  The image needs
+// the table-wide maximum, which a single CTA has without a grid-wide dependency.
+__global__ void __launch_bounds__(256)
+assemble_small_kernel(const float* __restrict__ learnable, const float* __restrict__ attr,
+                      const float* __restrict__ proj_w, const float* __restrict__ proj_b,
+                      int K, int D, int A, int Da, float* __restrict__ table,
+                      float* __restrict__ enorm, __nv_bfloat16* __restrict__ table_bf16, uint8_t* __restrict__ img) {
+    __shared__ float s_tab[64 * 64];
+    __shared__ float s_max[8], s_nrm[8];
+    const int Dl = D - Da;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch();                                      // the forward kernel may start its prologue (it waits before reading)
+    for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+        const int k = i / D, d = i - k * D;
+        const float v = table_entry(learnable, attr, proj_w, proj_b, k, d, Dl, A);
+        s_tab[i] = v;
+        table[i] = v;
+        if (table_bf16) table_bf16[i] = __float2bfloat16_rn(v);
     }
+    __syncthreads();
+    float gmax = 0.f, nmax = 0.f;
+    for (int k = warp; k < K; k += 8) {                // one warp per row: |e|^2, the table maximum, the largest row norm
+        float sq = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float v = s_tab[k * D + d];
+            gmax = fmaxf(gmax, fabsf(v));
+            sq = fmaf(v, v, sq);
+        }
+        sq = warp_sum(sq);
+        if (lane == 0 && enorm) enorm[k] = sq;
+        nmax = fmaxf(nmax, sq);
+    }
+    gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gmax)));   // non-negative floats order like uints
+    if (lane == 0) { s_max[warp] = gmax; s_nrm[warp] = nmax; }
+    __syncthreads();
+    gmax = 0.f; nmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gmax = fmaxf(gmax, s_max[i]); nmax = fmaxf(nmax, s_nrm[i]); }
+    write_image(s_tab, D, K, D, gmax, sqrtf(nmax), img);
 }
 
 // d_learnable = eff[:, :Dl];  d_proj_w = eff[:, Dl:]^T @ attr;  d_proj_b = colsum(eff[:, Dl:])
@@ -99,8 +120,10 @@ table_backward_kernel(const float* __restrict__ dtable, const float* __restrict_
 
 using namespace vqb;
 
+static bool small_table(int64_t n_codes, int64_t dim) { return n_codes <= 64 && (dim == 32 || dim == 64); }
+
 extern "C" size_t vqb_operand_cache_bytes(int64_t n_codes, int64_t dim) {
-    return 2 * (cache_hi_bytes(n_codes, dim) + cache_lo_bytes(n_codes, dim));
+    return small_table(n_codes, dim) ? (size_t)IMG_BYTES : 0;
 }
 
 extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr, const float* proj_w,
@@ -114,18 +137,16 @@ extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr,
     if (has_attr && (!proj_w || !proj_b || n_attr <= 0 || dim_attr <= 0 || dim_attr >= dim))
         return invalid("vqb_assemble_table: phn_attr given but projection is missing or 0 < D_a < D violated");
     if (!has_attr) { n_attr = 0; dim_attr = 0; }
-    float *f_hi = nullptr, *f_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
-    unsigned rows = (unsigned)n_codes;
-    if (operand_cache) {
-        uint8_t* oc = reinterpret_cast<uint8_t*>(operand_cache);
-        const size_t hb = cache_hi_bytes(n_codes, dim), lb = cache_lo_bytes(n_codes, dim);
-        f_hi = reinterpret_cast<float*>(oc);          f_lo = reinterpret_cast<float*>(oc + hb);
-        b_hi = reinterpret_cast<float*>(oc + hb + lb); b_lo = reinterpret_cast<float*>(oc + 2 * hb + lb);
-        rows = (unsigned)cache_rows(n_codes);
+    if (operand_cache && small_table(n_codes, dim)) {
+        assemble_small_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
+            learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
+            enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache));
+        VQB_CHECK_LAUNCH("assemble_small_kernel");
+        return VQB_OK;
     }
-    assemble_table_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(
+    assemble_table_kernel<<<(unsigned)n_codes, 128, 0, (cudaStream_t)stream>>>(
         learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
-        enorm, (__nv_bfloat16*)table_bf16, f_hi, f_lo, b_hi, b_lo);
+        enorm, (__nv_bfloat16*)table_bf16);
     VQB_CHECK_LAUNCH("assemble_table_kernel");
     return VQB_OK;
 }

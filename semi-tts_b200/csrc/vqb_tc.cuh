@@ -140,7 +140,41 @@ __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, float (&v)[
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 16 columns, no wait
+__device__ __forceinline__ void tmem_ld_32x16_nowait(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// NC columns (a multiple of 16, <= 64) of this warp's lane quadrant into v[0 .. NC): all loads in flight, one wait
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NC]) {
+    static_assert(NC % 16 == 0 && NC >= 16 && NC <= 64, "16, 32, 48 or 64 columns");
+    float a[32], b[32], c[16];
+    if constexpr (NC >= 32) tmem_ld_32x32_nowait(taddr, a);
+    if constexpr (NC == 64) tmem_ld_32x32_nowait(taddr + 32, b);
+    if constexpr (NC % 32 == 16) tmem_ld_32x16_nowait(taddr + (NC - 16), c);
+    tmem_ld_wait();
+    if constexpr (NC >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = a[i];
+    }
+    if constexpr (NC == 64) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[32 + i] = b[i];
+    }
+    if constexpr (NC % 32 == 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[NC - 16 + i] = c[i];
+    }
+}
 
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand stored as [rows][128 bytes] with the 128-byte swizzle

@@ -52,7 +52,8 @@ def assemble_table(learnable, phn_attr=None, proj_w=None, proj_b=None, want_bf16
     tbf = torch.empty(K, D, device=learnable.device, dtype=torch.bfloat16) if want_bf16 else None
     cache = None
     if want_cache:
-        cache = torch.empty(lib.vqb_operand_cache_bytes(K, D), device=learnable.device, dtype=torch.uint8)
+        nb = lib.vqb_operand_cache_bytes(K, D)           # 0: this shape has no tensor-core operand image
+        cache = torch.empty(nb, device=learnable.device, dtype=torch.uint8) if nb else None
     with torch.cuda.device(learnable.device):
         _lib.check(lib.vqb_assemble_table(ptr(learnable), ptr(phn_attr), ptr(proj_w), ptr(proj_b), K, D, A, Da,
                                           ptr(table), ptr(enorm), ptr(tbf), ptr(cache), _stream(learnable)))
@@ -144,7 +145,7 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.operand_cache = ptr(operand_cache)
     use_tail = bool(tail is not None and tail.enabled and (flags & _lib.SCORE_L2) and not separate_gather
-                    and lib.vqb_backward_kernel_name(ctypes.byref(a)) == b"vqb_bwd_h2_kernel")
+                    and lib.vqb_backward_kernel_name(ctypes.byref(a)) in (b"vqb_bwd_pcode_kernel", b"vqb_bwd_h2_kernel"))
     flat = tl = None
     if use_tail:
         # the tail overwrites its scratch and outputs: nothing to zero-fill
