@@ -1,9 +1,9 @@
-"""Import the unmodified reference modules from /root/reference (build container only).
+"""Import the unmodified reference modules: from /root/reference in the build container, otherwise from the
+installed copy baseline/_ref/ (baseline/install_reference.py: a verbatim copy, git-ignored, that travels to the GPU box).
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing
-that runs there may call this; it is used by `oracle/gen_golden.py` (to produce
-tests/golden/*.npz) and by the CPU-only tests that are skipped when the tree is
-absent.
+TEST INFRASTRUCTURE.  Used by `oracle/gen_golden.py` (to produce tests/golden/*.npz), by the CPU-only tests that are
+skipped when no tree is present, by the config-4 GPU test (the drop-in inside the reference VQVAE) and by
+`bench.py --impl reference` / the `cpu_baseline` leg (the reference's own modules timed on the host cores).
 
 src/util.py:7-12 imports editdistance, soundfile and matplotlib, none of which is
 installed; empty stub modules are enough because the quantizer never calls them.
@@ -13,7 +13,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VQB_REFERENCE_ROOT", "/root/reference")
+_INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("VQB_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _INSTALLED):
+        if os.path.isfile(os.path.join(cand, "src", "embed.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 _STUBS = ["editdistance", "soundfile", "matplotlib", "matplotlib.pyplot",
           "tensorboardX", "librosa"]

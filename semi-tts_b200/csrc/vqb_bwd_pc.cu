@@ -91,6 +91,7 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int K = p.K;
     const int n_my = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
     int tl_n = 0;
+    if (p.dbg && r == 0) p.dbg[128 + 2 * blockIdx.x] = globaltimer_ns();
 
     if (r == 0) {
         tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_dx);
@@ -175,10 +176,12 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         {
             float gg[KP];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                const bool on = valid && k < K;
-                c[k] = on ? stP[r * K + k] : 0.f;
-                gg[k] = on ? stG[r * K + k] : 0.f;
+            for (int k = 0; k < KP; ++k) { c[k] = 0.f; gg[k] = 0.f; }
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    if (k < KP - 15 || k < K) { c[k] = stP[r * K + k]; gg[k] = stG[r * K + k]; }
+                }
             }
 #pragma unroll
             for (int k = KP; k < 64; ++k) c[k] = 0.f;
@@ -378,14 +381,13 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         tcgen05_fence_after();
         VQB_BTL(5);
         if (r < TR) {
-            const float u1 = pow2i(er);
-            const float ad = L2 ? -2.f : 1.f;
+            const float u = pow2i(er) * uE * (L2 ? -2.f : 1.f);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
                 float a[32];
                 tmem_ld_32x32(d1 + lane_addr + kb * 32, a);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) gr[kb * 32 + j] = fmaf(ad, a[j] * u1 * uE, L2 ? gr[kb * 32 + j] : 0.f);
+                for (int j = 0; j < 32; ++j) gr[kb * 32 + j] = fmaf(a[j], u, L2 ? gr[kb * 32 + j] : 0.f);
             }
         }
         // ---- all MMAs retired: dx -> the (dead) g_q tile, D2 / D3 of this tile -> registers ---------------------------
@@ -402,18 +404,19 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         fence_proxy_async_smem();
         {
-            const float t1 = pow2i(t >> 1) * (L2 ? -2.f : 1.f), t2 = pow2i(t - (t >> 1));
+            // (t and g are exponents of ordinary magnitudes; the clamp of pow2i only matters beyond 2^+-126)
+            const float ts = pow2i(t) * (L2 ? -2.f : 1.f);
             float a[KP];
             tmem_ld_cols<KP>(d2 + lane_addr, a);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = fmaf(a[k] * t1, t2, acc[k]);
+            for (int k = 0; k < KP; ++k) acc[k] = fmaf(a[k], ts, acc[k]);
             if (do_scatter) {
-                const float g1 = pow2i(g >> 1), g2 = pow2i(g - (g >> 1));
+                const float gs = pow2i(g);
                 tmem_ld_cols<KP>(d3 + lane_addr, a);
 #pragma unroll
                 for (int k = 0; k < KP; ++k) {
-                    if (L2) acc[k] = fmaf(a[k] * g1, g2, acc[k]);
-                    else accg[k] = fmaf(a[k] * g1, g2, accg[k]);
+                    if (L2) acc[k] = fmaf(a[k], gs, acc[k]);
+                    else accg[k] = fmaf(a[k], gs, accg[k]);
                 }
             }
         }
@@ -486,6 +489,7 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<256>(tmem_base);
+    if (p.dbg && r == 0) p.dbg[129 + 2 * blockIdx.x] = globaltimer_ns();
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -544,7 +548,7 @@ int launch_backward_pcode(const vqb_bwd_args* a, cudaStream_t s) {
     const uint8_t* img = reinterpret_cast<const uint8_t*>(a->operand_cache);
     if (!cached) {
         uint8_t* w = reinterpret_cast<uint8_t*>(a->workspace) + rec_bytes;
-        int rc = launch_build_image(a->score_w, (int)K, (int)D, w, s);
+        int rc = launch_build_image(a->score_w, a->score_b, (int)K, (int)D, w, s);
         if (rc) return rc;
         img = w;
     }

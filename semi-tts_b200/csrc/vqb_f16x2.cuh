@@ -15,11 +15,13 @@ namespace vqb {
 // (or by build_image_kernel for a table that is not assembled here):
 //   [0, 8192)      hi pieces   [64 code rows][64 halves], 128-byte swizzle (chunk j of row k at sw128_offset(k, j))
 //   [8192, 16384)  lo pieces   same layout
-//   [16384, ...)   header: int32 gE (table scale: image = table * 2^-gE), float emax (max_k |w_k|_2)
+//   [16384, +64)   header: int32 gE (table scale: image = table * 2^-gE), float emax (max_k |w_k|_2)
+//   [16448, +256)  the score bias of the 64 codes: |e_k|^2 (L2) or b_k (LINEAR); entries >= K are 0
 // Rows >= K and columns >= D are zero.
 constexpr int IMG_PIECE = 64 * 128;
 constexpr int IMG_HDR = 2 * IMG_PIECE;
-constexpr int IMG_BYTES = 2 * IMG_PIECE + 256;
+constexpr int IMG_BIAS = IMG_HDR + 64;
+constexpr int IMG_BYTES = IMG_BIAS + 256;
 
 // floor(log2(|v|)) of a positive normal float; subnormals and zero give -127, inf/nan give 128
 __device__ __forceinline__ int exp_of(float v) { return (int)((__float_as_uint(v) >> 23) & 0xFFu) - 127; }
@@ -54,7 +56,8 @@ __device__ __forceinline__ int scale_exp(float mx) {
 
 // device part of the image build, called by every thread of ONE CTA: `tab` is the table in shared or global memory
 // ([K][ld] floats), gmax = max |tab|, emax = max row norm (both block-uniform)
-__device__ __forceinline__ void write_image(const float* tab, int ld, int K, int D, float gmax, float emax, uint8_t* img) {
+__device__ __forceinline__ void write_image(const float* tab, int ld, int K, int D, float gmax, float emax, const float* bias,
+                                            uint8_t* img) {
     const int gE = scale_exp(gmax);
     const float sE = pow2i(-gE);
     for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
@@ -71,9 +74,10 @@ __device__ __forceinline__ void write_image(const float* tab, int ld, int K, int
         *reinterpret_cast<int*>(img + IMG_HDR) = gE;
         *reinterpret_cast<float*>(img + IMG_HDR + 4) = emax;
     }
+    if (threadIdx.x < 64) reinterpret_cast<float*>(img + IMG_BIAS)[threadIdx.x] = ((int)threadIdx.x < K && bias) ? bias[threadIdx.x] : 0.f;
 }
 
 // host: enqueue the image build for a table that was not assembled by vqb_assemble_table (LINEAR score, raw C-ABI calls)
-int launch_build_image(const float* w, int K, int D, void* img, cudaStream_t s);
+int launch_build_image(const float* w, const float* bias, int K, int D, void* img, cudaStream_t s);
 
 }  // namespace vqb

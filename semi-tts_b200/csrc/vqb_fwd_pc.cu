@@ -66,13 +66,12 @@ __device__ __noinline__ float exact_s2(const float* __restrict__ xrow, const flo
     return mul * __fsub_rn(__fadd_rn(xx, b), 2.f * dot);
 }
 
-template <int KP, int D>
+template <int KP, int D, bool LINEAR>
 __global__ void __launch_bounds__(PM, 3)
 vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, PcP p) {
     constexpr int KB = D / 32;                      // raw fp32 blocks of an x tile
     constexpr int KS = D / 16;                      // MMA K-steps
     constexpr int DP = D + 4;                       // padded row of the fp32 gather table in shared memory
-    constexpr int TABV = (64 * D / 4 + PM - 1) / PM;   // float4 per thread that cover a [64][D] table
     const int K = p.K;
     const int KO = K | 1;                           // p_code staging row stride (odd: conflict-free)
 
@@ -82,22 +81,25 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     uint8_t* sE = sX + 2 * PBLK;                                    // e_hi | e_lo image, later the fp32 gather table
     float* sTab = reinterpret_cast<float*>(sE);
     float* sP = reinterpret_cast<float*>(sE + p.se_bytes);          // [128][KO] p_code staging
-    float* sBias = sP + PM * KO;                                    // [64]
-    float* sRed = sBias + 64;                                       // [4]
+    uint8_t* sHdr = reinterpret_cast<uint8_t*>(sP + PM * KO);       // image header: gE, emax | bias [64]
+    const float* sBias = reinterpret_cast<const float*>(sHdr + 64);
+    float* sRed = reinterpret_cast<float*>(sHdr + 64 + 256);        // [4]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 4);
     uint64_t* x_full = bars;
     uint64_t* e_full = bars + 1;
     uint64_t* mma_done = bars + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* t_full = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
     int tl_n = 0;
+    if (p.dbg && r == 0) p.dbg[128 + 2 * blockIdx.x] = globaltimer_ns();
     if (p.dbg && r == 0 && blockIdx.x == 0) p.dbg[60] = globaltimer_ns();
 
     if (r == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_q);
-        mbar_init(x_full, 1); mbar_init(e_full, 1); mbar_init(mma_done, 1);
+        mbar_init(x_full, 1); mbar_init(e_full, 1); mbar_init(mma_done, 1); mbar_init(t_full, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<64>(tmem_slot);
@@ -111,11 +113,10 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     pdl_launch();
     VQB_PTL(1);
 
-    const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
     const bool skip = (p.flags & VQB_SKIP) != 0;
     const float LOG2E = 1.4426950408889634f;
-    float mul = 0.f, uE = 1.f, win_c = 0.f, emax = 0.f;
     float se_acc = 0.f;
+    float temp_raw = 1.f;
     constexpr uint32_t IDESC = umma_idesc(0u, PM, KP);
 
     uint32_t it = 0;
@@ -132,23 +133,13 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         if (it == 0) {
             pdl_wait();
-            if (r < 64) sBias[r] = r < K ? __ldg(p.bias + r) : (linear ? -1e30f : 1e30f);
-            const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
-            mul = linear ? LOG2E : -tau * LOG2E;
-            uE = pow2i(__ldg(reinterpret_cast<const int*>(p.img + IMG_HDR)));
-            emax = __ldg(reinterpret_cast<const float*>(p.img + IMG_HDR + 4));
+            if (!LINEAR) temp_raw = __ldg(p.temp);                  // consumed after the MMA: its latency is hidden
         }
         if (r == 0) {
-            mbar_arrive_expect_tx(e_full, 2 * KP * 128);
+            mbar_arrive_expect_tx(e_full, 2 * KP * 128 + (it == 0 ? 320 : 0));
             bulk_load_1d(sE, p.img, KP * 128, e_full);
             bulk_load_1d(sE + KP * 128, p.img + IMG_PIECE, KP * 128, e_full);
-        }
-        // the fp32 gather table, on its way to shared memory through registers (it takes the image's place after the MMA)
-        float4 tv[TABV];
-#pragma unroll
-        for (int i = 0; i < TABV; ++i) {
-            const int i4 = r + PM * i;
-            tv[i] = i4 < K * (D / 4) ? ldg4(p.gtab + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it == 0) bulk_load_1d(sHdr, p.img + IMG_HDR, 320, e_full);   // scale, |e|_max and the 64 bias words
         }
         VQB_PTL(2);
         mbar_wait(x_full, ph);
@@ -202,30 +193,32 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         mbar_wait(mma_done, ph);
         tcgen05_fence_after();
         VQB_PTL(5);
-        // the MMAs have retired: the image's shared memory is dead, the gather table takes its place
-#pragma unroll
-        for (int i = 0; i < TABV; ++i) {
-            const int i4 = r + PM * i;
-            if (i4 < K * (D / 4)) {
-                const int k = i4 / (D / 4), c = i4 - k * (D / 4);
-                *reinterpret_cast<float4*>(sTab + k * DP + 4 * c) = tv[i];
-            }
+        // the MMAs have retired: the image's shared memory is dead, the fp32 gather table takes its place (bulk copies of
+        // one padded row each, issued by warp 0; every thread waits on t_full right before its gather)
+        if (warp == 0) {
+            if (lane == 0) mbar_arrive_expect_tx(t_full, (uint32_t)(K * D * 4));
+            __syncwarp();
+            for (int k = lane; k < K; k += 32) bulk_load_1d(sTab + k * DP, p.gtab + (size_t)k * D, D * 4, t_full);
         }
+        if (it == 0) mbar_wait(e_full, 0);           // the header (scale, bias) has landed with the image: visible to this thread
 
         // ---- scores (log2 domain) -> softmax -> p_code, argmax over p_code -----------------------------------------
         float v[KP];
         tmem_ld_cols<KP>(tmem_base + lane_addr, v);
         tcgen05_fence_before();
-        const float u1 = pow2i(er);
-        const float add = linear ? 0.f : xx;
+        const float tau = fmaxf(temp_raw, 0.f);
+        const float mul = LINEAR ? LOG2E : -tau * LOG2E;
+        const float emax = *reinterpret_cast<const float*>(sHdr + 4);
+        const float u = pow2i(er) * pow2i(*reinterpret_cast<const int*>(sHdr));
         float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            const float dot = v[k] * u1 * uE;
-            //   L2:     score = relu(temp) * -((|x|^2 + |e|^2) - 2 x.e)          (:115, :208-213)
+            const float dot = v[k] * u;
+            //   L2:     score = relu(temp) * -((|x|^2 + |e|^2) - 2 x.e)          (:115, :208-213)   [2 x.e is exact: one fma]
             //   LINEAR: score = x.w + b                                           (:190)
-            const float s2 = linear ? mul * (dot + sBias[k]) : mul * __fsub_rn(__fadd_rn(add, sBias[k]), 2.f * dot);
-            v[k] = s2;                              // padded codes: bias = +-1e30 -> s2 = -huge
+            float s2 = LINEAR ? mul * (dot + sBias[k]) : mul * fmaf(-2.f, dot, __fadd_rn(xx, sBias[k]));
+            if (k >= KP - 15) s2 = k < K ? s2 : -INFINITY;          // padded codes
+            v[k] = s2;
             m2 = fmaxf(m2, fminf(m1, s2));
             m1 = fmaxf(m1, s2);
         }
@@ -234,50 +227,45 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // of (|x|^2 + |e|^2) - 2 x.e itself
         {
             const float xn = sqrtf(xx);
-            const float wd = linear ? 1e-5f * xn * emax : 2e-5f * xn * emax + 2.4e-7f * (xn + emax) * (xn + emax);
-            win_c = fabsf(mul) * wd;
-        }
-        if (valid && m1 - m2 <= win_c && mul != 0.f) {
-            // near-tie: every code inside the window is re-evaluated in exact fp32 (rare: a few rows per 10^5 at config 2)
-            const float thr = m1 - win_c;
-            const float* xrow = p.x + (size_t)(row0 + r) * D;
+            const float wd = LINEAR ? 1e-5f * xn * emax : 2e-5f * xn * emax + 2.4e-7f * (xn + emax) * (xn + emax);
+            const float win = fabsf(mul) * wd;
+            if (valid && m1 - m2 <= win && mul != 0.f) {
+                // near-tie: every code inside the window is re-evaluated in exact fp32 (rare: a few rows per 10^5 at config 2)
+                const float thr = m1 - win;
+                const float* xrow = p.x + (size_t)(row0 + r) * D;
 #pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (k < K && v[k] >= thr) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, linear);
-            m1 = -INFINITY;
+                for (int k = 0; k < KP; ++k)
+                    if (k < K && v[k] >= thr) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, LINEAR);
+                m1 = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);
-            if (p.stats) atomicAdd(p.stats, 1u);
+                for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);
+                if (p.stats) atomicAdd(p.stats, 1u);
+            }
         }
         if (mul == 0.f) {                           // temp <= 0: uniform over the K real codes only
 #pragma unroll
             for (int k = 0; k < KP; ++k) v[k] = k < K ? 0.f : -INFINITY;
             m1 = 0.f;
         }
-        // four interleaved chains (k mod 4) for the sum and for the first-index arg-max of exp(score - max)
+        // exp(score - max): four interleaved sums; the maximum itself gives ex2(0) = 1 exactly, so the arg-max over
+        // p_code = e * inv (first index on ties, :130) is the first code whose e is 1
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        float bv4[4] = {-1.f, -1.f, -1.f, -1.f};
-        int bi4[4] = {0, 1, 2, 3};
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             float e;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m1));     // padded codes: ex2(-huge) = 0
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m1));     // padded codes: ex2(-inf) = 0
             v[k] = e;
             s4[k & 3] += e;
-            if (e > bv4[k & 3]) { bv4[k & 3] = e; bi4[k & 3] = k; }
         }
-        // argmax over p_code = e * inv (monotone in e), first index on ties (:130)
-        float bv = bv4[0];
-        int best = bi4[0];
+        int best = 0;
 #pragma unroll
-        for (int j = 1; j < 4; ++j)
-            if (bv4[j] > bv || (bv4[j] == bv && bi4[j] < best)) { bv = bv4[j]; best = bi4[j]; }
+        for (int k = KP - 1; k >= 0; --k) best = v[k] >= 1.f ? k : best;
         const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
         {
             float* prow = sP + r * KO;
 #pragma unroll
             for (int k = 0; k < KP; ++k)
-                if (k < K) prow[k] = v[k] * inv;    // softmax (:127)
+                if (k < KP - 15 || k < K) prow[k] = v[k] * inv;    // softmax (:127)
         }
         if (valid) p.idx[row0 + r] = best;
         if (p.hist) {
@@ -285,8 +273,8 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const unsigned peers = __match_any_sync(0xffffffffu, valid ? best : -1);
             if (valid && lane == (__ffs(peers) - 1)) atomicAdd(p.hist + best, (unsigned long long)__popc(peers));
         }
-        __syncthreads();                            // the gather table is complete in shared memory
         VQB_PTL(6);
+        mbar_wait(t_full, ph);                      // the gather table is complete in shared memory
 
         // ---- gather + straight-through: the row's result replaces its (dead) operand pieces in the x tile -----------
         {
@@ -299,7 +287,7 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     const float4 cv = *reinterpret_cast<const float4*>(crow + kb * 32 + 4 * c);
                     const float x0 = xr[kb * 32 + 4 * c], x1 = xr[kb * 32 + 4 * c + 1], x2 = xr[kb * 32 + 4 * c + 2], x3 = xr[kb * 32 + 4 * c + 3];
                     float4 o;
-                    if (linear) {
+                    if (LINEAR) {
                         o = cv;                                                         // (:194-197)
                     } else {
                         // new_latent = enc_embs + picked_code - enc_embs.detach()  (:145)
@@ -316,36 +304,39 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 }
             }
         }
+        // ---- this warp's 32 rows leave on their own: no CTA-wide barrier between the softmax and the stores -----------
         fence_proxy_async_smem();                   // tile / p_code writes -> bulk stores
-        __syncthreads();
+        __syncwarp();
         VQB_PTL(7);
-        if (r == 0) {
-            // new_latent tile: TMA store straight from the swizzled tile (rows beyond N are clipped by TMA)
+        const int rows_w = min(32, rows - 32 * warp);        // rows of this warp's slab inside the tensor (<= 0: none)
+        if (rows_w > 0) {
+            float* dst = p.pcode + (size_t)(row0 + 32 * warp) * K;
+            const float* src = sP + 32 * warp * KO;
+            const int n = rows_w * K;
+            if (lane == 0) {
+                // new_latent slab: TMA store straight from the swizzled tile (rows beyond N are clipped by TMA)
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) tma_store_2d(&tm_q, sX + kb * PBLK, kb * 32, row0);
-            if (K & 1) {
-                const uint32_t bytes = (uint32_t)(rows * K * 4) & ~15u;
-                if (bytes) bulk_store_1d(p.pcode + (size_t)row0 * K, sP, bytes);
+                for (int kb = 0; kb < KB; ++kb) tma_store_2d(&tm_q, sX + kb * PBLK + warp * 32 * 128, kb * 32, row0 + 32 * warp);
+                if (K & 1) {
+                    const uint32_t bytes = (uint32_t)(n * 4) & ~15u;
+                    if (bytes) bulk_store_1d(dst, src, bytes);
+                }
+                tma_store_commit();
             }
-            tma_store_commit();
-        }
-        {
-            float* dst = p.pcode + (size_t)row0 * K;
-            const int n = rows * K;
             if (K & 1) {
-                const int done = (int)(((uint32_t)(n * 4) & ~15u) >> 2);   // < 16 bytes of a ragged last tile
-                if (r < n - done) dst[done + r] = sP[done + r];
+                const int done = (int)(((uint32_t)(n * 4) & ~15u) >> 2);   // < 16 bytes of a ragged last slab
+                if (lane < n - done) dst[done + lane] = src[done + lane];
             } else {
-                int rr = r / K, k = r - rr * K;                 // running (row, code) of element i
-                const int step_r = PM / K, step_k = PM - step_r * K;
-                for (int i = r; i < n; i += PM) {
-                    __stcs(dst + i, sP[rr * KO + k]);
+                int rr = lane / K, k = lane - rr * K;           // running (row, code) of element i
+                const int step_r = 32 / K, step_k = 32 - step_r * K;
+                for (int i = lane; i < n; i += 32) {
+                    __stcs(dst + i, src[rr * KO + k]);
                     rr += step_r; k += step_k;
                     if (k >= K) { k -= K; ++rr; }
                 }
             }
+            if (lane == 0) tma_store_wait_read();   // this warp's shared memory may be overwritten from here on
         }
-        if (r == 0) tma_store_wait_read();          // shared memory may be overwritten from here on
         VQB_PTL(8);
         if (tile + (int)gridDim.x < p.num_tiles) __syncthreads();       // another tile follows: the buffers are free
     }
@@ -355,20 +346,20 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         __syncthreads();
         if (r == 0) atomicAdd(p.sqerr, (double)sRed[0] + (double)sRed[1] + (double)sRed[2] + (double)sRed[3]);
     }
-    if (r == 0) tma_store_wait_all();
     VQB_PTL(9);
 
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<64>(tmem_base);
     if (p.dbg && r == 0 && blockIdx.x == 0) p.dbg[61] = globaltimer_ns();
+    if (p.dbg && r == 0) p.dbg[129 + 2 * blockIdx.x] = globaltimer_ns();
 }
 
 // -----------------------------------------------------------------------------------------------------------
 // operand image of a table that was not assembled by vqb_assemble_table (LINEAR score; raw C-ABI calls without a cache)
 // -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-build_image_kernel(const float* __restrict__ w, int K, int D, uint8_t* __restrict__ img) {
+build_image_kernel(const float* __restrict__ w, const float* __restrict__ bias, int K, int D, uint8_t* __restrict__ img) {
     __shared__ float s_max[8], s_nrm[8];
     pdl_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,11 +379,11 @@ build_image_kernel(const float* __restrict__ w, int K, int D, uint8_t* __restric
     gmax = 0.f; nmax = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { gmax = fmaxf(gmax, s_max[i]); nmax = fmaxf(nmax, s_nrm[i]); }
-    write_image(w, D, K, D, gmax, sqrtf(nmax), img);
+    write_image(w, D, K, D, gmax, sqrtf(nmax), bias, img);
 }
 
-int launch_build_image(const float* w, int K, int D, void* img, cudaStream_t s) {
-    build_image_kernel<<<1, 256, 0, s>>>(w, K, D, reinterpret_cast<uint8_t*>(img));
+int launch_build_image(const float* w, const float* bias, int K, int D, void* img, cudaStream_t s) {
+    build_image_kernel<<<1, 256, 0, s>>>(w, bias, K, D, reinterpret_cast<uint8_t*>(img));
     VQB_CHECK_LAUNCH("build_image_kernel");
     return VQB_OK;
 }
@@ -408,12 +399,12 @@ bool forward_pcode_supported(const vqb_fwd_args* a) {
 
 size_t forward_pcode_workspace(const vqb_fwd_args* a) { return a->operand_cache ? 0 : (size_t)IMG_BYTES; }
 
-template <int KP, int D>
+template <int KP, int D, bool LINEAR>
 static int launch_pc(const CUtensorMap& tx, const CUtensorMap& tq, PcP p, cudaStream_t s, bool pdl) {
     const int tab_bytes = p.K * (D + 4) * 4, img_bytes = 2 * KP * 128;
     p.se_bytes = ((tab_bytes > img_bytes ? tab_bytes : img_bytes) + 1023) & ~1023;
-    const size_t smem = (size_t)2 * PBLK + p.se_bytes + (size_t)PM * (p.K | 1) * 4 + 64 * 4 + 4 * 4 + 3 * 8 + 16 + 1024;
-    auto kern = vqb_fwd_pcode_kernel<KP, D>;
+    const size_t smem = (size_t)2 * PBLK + p.se_bytes + (size_t)PM * (p.K | 1) * 4 + 320 + 4 * 4 + 4 * 8 + 16 + 1024;
+    auto kern = vqb_fwd_pcode_kernel<KP, D, LINEAR>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int slots = 3 * sm_count();
@@ -436,13 +427,13 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     }
     const uint8_t* img = reinterpret_cast<const uint8_t*>(cached ? a->operand_cache : a->workspace);
     if (!cached) {
-        int rc = launch_build_image(a->score_w, (int)K, (int)D, a->workspace, s);
+        int rc = launch_build_image(a->score_w, a->score_b, (int)K, (int)D, a->workspace, s);
         if (rc) return rc;
     }
     CUtensorMap tx, tq;
     int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, PM);
     if (rc) return rc;
-    if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, PM))) return rc;
+    if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, 32))) return rc;   // one warp's slab per store
     PcP p;
     p.x = a->x; p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.img = img;
     p.pcode = a->p_code; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
@@ -452,20 +443,13 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     // VQB_AFTER_ASSEMBLE) the table assembly
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
     const int KP = (int)((K + 15) / 16 * 16);
-    if (D == 32) {
-        switch (KP) {
-            case 16: return launch_pc<16, 32>(tx, tq, p, s, pdl);
-            case 32: return launch_pc<32, 32>(tx, tq, p, s, pdl);
-            case 48: return launch_pc<48, 32>(tx, tq, p, s, pdl);
-            default: return launch_pc<64, 32>(tx, tq, p, s, pdl);
-        }
-    }
-    switch (KP) {
-        case 16: return launch_pc<16, 64>(tx, tq, p, s, pdl);
-        case 32: return launch_pc<32, 64>(tx, tq, p, s, pdl);
-        case 48: return launch_pc<48, 64>(tx, tq, p, s, pdl);
-        default: return launch_pc<64, 64>(tx, tq, p, s, pdl);
-    }
+    const bool lin = (a->flags & VQB_SCORE_LINEAR) != 0;
+#define VQB_PC_CASE(kp, d) \
+    if (KP == kp && D == d) return lin ? launch_pc<kp, d, true>(tx, tq, p, s, pdl) : launch_pc<kp, d, false>(tx, tq, p, s, pdl);
+    VQB_PC_CASE(16, 32) VQB_PC_CASE(32, 32) VQB_PC_CASE(48, 32) VQB_PC_CASE(64, 32)
+    VQB_PC_CASE(16, 64) VQB_PC_CASE(32, 64) VQB_PC_CASE(48, 64) VQB_PC_CASE(64, 64)
+#undef VQB_PC_CASE
+    return invalid("vqb_forward: shape not supported by the parity-mode tensor-core kernel");
 }
 
 }  // namespace vqb

@@ -41,27 +41,47 @@ assemble_table_kernel(const float* __restrict__ learnable, const float* __restri
 
 // Small tables (K <= 64, D <= 64: every semi-tts configuration) in ONE CTA: the table, |e|^2 and -- in the same launch --
 // the fp16x2 operand image (vqb_f16x2.cuh) that the parity-mode forward and backward kernels consume.  The image needs
-// the table-wide maximum, which a single CTA has without a grid-wide dependency.
-__global__ void __launch_bounds__(256)
+// the table-wide maximum, which a single CTA has without a grid-wide dependency.  The inputs are staged in shared memory
+// with one round of coalesced loads, so the A-term projection sums (:110) never wait on global memory.
+__global__ void __launch_bounds__(512)
 assemble_small_kernel(const float* __restrict__ learnable, const float* __restrict__ attr,
                       const float* __restrict__ proj_w, const float* __restrict__ proj_b,
                       int K, int D, int A, int Da, float* __restrict__ table,
                       float* __restrict__ enorm, __nv_bfloat16* __restrict__ table_bf16, uint8_t* __restrict__ img) {
     __shared__ float s_tab[64 * 64];
-    __shared__ float s_max[8], s_nrm[8];
+    __shared__ float s_en[64];
+    __shared__ float s_max[16], s_nrm[16];
+    extern __shared__ float s_dyn[];                   // attr [K][A] | proj_w [Da][A] | proj_b [Da]
+    float* s_attr = s_dyn;
+    float* s_w = s_attr + K * A;
+    float* s_b = s_w + Da * A;
     const int Dl = D - Da;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     pdl_launch();                                      // the forward kernel may start its prologue (it waits before reading)
+    for (int i = threadIdx.x; i < K * Dl; i += blockDim.x) {
+        const int k = i / Dl, d = i - k * Dl;
+        s_tab[k * D + d] = learnable[i];
+    }
+    for (int i = threadIdx.x; i < K * A; i += blockDim.x) s_attr[i] = attr[i];
+    for (int i = threadIdx.x; i < Da * A; i += blockDim.x) s_w[i] = proj_w[i];
+    if ((int)threadIdx.x < Da) s_b[threadIdx.x] = proj_b[threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * Da; i += blockDim.x) {       // projected columns, same fmaf order as table_entry
+        const int k = i / Da, j = i - k * Da;
+        const float* a = s_attr + k * A;
+        const float* w = s_w + j * A;
+        float acc = 0.f;
+        for (int t = 0; t < A; ++t) acc = fmaf(a[t], w[t], acc);
+        s_tab[k * D + Dl + j] = acc + s_b[j];
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
-        const int k = i / D, d = i - k * D;
-        const float v = table_entry(learnable, attr, proj_w, proj_b, k, d, Dl, A);
-        s_tab[i] = v;
+        const float v = s_tab[i];
         table[i] = v;
         if (table_bf16) table_bf16[i] = __float2bfloat16_rn(v);
     }
-    __syncthreads();
     float gmax = 0.f, nmax = 0.f;
-    for (int k = warp; k < K; k += 8) {                // one warp per row: |e|^2, the table maximum, the largest row norm
+    for (int k = warp; k < K; k += nwarp) {            // one warp per row: |e|^2, the table maximum, the largest row norm
         float sq = 0.f;
         for (int d = lane; d < D; d += 32) {
             const float v = s_tab[k * D + d];
@@ -69,16 +89,15 @@ assemble_small_kernel(const float* __restrict__ learnable, const float* __restri
             sq = fmaf(v, v, sq);
         }
         sq = warp_sum(sq);
-        if (lane == 0 && enorm) enorm[k] = sq;
+        if (lane == 0) { s_en[k] = sq; if (enorm) enorm[k] = sq; }
         nmax = fmaxf(nmax, sq);
     }
     gmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gmax)));   // non-negative floats order like uints
     if (lane == 0) { s_max[warp] = gmax; s_nrm[warp] = nmax; }
     __syncthreads();
     gmax = 0.f; nmax = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { gmax = fmaxf(gmax, s_max[i]); nmax = fmaxf(nmax, s_nrm[i]); }
-    write_image(s_tab, D, K, D, gmax, sqrtf(nmax), img);
+    for (int i = 0; i < nwarp; ++i) { gmax = fmaxf(gmax, s_max[i]); nmax = fmaxf(nmax, s_nrm[i]); }
+    write_image(s_tab, D, K, D, gmax, sqrtf(nmax), s_en, img);
 }
 
 // d_learnable = eff[:, :Dl];  d_proj_w = eff[:, Dl:]^T @ attr;  d_proj_b = colsum(eff[:, Dl:])
@@ -137,8 +156,9 @@ extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr,
     if (has_attr && (!proj_w || !proj_b || n_attr <= 0 || dim_attr <= 0 || dim_attr >= dim))
         return invalid("vqb_assemble_table: phn_attr given but projection is missing or 0 < D_a < D violated");
     if (!has_attr) { n_attr = 0; dim_attr = 0; }
-    if (operand_cache && small_table(n_codes, dim)) {
-        assemble_small_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
+    if (operand_cache && small_table(n_codes, dim) && n_attr <= 63) {
+        const size_t dyn = (size_t)(n_codes * n_attr + dim_attr * n_attr + dim_attr) * 4;      // <= 32.5 KB
+        assemble_small_kernel<<<1, 512, dyn, (cudaStream_t)stream>>>(
             learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
             enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache));
         VQB_CHECK_LAUNCH("assemble_small_kernel");

@@ -34,6 +34,21 @@ def dump(title, raw, names):
         print("%-18s +%7.2f us" % ("kernel_exit", ((raw[61] & mask) - t0) / 1e3))
 
 
+def spans(title, raw):
+    """per-CTA (start, end) marks at raw[128 + 2 b], raw[129 + 2 b]: when do the CTAs start, how long do they live"""
+    st = [raw[128 + 2 * b] for b in range(960) if raw[128 + 2 * b] and raw[129 + 2 * b]]
+    en = [raw[129 + 2 * b] for b in range(960) if raw[128 + 2 * b] and raw[129 + 2 * b]]
+    if not st:
+        return
+    t0 = min(st)
+    starts = sorted((s - t0) / 1e3 for s in st)
+    life = sorted((e - s) / 1e3 for s, e in zip(st, en))
+    q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]
+    print("== %s: %d CTAs; start after the first CTA: median %.2f us, p90 %.2f, max %.2f; lifetime: min %.2f, median %.2f, p90 %.2f, "
+          "max %.2f us; last exit at +%.2f us" % (title, len(st), q(starts, .5), q(starts, .9), starts[-1], life[0], q(life, .5),
+                                                  q(life, .9), life[-1], (max(en) - t0) / 1e3))
+
+
 def main():
     g = load_golden("l2_attr_stopgrad")
     m = build_module(g, "l2")
@@ -42,7 +57,7 @@ def main():
     x = torch.randn(64, 800, 64, device="cuda", requires_grad=True)
     gp = torch.randn(64, 800, 43, device="cuda")
     gq = torch.randn(64, 800, 64, device="cuda")
-    buf = torch.zeros(128, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
     for _ in range(3):
         p, q, _, _ = m(x)
         torch.autograd.backward([p, q], [gp, gq])
@@ -65,7 +80,9 @@ def main():
     print("module forward call %.1f us, backward call %.1f us (eager, all kernels + host)" % (e0.elapsed_time(e1) * 1e3,
                                                                                          e2.elapsed_time(e3) * 1e3))
     dump("forward, CTA 0 thread 0", fwd, FWD)
+    spans("forward", fwd)
     dump("backward, CTA 0 thread 0", bwd, BWD)
+    spans("backward", bwd)
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ g = torch.Generator().manual_seed(rank)
 x = torch.randn(64, 800, 64, generator=g).to(dev).requires_grad_(True)
 gp, gq = torch.randn(64, 800, 43, generator=g).to(dev), torch.randn(64, 800, 64, generator=g).to(dev)
 lib = V._lib.load()
-buf = torch.zeros(128, dtype=torch.int64, device=dev)
+buf = torch.zeros(2048, dtype=torch.int64, device=dev)     # vqb_debug_set_timeline: 2048 u64 (phase marks + per-CTA start/end)
 for it in range(6):
     for p_ in m.parameters(): p_.grad = None
     p, q, _, _ = m(x)
