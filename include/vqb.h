@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQB_ABI_VERSION 2
+#define VQB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VQB_API __attribute__((visibility("default")))
@@ -147,15 +147,21 @@ VQB_API int vqb_forward(const vqb_fwd_args* args, void* stream);
  * Exchange buffer of each rank (peer-mapped, e.g. torch symmetric memory), vqb_exchange_bytes(n_flat, world) bytes,
  * zero-filled once before the first call:  [2 slots][world senders][n_flat padded to a multiple of 4] 8-byte words.
  * Words carry a call counter (`epoch`, never 0) and the slots alternate with its parity, so the buffers need no reset
- * between calls or CUDA-graph replays; all ranks must make the same sequence of calls. */
+ * between calls or CUDA-graph replays; all ranks must make the same sequence of calls.  A rank whose shard is empty
+ * (n_rows == 0) still calls vqb_backward with the tail: only the tail kernel runs, over zero partial records. */
 typedef struct vqb_bwd_tail {
     const float* phn_attr;       /* [K,A], A <= 63, or NULL (then n_attr = dim_attr = 0 and d_flat = d_learnable only) */
     int64_t n_attr, dim_attr;
     float* d_flat;               /* [K*D_l + D_a*A + D_a] = d_learnable | d_proj_w | d_proj_b, overwritten */
-    uint32_t* counter;           /* [2] device words, zero before the first call: [0] block ticket (left zero),
-                                    [1] epoch of the exchange (incremented by every call with world > 1) */
+    uint32_t* counter;           /* [4] device words, zero before the first call: [0] block ticket (left zero),
+                                    [1] epoch of the exchange (incremented by every call with world > 1),
+                                    [2] error flag: 0, or 1 + the rank an exchange gave up waiting for (sticky; the host
+                                    reads it when it synchronises anyway), [3] reserved */
     int32_t world, rank;         /* world <= 1: no exchange */
     void* const* peer_bufs;      /* DEVICE array [world] of each rank's exchange-buffer address as mapped here */
+    uint32_t timeout_ms;         /* how long a block polls for a peer's words before it raises counter[2] and returns
+                                    with an incomplete sum (no trap: the context survives); 0 = 120 000 ms */
+    uint32_t reserved;
 } vqb_bwd_tail;
 
 #define VQB_MAX_WORLD 16

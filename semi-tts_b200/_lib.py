@@ -5,7 +5,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqb200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # flags (include/vqb.h)
 SCORE_L2 = 0x0001
@@ -30,7 +30,8 @@ class FwdArgs(ctypes.Structure):
 
 class BwdTail(ctypes.Structure):
     _fields_ = [("phn_attr", _p), ("n_attr", ctypes.c_int64), ("dim_attr", ctypes.c_int64), ("d_flat", _p),
-                ("counter", _p), ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_bufs", _p)]
+                ("counter", _p), ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_bufs", _p),
+                ("timeout_ms", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class BwdArgs(ctypes.Structure):

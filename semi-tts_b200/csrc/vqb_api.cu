@@ -99,6 +99,11 @@ extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_mc2(
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_cs2(int v) { vqb::set_debug_search_cs2(v); }
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_pipe(int v) { vqb::set_debug_search_pipe(v); }
 
+namespace vqb { void set_debug_fwd_stagger(int ns); void set_debug_bwd_stagger(int ns); }
+// undocumented developer hook: start delay (ns) per co-resident CTA slot of the parity-mode forward / backward kernels
+extern "C" __attribute__((visibility("default"))) void vqb_debug_set_stagger(int fwd_ns, int bwd_ns) {
+    vqb::set_debug_fwd_stagger(fwd_ns); vqb::set_debug_bwd_stagger(bwd_ns);
+}
 namespace vqb {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -219,9 +224,17 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
     int rc = validate_bwd(a);
     if (rc) return rc;
     if ((rc = require_device())) return rc;
-    if (a->n_rows == 0) return VQB_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const bool l2 = a->flags & VQB_SCORE_L2;
+    if (a->n_rows == 0) {
+        // an empty shard of a data-parallel run: the fused tail still runs (over zero partial records), so that this rank
+        // pushes its zeros and its peers' exchange completes
+        if (a->tail && l2) {
+            if (!a->tail->d_flat || !a->tail->counter || !a->gather_table) return invalid("vqb_backward: tail.d_flat, tail.counter and gather_table are required");
+            return launch_bwd_reduce(a, nullptr, 0, s, nullptr);
+        }
+        return VQB_OK;
+    }
     const bool stop_grad = a->flags & VQB_STOP_GRAD;
     const bool skip = a->flags & VQB_SKIP;
     const size_t nd_bytes = (size_t)a->n_rows * a->dim * sizeof(float);

@@ -53,6 +53,7 @@ struct BwdPcP {
     int N, K, n_real, num_tiles;
     int t_first;              // L2 + fused tail: columns d >= t_first are also stored transposed (record plane 1), else 64
     int pg_bytes, stage_bytes;
+    int stagger_ns, n_sm;     // start delay of the second co-resident CTA of an SM (see the forward kernel)
     unsigned flags;
 };
 
@@ -138,6 +139,13 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             tma_load_2d(sG + TBLK, &tm_g, 32, row0, in_full);
         }
     };
+    if (p.stagger_ns > 0 && r == 0) {
+        const unsigned long long wait_ns = (unsigned long long)(blockIdx.x / p.n_sm) * (unsigned long long)p.stagger_ns;
+        if (wait_ns) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (globaltimer_ns() - t0 < wait_ns) __nanosleep(100);
+        }
+    }
     if (r == 0 && n_my > 0) issue_loads(0);
     VQB_BTL(1);
 
@@ -496,6 +504,8 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 // host side
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
+static int g_bwd_stagger_ns = getenv("VQB_BWD_STAGGER_NS") ? atoi(getenv("VQB_BWD_STAGGER_NS")) : 0;
+void set_debug_bwd_stagger(int ns) { g_bwd_stagger_ns = ns; }
 
 bool backward_pcode_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
@@ -567,6 +577,8 @@ int launch_backward_pcode(const vqb_bwd_args* a, cudaStream_t s) {
     p.flags = a->flags;
     p.t_first = (a->tail && l2) ? 64 - (int)a->tail->dim_attr : 64;
     p.pg_bytes = p.stage_bytes = 0;
+    p.stagger_ns = g_bwd_stagger_ns;
+    p.n_sm = sm_count();
     const int KP = (int)((K + 15) / 16 * 16);
     if (l2) {
         switch (KP) {

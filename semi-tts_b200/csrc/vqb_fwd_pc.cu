@@ -45,6 +45,8 @@ struct PcP {
     unsigned long long* dbg;   // optional timeline buffer (vqb_debug_set_timeline), NULL in production
     int N, K, num_tiles;
     int se_bytes;              // shared-memory bytes of the table region (image, later the fp32 gather table)
+    int stagger_ns;            // start delay per co-resident CTA slot (see the kernel)
+    int n_sm;
     unsigned flags;
 };
 
@@ -62,7 +64,7 @@ __device__ __noinline__ float exact_s2(const float* __restrict__ xrow, const flo
         dot = fmaf(xv.x, w.x, dot); dot = fmaf(xv.y, w.y, dot);
         dot = fmaf(xv.z, w.z, dot); dot = fmaf(xv.w, w.w, dot);
     }
-    if (linear) return mul * (dot + b);
+    if (linear) return mul * -(dot + b);                             // mul = -log2(e): see the kernel
     return mul * __fsub_rn(__fadd_rn(xx, b), 2.f * dot);
 }
 
@@ -118,6 +120,18 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     float se_acc = 0.f;
     float temp_raw = 1.f;
     constexpr uint32_t IDESC = umma_idesc(0u, PM, KP);
+
+    // Phase stagger.  The CTAs that share an SM (blockIdx, blockIdx + #SM, blockIdx + 2 #SM in the first wave) would otherwise
+    // run in lockstep -- all loading, then all computing, then all storing -- so that HBM, the issue slots and the L2
+    // write path are each busy a third of the time.  Slot j starts j * stagger_ns later: load, compute and store phases
+    // of the three tiles of an SM overlap like the stages of a software pipeline.
+    if (p.stagger_ns > 0 && r == 0) {
+        const unsigned long long wait_ns = (unsigned long long)(blockIdx.x / p.n_sm) * (unsigned long long)p.stagger_ns;
+        if (wait_ns) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (globaltimer_ns() - t0 < wait_ns) __nanosleep(100);
+        }
+    }
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -203,60 +217,79 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         if (it == 0) mbar_wait(e_full, 0);           // the header (scale, bias) has landed with the image: visible to this thread
 
         // ---- scores (log2 domain) -> softmax -> p_code, argmax over p_code -----------------------------------------
-        float v[KP];
-        tmem_ld_cols<KP>(tmem_base + lane_addr, v);
-        tcgen05_fence_before();
+        //   L2:     score = relu(temp) * -((|x|^2 + |e|^2) - 2 x.e)          (:115, :208-213)
+        //   LINEAR: score = x.w + b                                           (:190)
+        // Both as s2 = mul * q with mul <= 0:  q = (|x|^2 + |e|^2) - 2 x.e  (L2: the reference's own association; 2 x.e is
+        // an exact scaling of the accumulator, so one fma rounds like the reference's subtraction) or q = -(x.w + b).
         const float tau = fmaxf(temp_raw, 0.f);
-        const float mul = LINEAR ? LOG2E : -tau * LOG2E;
+        const float mul = (LINEAR ? -1.f : -tau) * LOG2E;
         const float emax = *reinterpret_cast<const float*>(sHdr + 4);
-        const float u = pow2i(er) * pow2i(*reinterpret_cast<const int*>(sHdr));
-        float m1 = -INFINITY, m2 = -INFINITY;
+        const float u = pow2i(er) * pow2i(*reinterpret_cast<const int*>(sHdr)) * (LINEAR ? -1.f : -2.f);
+        float v[KP];
+        auto load_scores = [&]() -> float {
+            tmem_ld_cols<KP>(tmem_base + lane_addr, v);
+            float m = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const float dot = v[k] * u;
-            //   L2:     score = relu(temp) * -((|x|^2 + |e|^2) - 2 x.e)          (:115, :208-213)   [2 x.e is exact: one fma]
-            //   LINEAR: score = x.w + b                                           (:190)
-            float s2 = LINEAR ? mul * (dot + sBias[k]) : mul * fmaf(-2.f, dot, __fadd_rn(xx, sBias[k]));
-            if (k >= KP - 15) s2 = k < K ? s2 : -INFINITY;          // padded codes
-            v[k] = s2;
-            m2 = fmaxf(m2, fminf(m1, s2));
-            m1 = fmaxf(m1, s2);
-        }
-        // window: |acc - exact fp32 dot| <= 5e-6 |x||e| (operand pieces 2 * 2^-22, fp32 accumulation in the tensor core and
-        // in the exact kernel's 64-term fmaf chain), twice for the two candidates, doubled in the distance; plus the rounding
-        // of (|x|^2 + |e|^2) - 2 x.e itself
-        {
-            const float xn = sqrtf(xx);
-            const float wd = LINEAR ? 1e-5f * xn * emax : 2e-5f * xn * emax + 2.4e-7f * (xn + emax) * (xn + emax);
-            const float win = fabsf(mul) * wd;
-            if (valid && m1 - m2 <= win && mul != 0.f) {
-                // near-tie: every code inside the window is re-evaluated in exact fp32 (rare: a few rows per 10^5 at config 2)
-                const float thr = m1 - win;
-                const float* xrow = p.x + (size_t)(row0 + r) * D;
-#pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (k < K && v[k] >= thr) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, LINEAR);
-                m1 = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);
-                if (p.stats) atomicAdd(p.stats, 1u);
+            for (int k = 0; k < KP; ++k) {
+                const float q = fmaf(v[k], u, LINEAR ? -sBias[k] : __fadd_rn(xx, sBias[k]));
+                float s2 = mul * q;
+                if (k >= KP - 15) s2 = k < K ? s2 : -INFINITY;      // padded codes
+                v[k] = s2;
+                m = fmaxf(m, s2);
             }
-        }
+            return m;
+        };
+        float s4[4];
+        auto exp_scores = [&](float m) {            // v <- ex2(v - m): the maximum itself gives ex2(0) = 1 exactly
+            s4[0] = s4[1] = s4[2] = s4[3] = 0.f;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m));     // padded codes: ex2(-inf) = 0
+                v[k] = e;
+                s4[k & 3] += e;
+            }
+        };
+        float m1 = load_scores();
+        tcgen05_fence_before();
         if (mul == 0.f) {                           // temp <= 0: uniform over the K real codes only
 #pragma unroll
             for (int k = 0; k < KP; ++k) v[k] = k < K ? 0.f : -INFINITY;
             m1 = 0.f;
         }
-        // exp(score - max): four interleaved sums; the maximum itself gives ex2(0) = 1 exactly, so the arg-max over
-        // p_code = e * inv (first index on ties, :130) is the first code whose e is 1
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        exp_scores(m1);
+        // Index exactness.  |acc - exact fp32 dot| <= 5e-6 |x||e| (operand pieces 2 * 2^-22, fp32 accumulation in the tensor
+        // core and in the exact kernel's 64-term fmaf chain), twice for the two candidates, doubled in the distance, plus the
+        // rounding of (|x|^2 + |e|^2) - 2 x.e itself: `win` in score units.  A second code can only lie inside that window
+        // of the best one if the other codes' exponentials sum to at least ex2(-win) -- one compare per row; rows that pass
+        // it (a handful per 10^5 at config 2) list the codes inside the window, re-evaluate them in exact fp32 (same
+        // expression and fmaf order as vqb_fwd_simt.cu) and redo the softmax.
+        {
+            const float xn = sqrtf(xx);
+            const float wd = LINEAR ? 1e-5f * xn * emax : 2e-5f * xn * emax + 2.4e-7f * (xn + emax) * (xn + emax);
+            const float win = fabsf(mul) * wd;
+            float thr_e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(thr_e) : "f"(-win));
+            thr_e *= 0.999f;
+            if (valid && mul != 0.f && ((s4[0] + s4[1]) + (s4[2] + s4[3])) - 1.f >= thr_e) {
+                unsigned long long cand = 0ull;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            float e;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m1));     // padded codes: ex2(-inf) = 0
-            v[k] = e;
-            s4[k & 3] += e;
+                for (int k = 0; k < KP; ++k) cand |= v[k] >= thr_e ? (1ull << k) : 0ull;
+                if (__popcll(cand) >= 2) {
+                    const float* xrow = p.x + (size_t)(row0 + r) * D;
+                    load_scores();
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if ((cand >> k) & 1ull) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, LINEAR);
+                    m1 = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);
+                    exp_scores(m1);
+                    if (p.stats) atomicAdd(p.stats, 1u);
+                }
+            }
         }
+        // arg-max over p_code = e * inv (monotone in e), first index on ties (:130): the first code whose e is 1
         int best = 0;
 #pragma unroll
         for (int k = KP - 1; k >= 0; --k) best = v[k] >= 1.f ? k : best;
@@ -392,6 +425,9 @@ int launch_build_image(const float* w, const float* bias, int K, int D, void* im
 // host side
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
+// start delay per co-resident CTA slot (ns); developer hook vqb_debug_set_stagger / VQB_FWD_STAGGER_NS
+static int g_fwd_stagger_ns = getenv("VQB_FWD_STAGGER_NS") ? atoi(getenv("VQB_FWD_STAGGER_NS")) : 0;
+void set_debug_fwd_stagger(int ns) { g_fwd_stagger_ns = ns; }
 
 bool forward_pcode_supported(const vqb_fwd_args* a) {
     return a->p_code != nullptr && a->n_codes <= 64 && (a->dim == 32 || a->dim == 64);
@@ -439,6 +475,8 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     p.pcode = a->p_code; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
     p.stats = a->search_stats; p.dbg = get_debug_timeline();
     p.N = (int)N; p.K = (int)K; p.num_tiles = (int)ceil_div(N, PM); p.se_bytes = 0; p.flags = a->flags;
+    p.stagger_ns = g_fwd_stagger_ns;
+    p.n_sm = sm_count();
     // PDL when the kernel enqueued immediately before is ours: the image build above, or (the caller vouches,
     // VQB_AFTER_ASSEMBLE) the table assembly
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);

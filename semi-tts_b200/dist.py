@@ -15,23 +15,39 @@ def shard_bounds(n_items, rank, world):
 
 
 def _flat_view(grads):
-    """If the gradients are consecutive views of one storage (as the backward of this package produces them),
-    return that span as a single 1-D tensor; otherwise None."""
+    """If the gradients are views of one storage that tile a contiguous span of it (as the backward of this package
+    produces them: d_learnable | d_proj_w | d_proj_b, whatever order module.parameters() lists them in), return that span
+    as a single 1-D tensor; otherwise None."""
     if not grads:
         return None
     first = grads[0]
     try:
         base_ptr = first.untyped_storage().data_ptr()
+        for g in grads:
+            if not g.is_contiguous() or g.dtype != first.dtype or g.untyped_storage().data_ptr() != base_ptr:
+                return None
     except Exception:                                   # noqa: BLE001
         return None
-    off = first.storage_offset()
-    for g in grads:
-        if not g.is_contiguous() or g.dtype != first.dtype or g.untyped_storage().data_ptr() != base_ptr \
-                or g.storage_offset() != off:
+    order = sorted(grads, key=lambda g: g.storage_offset())
+    off = order[0].storage_offset()
+    for g in order:
+        if g.storage_offset() != off:                   # gap or overlap
             return None
         off += g.numel()
-    n = off - first.storage_offset()
-    return torch.as_strided(first, (n,), (1,), first.storage_offset())
+    n = off - order[0].storage_offset()
+    return torch.as_strided(order[0], (n,), (1,), order[0].storage_offset())
+
+
+def reduce_route_output(flat, tail, group=None):
+    """Called by the autograd backward of every route that does NOT end in the fused tail kernel (inference() lookups, the
+    scatter-only route, the loss extensions, shapes outside the tensor-core kernels) when the module has a fused exchange
+    attached: the route's flat parameter gradient is summed over the group right here, with one NCCL all-reduce, before
+    autograd accumulates it into p.grad.  With an exchange attached every contribution to p.grad is therefore already a
+    global sum -- whatever mixture of routes a step takes -- and allreduce_codebook_grads() has nothing left to add."""
+    if tail is None or tail.exchange is None or flat is None:
+        return
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(tail.exchange.group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=tail.exchange.group)
 
 
 class PeerExchange:
@@ -43,6 +59,7 @@ class PeerExchange:
         import torch.distributed._symmetric_memory as symm
         from . import _lib
         group = group if group is not None else dist.group.WORLD
+        self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 16:
             raise RuntimeError("semi-tts_b200: the fused exchange supports up to 16 GPUs of one NVLink domain")
@@ -65,8 +82,12 @@ class PeerExchange:
 def enable_fused_allreduce(module, group=None):
     """Sum the quantizer's parameter gradients over `group` INSIDE the backward's tail kernel (one-shot all-reduce over
     NVLink peer memory) instead of an NCCL call after it.  Collective: call on every rank, once, after the process
-    group is up and the module is on its GPU.  allreduce_codebook_grads() then skips gradients that the fused route
-    has already summed (it still reduces them with NCCL whenever a backward took another route)."""
+    group is up and the module is on its GPU.  From then on EVERY gradient the module's autograd functions hand to
+    autograd is already summed over the group: the tensor-core forward route by the tail kernel, every other route
+    (inference() lookups, scatter-only, loss extensions) by an NCCL all-reduce of its own output inside its backward
+    (reduce_route_output).  allreduce_codebook_grads() then only applies `average`.
+    All ranks must run the same sequence of quantizer calls with the same set of upstream gradients (as data-parallel
+    replicas of one model do); a rank whose shard is empty still takes part (its tail runs over zero rows)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
     n = sum(p.numel() for p in module.parameters() if p.requires_grad)
@@ -75,14 +96,29 @@ def enable_fused_allreduce(module, group=None):
     return ex
 
 
+def check_exchange(module):
+    """Raise if an in-kernel exchange of this module has timed out waiting for a peer (one host synchronisation; call it
+    where the trainer synchronises anyway, e.g. where it reads the loss).  The kernel itself never traps: it records the
+    failure in the module's status words and returns, so the CUDA context survives and the error is recoverable."""
+    tail = getattr(module, "fused_tail", None)
+    if tail is None or tail.counter is None:
+        return
+    flag = int(tail.counter[2].item())
+    if flag:
+        raise RuntimeError("semi-tts_b200: the fused gradient exchange timed out waiting for rank %d "
+                           "(VQB_EXCHANGE_TIMEOUT_MS, default 120000); the gradients of that step are incomplete" % (flag - 1))
+
+
 def allreduce_codebook_grads(module, group=None, average=False, include_usage=False):
     """Sum (or average) the quantizer's parameter gradients and its usage histogram across ranks: the only
     exchange of the data-parallel path.  No host synchronisation (CUDA-graph capturable).
-    Gradients produced by this package's backward are views of one flat buffer and are reduced in place by ONE
-    all-reduce.  Gradients from elsewhere (e.g. after accumulation into pre-existing .grad tensors) are packed into
-    a temporary buffer first.  The int64 usage histogram is only consumed at plot time (every 500 steps,
-    bin/train_vqvae.py:305), so by default it is exchanged there (`allreduce_usage`, or `include_usage=True` to do it
-    in the same call: a second, 8*K-byte all-reduce of the counts accumulated since the previous exchange)."""
+    With a fused exchange attached (enable_fused_allreduce) every contribution to p.grad was already summed over the
+    group when autograd received it, so only `average` is applied here.  Otherwise ONE NCCL all-reduce: gradients produced
+    by this package's backward are views of one flat buffer and are reduced in place; gradients from elsewhere (e.g.
+    after accumulation into pre-existing .grad tensors) are packed into a temporary buffer first.  The int64 usage
+    histogram is only consumed at plot time (every 500 steps, bin/train_vqvae.py:305), so by default it is exchanged
+    there (`allreduce_usage`, or `include_usage=True` to do it in the same call: a second, 8*K-byte all-reduce of the
+    counts accumulated since the previous exchange)."""
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = dist.get_world_size(group)
@@ -90,8 +126,8 @@ def allreduce_codebook_grads(module, group=None, average=False, include_usage=Fa
         return
     grads = [p.grad for p in module.parameters() if p.requires_grad and p.grad is not None]
     tail = getattr(module, "fused_tail", None)
-    if grads and tail is not None and tail.exchange is not None and tail.fused:
-        # already summed over the group by the backward's tail kernel
+    if grads and tail is not None and tail.exchange is not None:
+        # already summed over the group, route by route
         if average:
             flat = _flat_view(grads)
             for g in ([flat] if flat is not None else grads):

@@ -138,7 +138,7 @@ class L2Embedding(_QuantizerBase):
         return nn.Embedding.from_pretrained(table)
 
     def inference(self, txt):
-        return VF.codebook_lookup(txt, self.learnable_table, *self._attr_params())
+        return VF.codebook_lookup(txt, self.learnable_table, *self._attr_params(), tail=self.fused_tail)
 
     def forward(self, enc_embs, first_n_real_mel=0):
         B, S, _ = enc_embs.shape
@@ -172,13 +172,14 @@ class SeperateEmbedding(_QuantizerBase):
         self.embedding = nn.Embedding(vocab_size, latent_dim - d_attr)
 
     def inference(self, txt):
-        return VF.codebook_lookup(txt, self.embedding.weight, *self._attr_params())
+        return VF.codebook_lookup(txt, self.embedding.weight, *self._attr_params(), tail=self.fused_tail)
 
     def forward(self, enc_embs, first_n_real_mel=0):
         # first_n_real_mel is unused here, as in the reference (src/embed.py:188)
         attr, pw, pb = self._attr_params()
         p_code, new_latent, idx = VF.vq_linear(
             enc_embs, self.asr_final_layer.weight, self.asr_final_layer.bias, self.embedding.weight,
-            attr, pw, pb, stop_grad=self.stop_grad, hist=self._hist(enc_embs), tensor_cores=self.tensor_cores)
+            attr, pw, pb, stop_grad=self.stop_grad, hist=self._hist(enc_embs), tensor_cores=self.tensor_cores,
+            tail=self.fused_tail)
         self.last_idx = idx
         return p_code, new_latent, 0, 0

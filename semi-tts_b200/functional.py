@@ -62,8 +62,10 @@ def assemble_table(learnable, phn_attr=None, proj_w=None, proj_b=None, want_bf16
     return table, enorm, tbf
 
 
-def _table_backward(dtable, table, colsum, phn_attr, Da):
-    """Returns (d_learnable, d_proj_w, d_proj_b) from the accumulated dtable (+ the |e|^2 term)."""
+def _table_backward(dtable, table, colsum, phn_attr, Da, tail=None):
+    """Returns (d_learnable, d_proj_w, d_proj_b) from the accumulated dtable (+ the |e|^2 term).  With a fused exchange
+    attached to the module (`tail.exchange`), the flat result is summed over the data-parallel group here (NCCL), so that
+    every gradient autograd receives from this package is already a global sum (dist.reduce_route_output)."""
     lib = _lib.load()
     K, D = dtable.shape
     A = phn_attr.shape[1] if phn_attr is not None else 0
@@ -79,6 +81,9 @@ def _table_backward(dtable, table, colsum, phn_attr, Da):
     with torch.cuda.device(dtable.device):
         _lib.check(lib.vqb_table_backward(ptr(dtable), ptr(table), ptr(colsum), ptr(phn_attr), K, D, A, Da,
                                           ptr(d_learn), ptr(d_w), ptr(d_b), _stream(dtable)))
+    if tail is not None and tail.exchange is not None:
+        from .dist import reduce_route_output
+        reduce_route_output(flat, tail)
     return d_learn, d_w, d_b
 
 
@@ -123,9 +128,18 @@ class FusedTail:
         self.enabled = not os.environ.get("VQB_NO_TAIL_TEST")     # developer switch
 
     def counter_for(self, dev):
+        # [0] block ticket, [1] epoch of the exchange, [2] error flag (1 + the rank a timed-out exchange waited for), [3] spare
         if self.counter is None or self.counter.device != dev:
-            self.counter = torch.zeros(2, device=dev, dtype=torch.int32)
+            self.counter = torch.zeros(4, device=dev, dtype=torch.int32)
         return self.counter
+
+
+def _exchange_timeout_ms():
+    """How long the in-kernel exchange waits for a peer before it gives up and raises the module's error flag
+    (dist.check_exchange); comparable to NCCL's watchdog rather than to a step time: rank-0 validation, checkpointing or a
+    data-loader stall must not kill the job."""
+    import os
+    return int(os.environ.get("VQB_EXCHANGE_TIMEOUT_MS", "120000"))
 
 
 def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp, p_code, idx, g_p, g_q,
@@ -145,7 +159,8 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.operand_cache = ptr(operand_cache)
     use_tail = bool(tail is not None and tail.enabled and (flags & _lib.SCORE_L2) and not separate_gather
-                    and lib.vqb_backward_kernel_name(ctypes.byref(a)) in (b"vqb_bwd_pcode_kernel", b"vqb_bwd_h2_kernel"))
+                    and (lib.vqb_backward_kernel_name(ctypes.byref(a)) in (b"vqb_bwd_pcode_kernel", b"vqb_bwd_h2_kernel")
+                         or (N == 0 and tail.exchange is not None)))      # an empty shard still joins its peers' exchange
     flat = tl = None
     if use_tail:
         # the tail overwrites its scratch and outputs: nothing to zero-fill
@@ -159,6 +174,7 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
         tl.counter = ptr(tail.counter_for(dev))
         ex = tail.exchange
         tl.world, tl.rank, tl.peer_bufs = (ex.world, ex.rank, ex.peer_ptrs_dev(n_flat)) if ex is not None else (1, 0, None)
+        tl.timeout_ms = _exchange_timeout_ms()
         a.tail = ctypes.pointer(tl)
     else:
         # one zero-filled buffer (one fill kernel) carved into the accumulation targets
@@ -260,9 +276,12 @@ class _VQL2(torch.autograd.Function):
         B, S, D, K = ctx.shape
         N = B * S
         have_loss = g_vq is not None or g_commit is not None
-        if (g_p is None and g_q is None and not have_loss) or N == 0:
+        if g_p is None and g_q is None and not have_loss:
             return (None,) * 7
         dev = x2d.device
+        exchange_on = cfg.tail is not None and cfg.tail.exchange is not None
+        if N == 0 and not exchange_on:
+            return (None,) * 7
         g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
         flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TEMP_GRAD if ctx.temp_grad else 0) | \
@@ -270,7 +289,16 @@ class _VQL2(torch.autograd.Function):
         d_temp = colsum = flat = None
         if cfg.tail is not None:
             cfg.tail.fused = False
-        if g_p2 is None and g_q2 is None:
+        if N == 0:
+            # an empty shard of a data-parallel run still takes part in the exchange its peers run
+            dx = torch.zeros(0, D, device=dev, dtype=torch.float32)
+            if g_p2 is not None and not have_loss:
+                _, d_w, colsum, _, d_temp, flat = _run_backward(
+                    flags, 0, x2d, table, enorm, table, temp, p_code, idx, g_p2, g_q2, False, False, ctx.op_cache,
+                    tail=cfg.tail, phn_attr=phn_attr, Da=ctx.Da)
+            if flat is None:
+                d_w = torch.zeros(K, D, device=dev, dtype=torch.float32)
+        elif g_p2 is None and g_q2 is None:
             dx, d_w = None, torch.zeros(K, D, device=dev, dtype=torch.float32)
         elif g_p2 is None and cfg.stop_grad:
             # scatter-only: dx = g_q, the straight-through identity, returned as the same tensor (zero bytes)
@@ -287,7 +315,7 @@ class _VQL2(torch.autograd.Function):
             n_l, n_w = K * (D - Da), Da * A
             return dx.view(B, S, D), flat[:n_l].view(K, D - Da), None, \
                 (flat[n_l:n_l + n_w].view(Da, A) if Da else None), (flat[n_l + n_w:] if Da else None), None, None
-        if have_loss:
+        if have_loss and N > 0:
             if dx is None:
                 dx, acc = torch.empty(N, D, device=dev, dtype=torch.float32), False
             elif dx is g_q2:
@@ -295,7 +323,10 @@ class _VQL2(torch.autograd.Function):
             else:
                 acc = True
             _loss_backward(x2d, table, idx, _g32(g_vq), _g32(g_commit), dx, acc, d_w)
-        d_learn, d_pw, d_pb = _table_backward(d_w, table, colsum, phn_attr, ctx.Da)
+        d_learn, d_pw, d_pb = _table_backward(d_w, table, colsum, phn_attr, ctx.Da, cfg.tail)
+        if ctx.temp_grad and exchange_on and d_temp is not None:
+            from .dist import reduce_route_output
+            reduce_route_output(d_temp, cfg.tail)
         if ctx.temp_grad and d_temp is None:
             d_temp = torch.zeros(1, device=dev, dtype=torch.float32)
         return (dx.view(B, S, D) if dx is not None else None), d_learn, None, d_pw, d_pb, \
@@ -366,13 +397,17 @@ class _VQLinear(torch.autograd.Function):
         flags = _fwd_flags(_lib.SCORE_LINEAR, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         dx, d_w, colsum, d_tab, _, _ = _run_backward(flags, 0, x2d, w, None, table, None, p_code, idx, g_p2, g_q2,
                                                      True, True)
-        d_emb, d_pw, d_pb = _table_backward(d_tab, None, None, phn_attr, ctx.Da)
+        d_emb, d_pw, d_pb = _table_backward(d_tab, None, None, phn_attr, ctx.Da, cfg.tail)
+        if cfg.tail is not None and cfg.tail.exchange is not None:
+            from .dist import reduce_route_output
+            reduce_route_output(d_w, cfg.tail)
+            reduce_route_output(colsum, cfg.tail)
         return dx.view(B, S, D), d_w, colsum, d_emb, None, d_pw, d_pb, None
 
 
-def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None, tensor_cores=True):
+def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None, tensor_cores=True, tail=None):
     """Separate quantizer (src/embed.py:187-205). Returns (p_code, new_latent, idx)."""
-    cfg = _Cfg(stop_grad=stop_grad, hist=hist, tensor_cores=tensor_cores)
+    cfg = _Cfg(stop_grad=stop_grad, hist=hist, tensor_cores=tensor_cores, tail=tail)
     return _VQLinear.apply(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, cfg)
 
 
@@ -381,7 +416,7 @@ def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, 
 # ------------------------------------------------------------------------------------------------
 class _Lookup(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, txt, learnable, phn_attr, proj_w, proj_b):
+    def forward(ctx, txt, learnable, phn_attr, proj_w, proj_b, tail):
         _require(txt, "txt", torch.int64)
         lib = _lib.load()
         table, _, _ = assemble_table(learnable, phn_attr, proj_w, proj_b)
@@ -392,13 +427,14 @@ class _Lookup(torch.autograd.Function):
             _lib.check(lib.vqb_inference_gather(ptr(t), t.numel(), ptr(table), K, D, ptr(out), _stream(t)))
         ctx.set_materialize_grads(False)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
+        ctx.tail = tail
         ctx.save_for_backward(t, table, phn_attr)
         return out
 
     @staticmethod
     def backward(ctx, g):
         if g is None:
-            return (None,) * 5
+            return (None,) * 6
         t, table, phn_attr = ctx.saved_tensors
         lib = _lib.load()
         K, D = table.shape
@@ -409,11 +445,12 @@ class _Lookup(torch.autograd.Function):
             _lib.check(lib.vqb_scatter_workspace(t.numel(), K, D, ctypes.byref(nb)))
             ws = torch.empty(nb.value, device=g2.device, dtype=torch.uint8) if nb.value else None
             _lib.check(lib.vqb_scatter_add(ptr(t), t.numel(), ptr(g2), K, D, ptr(dtab), None, ptr(ws), nb.value, _stream(g2)))
-        d_learn, d_pw, d_pb = _table_backward(dtab, None, None, phn_attr, ctx.Da)
-        return None, d_learn, None, d_pw, d_pb
+        d_learn, d_pw, d_pb = _table_backward(dtab, None, None, phn_attr, ctx.Da, ctx.tail)
+        return None, d_learn, None, d_pw, d_pb, None
 
 
-def codebook_lookup(txt, learnable_table, phn_attr=None, proj_w=None, proj_b=None):
+def codebook_lookup(txt, learnable_table, phn_attr=None, proj_w=None, proj_b=None, tail=None):
     """inference(txt): table[txt] on the assembled table (src/embed.py:96-103, :180-185), differentiable
-    w.r.t. learnable_table / proj_attr (the text->speech branch trains the codebook through it)."""
-    return _Lookup.apply(txt, learnable_table, phn_attr, proj_w, proj_b)
+    w.r.t. learnable_table / proj_attr (the text->speech branch trains the codebook through it).  `tail`: the module's
+    FusedTail; with a fused exchange attached the lookup's gradient is summed over the data-parallel group in its backward."""
+    return _Lookup.apply(txt, learnable_table, phn_attr, proj_w, proj_b, tail)

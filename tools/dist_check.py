@@ -30,12 +30,21 @@ def main():
     sets = [[torch.randn(B, S, D, generator=g).to(dev).requires_grad_(True), torch.randn(B, S, K, generator=g).to(dev),
              torch.randn(B, S, D, generator=g).to(dev)] for _ in range(3)]
 
+    txt = torch.randint(0, K, (B, 37), generator=g).to(dev)
+    g_inf = torch.randn(B, 37, D, generator=g).to(dev)
+    with_lookup = [False]
+
     def step(s):
         for p_ in m.parameters():
             p_.grad = None
         s[0].grad = None
         p, q, _, _ = m(s[0])
-        torch.autograd.backward([p, q], [s[1], s[2]])
+        outs, grads = [p, q], [s[1], s[2]]
+        if with_lookup[0]:
+            # the text branch trains the codebook through inference() in every reference step (src/vqvae.py:147): a second,
+            # non-fused contribution to the same parameter gradients
+            outs.append(m.inference(txt)); grads.append(g_inf)
+        torch.autograd.backward(outs, grads)
         V.dist.allreduce_codebook_grads(m)
         return torch.cat([p_.grad.reshape(-1) for p_ in m.parameters() if p_.requires_grad]).clone(), s[0].grad.clone()
 
@@ -43,6 +52,9 @@ def main():
     m.fused_tail.enabled = False
     ref = [step(s) for s in sets]
     assert not m.fused_tail.fused
+    with_lookup[0] = True
+    ref_lookup = [step(s) for s in sets]
+    with_lookup[0] = False
     # fused route
     m.fused_tail.enabled = True
     V.dist.enable_fused_allreduce(m)
@@ -57,6 +69,43 @@ def main():
             dist.all_gather(gathered, got)
             same = all(torch.equal(gathered[0], t) for t in gathered)
             ok = ok and err < 2e-6 and same
+    # mixed routes in one step: fused tail (forward path) + inference() lookups (NCCL inside their backward)
+    with_lookup[0] = True
+    worst_mixed = 0.0
+    for s, (rg, rdx) in zip(sets, ref_lookup):
+        got, dx = step(s)
+        err = float((got - rg).norm() / rg.norm())
+        worst_mixed = max(worst_mixed, err)
+        gathered = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(gathered, got)
+        ok = ok and err < 2e-6 and all(torch.equal(gathered[0], t) for t in gathered)
+    with_lookup[0] = False
+    # an empty shard on the last rank: it still joins the exchange (its tail runs over zero rows); expected = the sum of the
+    # other ranks' local gradients
+    ex = m.fused_tail.exchange
+    m.fused_tail.exchange = None
+
+    def local_grads(s):
+        for p_ in m.parameters():
+            p_.grad = None
+        if s[0].shape[0]:
+            p, q, _, _ = m(s[0])
+            torch.autograd.backward([p, q], [s[1], s[2]])
+            return torch.cat([p_.grad.reshape(-1) for p_ in m.parameters() if p_.requires_grad]).clone()
+        return torch.zeros(sum(p_.numel() for p_ in m.parameters() if p_.requires_grad), device=dev)
+
+    last = rank == world - 1
+    s_e = [t[:0] if last else t for t in sets[1]]
+    s_e[0] = s_e[0].detach().requires_grad_(True)
+    loc = local_grads(s_e)
+    gathered = [torch.empty_like(loc) for _ in range(world)]
+    dist.all_gather(gathered, loc)
+    want = torch.stack(gathered).sum(0)
+    m.fused_tail.exchange = ex
+    got, _ = step(s_e)
+    err_empty = float((got - want).norm() / want.norm())
+    ok = ok and err_empty < 2e-6
+    V.dist.check_exchange(m)
     # CUDA-graph replay of the fused step
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
@@ -89,7 +138,8 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "ok": bool(flag.item()), "max_rel_err_vs_nccl": worst, "max_abs_dx_diff": worst_dx,
-                          "graph_replay_rel_err": err_g, "fused_step_us_16x200": fused_us}), flush=True)
+                          "graph_replay_rel_err": err_g, "mixed_routes_rel_err": worst_mixed, "empty_shard_rel_err": err_empty,
+                          "fused_step_us_16x200": fused_us}), flush=True)
     dist.barrier(); torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0 if flag.item() else 1)
