@@ -251,7 +251,6 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
         };
         float m1 = load_scores();
-        tcgen05_fence_before();
         if (mul == 0.f) {                           // temp <= 0: uniform over the K real codes only
 #pragma unroll
             for (int k = 0; k < KP; ++k) v[k] = k < K ? 0.f : -INFINITY;
@@ -271,24 +270,30 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             float thr_e;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(thr_e) : "f"(-win));
             thr_e *= 0.999f;
+            unsigned long long cand = 0ull;
             if (valid && mul != 0.f && ((s4[0] + s4[1]) + (s4[2] + s4[3])) - 1.f >= thr_e) {
-                unsigned long long cand = 0ull;
 #pragma unroll
                 for (int k = 0; k < KP; ++k) cand |= v[k] >= thr_e ? (1ull << k) : 0ull;
-                if (__popcll(cand) >= 2) {
+            }
+            const bool need = __popcll(cand) >= 2;
+            // tcgen05.ld is warp-collective: if any row of the warp needs the exact path, the whole warp reloads its scores
+            // (rows that do not need it recompute the same softmax)
+            if (__any_sync(0xffffffffu, need)) {
+                m1 = load_scores();
+                if (need) {
                     const float* xrow = p.x + (size_t)(row0 + r) * D;
-                    load_scores();
 #pragma unroll
                     for (int k = 0; k < KP; ++k)
                         if ((cand >> k) & 1ull) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, LINEAR);
                     m1 = -INFINITY;
 #pragma unroll
                     for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);
-                    exp_scores(m1);
                     if (p.stats) atomicAdd(p.stats, 1u);
                 }
+                exp_scores(m1);
             }
         }
+        tcgen05_fence_before();
         // arg-max over p_code = e * inv (monotone in e), first index on ties (:130): the first code whose e is 1
         int best = 0;
 #pragma unroll
