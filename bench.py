@@ -33,6 +33,20 @@ RING = 8             # distinct input/output sets cycled through so that no step
 WORKLOAD = "semi-tts L2 quantizer fwd+bwd, batch 64 x 800 frames, K=43 D=64 (config/semi-multi-spkr-paired-data.yaml codebook)"
 
 
+def _config(world):
+    """The `config` object of the JSON line: built from the workload constants and the world size only, so that the GPU arm
+    and the reference arm print the SAME dict."""
+    fwd_bytes = N_ROWS * (8 * D + 8 + 4 * K)
+    bwd_bytes = N_ROWS * (12 * D + 8 * K + 8)
+    return {"workload": WORKLOAD, "rows_per_step_per_gpu": N_ROWS, "grads": "g_p+g_q",
+            "launch": "GPU arm: one CUDA graph per step (assemble, forward, backward, tail); reference arm: eager torch CPU ops",
+            "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
+                RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
+            "parallelism": "dp%d (frames sharded by batch, codebook replicated; codebook-gradient sum over GPUs inside the "
+                           "backward's tail kernel, one-shot all-reduce over NVLink peer memory; the usage histogram is "
+                           "exchanged once per timed window, where the trainer reads it)" % world}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -119,37 +133,73 @@ def _cpu_state(seed=0):
     return lt, tab.float(), pw, pb, torch.ones(1)
 
 
+def _reference_module():
+    """The UNMODIFIED reference quantizer (src/embed.py: L2Embedding) from the installed tree baseline/_ref (or
+    /root/reference in the build container), built exactly as src/vqvae.py:57 builds it; None if no tree is present."""
+    try:
+        from oracle import ref_import
+        if not ref_import.available():
+            return None
+        ref_embed = ref_import.import_reference()
+        cb = ref_import.load_codebook_cfg("semi-multi-spkr-paired-data.yaml")
+        cb.pop("bone")
+        with ref_import.reference_cwd():
+            torch.manual_seed(0)
+            return ref_embed.L2Embedding(K, False, **cb)
+    except Exception as e:                               # noqa: BLE001 -- fall back to the port, say why
+        print("[bench] reference modules unavailable (%s); timing the port" % str(e).splitlines()[0], file=sys.stderr)
+        return None
+
+
 def cpu_fwd_bwd_rate(steps, warmup, budget_s=None):
-    """frames/s of the reference op sequence (fwd + autograd bwd, both upstream grads) on all host threads."""
-    from oracle import torch_port as TP
+    """frames/s of the reference quantizer (fwd + autograd bwd, both upstream grads) on all host threads: the reference's
+    own module when it is installed (kind "reference"), otherwise the op-sequence port (kind "port")."""
     torch.set_num_threads(os.cpu_count() or 1)
-    lt, tab, pw, pb, temp = _cpu_state()
     x, gp, gq = _inputs(1)
     x.requires_grad_(True)
+    mod = _reference_module()
+    if mod is not None:
+        mod.train()
+        kind = "reference"
+        what = "the reference's own src/embed.py L2Embedding (installed copy baseline/_ref), torch autograd backward"
+
+        def one():
+            x.grad = None
+            for p_ in mod.parameters():
+                p_.grad = None
+            p, q, _, _ = mod(x)                           # src/vqvae.py:119
+            torch.autograd.backward([p, q], [gp, gq])     # src/solver.py:144
+    else:
+        from oracle import torch_port as TP
+        lt, tab, pw, pb, temp = _cpu_state()
+        kind = "port"
+        what = "oracle/torch_port.py: the reference's ATen op sequence, src/embed.py:105-147, torch autograd backward"
+
+        def one():
+            TP.l2_step(x, lt, tab, pw, pb, temp, gp, gq)
     for _ in range(warmup):
-        TP.l2_step(x, lt, tab, pw, pb, temp, gp, gq)
+        one()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        TP.l2_step(x, lt, tab, pw, pb, temp, gp, gq)
+        one()
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return N_ROWS * done / dt, dt / done * 1e3, done, torch.get_num_threads()
+    return N_ROWS * done / dt, dt / done * 1e3, done, torch.get_num_threads(), kind, what
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    rate, ms, done, cores = cpu_fwd_bwd_rate(args.steps, args.warmup, budget_s=120.0)
+    rate, ms, done, cores, kind, what = cpu_fwd_bwd_rate(args.steps, args.warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": "vq_fwd_bwd_frames_per_sec", "value": rate, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_step": N_ROWS, "grads": "g_p+g_q"},
-            "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d full steps of the same workload (oracle/torch_port.py: the reference's ATen op "
-                                       "sequence, src/embed.py:105-147, with torch autograd backward)" % done},
+            "config": _config(args.gpus),
+            "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "%d full steps of the same workload (%s)" % (done, what)},
             "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -219,6 +269,24 @@ def _time_kernels(V, m, sets, iters=24):
     kf = lib.vqb_forward_kernel_name(ctypes.byref(fa[0])).decode()
     kb = lib.vqb_backward_kernel_name(ctypes.byref(ba[0])).decode()
     return statistics.mean(fwd_ms), statistics.mean(bwd_ms), kf, kb
+
+
+def _c3_sweep(local_rank):
+    """BASELINE configs[2]: the large-codebook sweep (K x D at N = 2^20 frames, fused mode) as a sub-record of the bench line:
+    tensor-pipe fraction of the search kernel (stated against BOTH the measured dense bf16 peak and its tf32 half -- the
+    MMA runs kind::tf32) and HBM fraction of the scatter, with the clocks sampled during the sweep."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep_c3
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    pts = sweep_c3.main(quiet=True)
+    clocks = sampler.stop()
+    keep = ("N", "K", "D", "fwd_ms", "search_tflops", "tensor_frac_of_tf32_peak", "tensor_frac_of_dense_bf16_peak",
+            "reranked_rows", "full_scan_rows", "scatter_ms", "scatter_gbs", "scatter_hbm_frac", "frames_per_s_fwd_bwd")
+    return {"workload": "configs[2]: K in {256,1024,4096,8192} x D in {64,256}, N = 2^20 frames, fused mode (no p_code): "
+                        "tcgen05 search forward + scatter-add backward",
+            "points": [{k: p[k] for k in keep if k in p} for p in pts], "clocks": clocks, "seconds": time.perf_counter() - t0}
 
 
 def _log(rank, msg):
@@ -339,33 +407,34 @@ def run_ours(args, rank, world, local_rank):
     value = N_ROWS * world * args.steps / (ms_total * 1e-3)
     _log(rank, "device-resident timing done: %.3f ms/step" % (ms_total / args.steps))
 
-    # ---- e2e: public module API, HOST (pinned) inputs, H2D + D2H inside the timed region ---------------------
-    host_sets = [_inputs(5000 + 1000 * rank + i, "cpu", pin=True) for i in range(4)]
+    # ---- e2e: public module API, the step's HOST input (pinned) uploaded and its results read back inside the region ----
+    # The module's input is enc_embs; the upstream gradients g_p / g_q are produced ON THE DEVICE by whatever consumes the
+    # module's outputs (CTC loss, Tacotron: bin/train_vqvae.py:208,:174), so they stay device-resident here as well.
+    # Every step: H2D x (13.1 MB), forward + backward through the nn.Module, D2H of the picked indices, the parameter
+    # gradients and the usage histogram.
+    host_x = [_inputs(5000 + 1000 * rank + i, "cpu", pin=True)[0] for i in range(4)]
     n_grad = sum(p_.numel() for p_ in m.parameters() if p_.requires_grad)
     h_idx = torch.empty(B, S, dtype=torch.int64).pin_memory()
     h_grad = torch.empty(n_grad + K, dtype=torch.float32).pin_memory()
+    g_dev = [(s_[1], s_[2]) for s_ in sets[:4]]
 
-    # double-buffered pipeline: a copy stream uploads step i+1's pinned host inputs while the compute stream runs step i;
-    # every step still pays its own H2D (x, g_p, g_q) and D2H (indices, codebook gradients, histogram) inside the region
+    # double-buffered pipeline: a copy stream uploads step i+1's pinned host input while the compute stream runs step i
     NBUF = 3
     comp, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
-    dbuf = [[torch.empty_like(t, device=dev) for t in host_sets[0]] for _ in range(NBUF)]
-    for b_ in dbuf:
-        b_[0].requires_grad_(True)
+    dbuf = [torch.empty_like(host_x[0], device=dev).requires_grad_(True) for _ in range(NBUF)]
     ready = [torch.cuda.Event() for _ in range(NBUF)]
     free = [torch.cuda.Event() for _ in range(NBUF)]
 
     def upload(i):
-        b_, hs = dbuf[i % NBUF], host_sets[i % 4]
         with torch.cuda.stream(copy_s):
             copy_s.wait_event(free[i % NBUF])
             with torch.no_grad():
-                for d_, h_ in zip(b_, hs):
-                    d_.copy_(h_, non_blocking=True)
+                dbuf[i % NBUF].copy_(host_x[i % 4], non_blocking=True)
             ready[i % NBUF].record(copy_s)
 
     def e2e_step(i):
-        x, gp, gq = dbuf[i % NBUF]
+        x = dbuf[i % NBUF]
+        gp, gq = g_dev[i % 4]
         comp.wait_event(ready[i % NBUF])
         x.grad = None
         for p_ in m.parameters():
@@ -404,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     _log(rank, "e2e timing done")
     e2e_value = N_ROWS * world * e2e_steps / (e2e_ms * 1e-3)
-    h2d = 4 * (B * S * D * 2 + B * S * K)
+    h2d = 4 * B * S * D
     d2h = 8 * B * S + 4 * (n_grad + K)
 
     if rank == 0:
@@ -414,32 +483,36 @@ def run_ours(args, rank, world, local_rank):
         bwd_bytes = N_ROWS * (12 * D + 8 * K + 8)                     # read x, g_q, p_code, g_p, idx; write dx
         dom = (kb_, bwd_ms, bwd_bytes) if bwd_ms >= fwd_ms else (kf, fwd_ms, fwd_bytes)
         achieved = dom[2] / (dom[1] * 1e-3) / 1e9
-        cpu_rate, cpu_ms, cpu_done, cores = cpu_fwd_bwd_rate(400, 3, budget_s=12.0)
         line = {"metric": "vq_fwd_bwd_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rows_per_step_per_gpu": N_ROWS, "grads": "g_p+g_q",
-                           "launch": "cuda_graph" if use_graph else "eager",
-                           "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
-                               RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
-                           "parallelism": "dp%d (frames sharded by batch, codebook replicated%s)" % (
-                               world, ", codebook-gradient sum over GPUs %s; the usage histogram is "
-                               "exchanged once per timed window, where the trainer reads it" % (
-                                   "fused into the backward tail kernel (one-shot all-reduce over NVLink peer memory)"
-                                   if m.fused_tail.exchange is not None else "by one NCCL all-reduce per step") if dist_on else "")},
+                "config": _config(world),
+                "launch_mode": "cuda_graph" if use_graph else "eager",
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                        "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                        "note": "enc_embs uploaded from pinned host memory every step; the upstream gradients are device-resident "
+                                "(the downstream losses produce them on the device); indices, parameter gradients and the usage "
+                                "histogram read back every step"},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": _ncu_traffic(dom[0]), "peak_source": peak_src,
                              "kernel_ms": {kf: fwd_ms, kb_: bwd_ms},
+                             "frac_per_kernel": {kf: fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peak, kb_: bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak},
+                             "step_frac": (fwd_bytes + bwd_bytes) / (ms_total / args.steps * 1e-3) / 1e9 / peak if world == 1 else None,
                              "note": "kernel_ms = CUDA-event time of the named kernel alone: the library records the two events on "
                                      "the launch stream immediately around that launch (vqb_debug_set_kernel_events); "
                                      "averaged over ring-rotated inputs (> L2)",
                              "algorithmic_bytes": {"fwd": fwd_bytes, "bwd": bwd_bytes}},
-                "cpu_baseline": {"value": cpu_rate, "unit": "frames/s", "cores": cores, "kind": "port",
-                                 "sample": "%d full steps of the same workload on the host (oracle/torch_port.py)" % cpu_done},
                 "clocks": clocks}
+        if world == 1:
+            # the CPU arm beside it: measured once, at N = 1 only (at N > 1 the other ranks would spin in a barrier meanwhile)
+            cpu_rate, cpu_ms, cpu_done, cores, kind, what = cpu_fwd_bwd_rate(400, 3, budget_s=12.0)
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": "frames/s", "cores": cores, "kind": kind,
+                                    "sample": "%d full steps of the same workload on the host (%s)" % (cpu_done, what)}
+            if not args.no_sweep:
+                line["sweep"] = _c3_sweep(local_rank)
+        else:
+            line["cpu_baseline"] = None
         print(json.dumps(line))
     faulthandler.cancel_dump_traceback_later()
     sys.stdout.flush()
@@ -459,6 +532,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-3 roofline sweep sub-record (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -99,11 +99,6 @@ extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_mc2(
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_cs2(int v) { vqb::set_debug_search_cs2(v); }
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_pipe(int v) { vqb::set_debug_search_pipe(v); }
 
-namespace vqb { void set_debug_fwd_stagger(int ns); void set_debug_bwd_stagger(int ns); }
-// undocumented developer hook: start delay (ns) per co-resident CTA slot of the parity-mode forward / backward kernels
-extern "C" __attribute__((visibility("default"))) void vqb_debug_set_stagger(int fwd_ns, int bwd_ns) {
-    vqb::set_debug_fwd_stagger(fwd_ns); vqb::set_debug_bwd_stagger(bwd_ns);
-}
 namespace vqb {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

@@ -736,6 +736,7 @@ bwd_tail_h2_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t)
     const int Dl = 64 - t.Da;
     const int n_l = K * Dl, n_w = t.Da * t.A, n_flat = n_l + n_w + t.Da;
     const bool exchange = t.world > 1;
+    pdl_launch();                                                   // a PDL-launched successor (the next table assembly) may queue up
     if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100] = globaltimer_ns();
     if ((int)blockIdx.x >= t.n_learn_blocks) {
         // constants of a projection block (frozen attribute table, this step's codebook column): fetched while the main

@@ -53,7 +53,6 @@ struct BwdPcP {
     int N, K, n_real, num_tiles;
     int t_first;              // L2 + fused tail: columns d >= t_first are also stored transposed (record plane 1), else 64
     int pg_bytes, stage_bytes;
-    int stagger_ns, n_sm;     // start delay of the second co-resident CTA of an SM (see the forward kernel)
     unsigned flags;
 };
 
@@ -110,6 +109,10 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const uint32_t d1 = tmem_base, d2 = tmem_base + 64, d3 = tmem_base + 64 + KP;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
 
+    // PDL, other direction: this kernel is launched with programmatic stream serialization as well, so its prologue above
+    // (barriers, TMEM, descriptor prefetch) may run under the tail of whatever precedes it in the stream; nothing that
+    // kernel produced is touched before this point.  (A predecessor that never signals simply completes first.)
+    pdl_wait();
     const float tau = L2 ? fmaxf(__ldg(p.temp), 0.f) : 1.f;
     const float cmul = L2 ? -tau : 1.f;
     const int gE = __ldg(reinterpret_cast<const int*>(p.img + IMG_HDR));
@@ -139,13 +142,6 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             tma_load_2d(sG + TBLK, &tm_g, 32, row0, in_full);
         }
     };
-    if (p.stagger_ns > 0 && r == 0) {
-        const unsigned long long wait_ns = (unsigned long long)(blockIdx.x / p.n_sm) * (unsigned long long)p.stagger_ns;
-        if (wait_ns) {
-            const unsigned long long t0 = globaltimer_ns();
-            while (globaltimer_ns() - t0 < wait_ns) __nanosleep(100);
-        }
-    }
     if (r == 0 && n_my > 0) issue_loads(0);
     VQB_BTL(1);
 
@@ -504,8 +500,6 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 // host side
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
-static int g_bwd_stagger_ns = getenv("VQB_BWD_STAGGER_NS") ? atoi(getenv("VQB_BWD_STAGGER_NS")) : 0;
-void set_debug_bwd_stagger(int ns) { g_bwd_stagger_ns = ns; }
 
 bool backward_pcode_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
@@ -535,10 +529,10 @@ static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtenso
     auto kern = vqb_bwd_pcode_kernel<KP, L2>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    // a plain stream-ordered launch: what precedes the backward in the stream (the producer of g_p / g_q, possibly a
-    // copy) is not ours to overlap.  The kernel still releases its own successor early (the fused tail).
+    // launched with programmatic stream serialization: the prologue overlaps the predecessor's tail when that kernel
+    // signals early (this library's forward does); the kernel waits (griddepcontrol.wait) before its first global read
     kernel_event_begin(s);
-    kern<<<grid, BP_THREADS, smem, s>>>(tx, tg, td, p);
+    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(BP_THREADS), smem, s, tx, tg, td, p));
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_pcode_kernel");
     return VQB_OK;
@@ -577,8 +571,6 @@ int launch_backward_pcode(const vqb_bwd_args* a, cudaStream_t s) {
     p.flags = a->flags;
     p.t_first = (a->tail && l2) ? 64 - (int)a->tail->dim_attr : 64;
     p.pg_bytes = p.stage_bytes = 0;
-    p.stagger_ns = g_bwd_stagger_ns;
-    p.n_sm = sm_count();
     const int KP = (int)((K + 15) / 16 * 16);
     if (l2) {
         switch (KP) {

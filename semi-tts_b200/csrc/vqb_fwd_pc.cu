@@ -45,8 +45,6 @@ struct PcP {
     unsigned long long* dbg;   // optional timeline buffer (vqb_debug_set_timeline), NULL in production
     int N, K, num_tiles;
     int se_bytes;              // shared-memory bytes of the table region (image, later the fp32 gather table)
-    int stagger_ns;            // start delay per co-resident CTA slot (see the kernel)
-    int n_sm;
     unsigned flags;
 };
 
@@ -120,18 +118,6 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     float se_acc = 0.f;
     float temp_raw = 1.f;
     constexpr uint32_t IDESC = umma_idesc(0u, PM, KP);
-
-    // Phase stagger.  The CTAs that share an SM (blockIdx, blockIdx + #SM, blockIdx + 2 #SM in the first wave) would otherwise
-    // run in lockstep -- all loading, then all computing, then all storing -- so that HBM, the issue slots and the L2
-    // write path are each busy a third of the time.  Slot j starts j * stagger_ns later: load, compute and store phases
-    // of the three tiles of an SM overlap like the stages of a software pipeline.
-    if (p.stagger_ns > 0 && r == 0) {
-        const unsigned long long wait_ns = (unsigned long long)(blockIdx.x / p.n_sm) * (unsigned long long)p.stagger_ns;
-        if (wait_ns) {
-            const unsigned long long t0 = globaltimer_ns();
-            while (globaltimer_ns() - t0 < wait_ns) __nanosleep(100);
-        }
-    }
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -430,9 +416,6 @@ int launch_build_image(const float* w, const float* bias, int K, int D, void* im
 // host side
 // -----------------------------------------------------------------------------------------------------------
 unsigned long long* get_debug_timeline();
-// start delay per co-resident CTA slot (ns); developer hook vqb_debug_set_stagger / VQB_FWD_STAGGER_NS
-static int g_fwd_stagger_ns = getenv("VQB_FWD_STAGGER_NS") ? atoi(getenv("VQB_FWD_STAGGER_NS")) : 0;
-void set_debug_fwd_stagger(int ns) { g_fwd_stagger_ns = ns; }
 
 bool forward_pcode_supported(const vqb_fwd_args* a) {
     return a->p_code != nullptr && a->n_codes <= 64 && (a->dim == 32 || a->dim == 64);
@@ -480,8 +463,6 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     p.pcode = a->p_code; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
     p.stats = a->search_stats; p.dbg = get_debug_timeline();
     p.N = (int)N; p.K = (int)K; p.num_tiles = (int)ceil_div(N, PM); p.se_bytes = 0; p.flags = a->flags;
-    p.stagger_ns = g_fwd_stagger_ns;
-    p.n_sm = sm_count();
     // PDL when the kernel enqueued immediately before is ours: the image build above, or (the caller vouches,
     // VQB_AFTER_ASSEMBLE) the table assembly
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);

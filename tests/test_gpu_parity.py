@@ -27,6 +27,15 @@ def _cuda(a):
     return None if a is None else torch.from_numpy(np.asarray(a).copy()).cuda()
 
 
+def _record(name, obj):
+    """index-mismatch counts and similar evidence of the size tests -> gpurun_out/ (copied to profiles/ per round)"""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "test_records.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **obj}, default=lambda o: o.item() if hasattr(o, "item") else str(o)) + "\n")
+
+
 def _table64(g, key="sd.learnable_table"):
     return O.assemble_table(g[key], g.get("sd.phn_attr.weight"), g.get("sd.proj_attr.weight"), g.get("sd.proj_attr.bias"))
 

@@ -13,7 +13,7 @@ import semi_tts_b200 as V  # noqa: E402
 from semi_tts_b200 import _lib, functional as VF  # noqa: E402
 
 
-def main():
+def main(quiet=False):
     N = int(os.environ.get("VQB_SWEEP_N", 1 << 20))
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     tf32_peak = peaks["bf16_tflops"] / 2.0          # kind::tf32 runs at half the dense bf16 rate
@@ -101,13 +101,15 @@ def main():
             bwd_bytes = N * (4 * D + 8)
             rec = {"N": N, "K": K, "D": D, "fwd_ms": fwd_ms, "search_tflops": flops / fwd_ms / 1e9,
                    "tensor_frac_of_tf32_peak": flops / fwd_ms / 1e9 / tf32_peak, "tf32_peak_tflops": tf32_peak,
+                   "tensor_frac_of_dense_bf16_peak": flops / fwd_ms / 1e9 / peaks["bf16_tflops"],
                    "fwd_gbs": fwd_bytes / fwd_ms / 1e6, "fwd_hbm_frac": fwd_bytes / fwd_ms / 1e6 / peaks["hbm_gbs"],
                    "reranked_rows": st[0], "full_scan_rows": st[1],
                    "scatter_ms": bwd_ms, "scatter_gbs": bwd_bytes / bwd_ms / 1e6,
                    "scatter_hbm_frac": bwd_bytes / bwd_ms / 1e6 / peaks["hbm_gbs"],
                    "frames_per_s_fwd_bwd": N / ((fwd_ms + bwd_ms) * 1e-3)}
             rec.update(ab)
-            print(json.dumps(rec), flush=True)
+            if not quiet:
+                print(json.dumps(rec), flush=True)
             out.append(rec)
     return out
 

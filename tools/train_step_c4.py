@@ -128,14 +128,14 @@ class Step:
             b["x"] = x.detach().clone()
             b["first_n"] = args[1] if len(args) > 1 else 0
             if x.requires_grad:
-                x.register_hook(lambda g: b.__setitem__("dx", g.detach().clone()))
+                x.register_hook(lambda g: b.__setitem__("dx", g.detach().clone()) if g is not None else None)
 
         def post(_m, _args, out):
             b["p_code"], b["new_latent"] = out[0].detach().clone(), out[1].detach().clone()
             if out[0].requires_grad:
-                out[0].register_hook(lambda g: b.__setitem__("g_p", g.detach().clone()))
+                out[0].register_hook(lambda g: b.__setitem__("g_p", g.detach().clone()) if g is not None else None)
             if out[1].requires_grad:
-                out[1].register_hook(lambda g: b.__setitem__("g_q", g.detach().clone()))
+                out[1].register_hook(lambda g: b.__setitem__("g_q", g.detach().clone()) if g is not None else None)
 
         return [cb.register_forward_pre_hook(pre), cb.register_forward_hook(post)]
 
@@ -180,9 +180,11 @@ class Step:
             if step > hp["unpair_speech_start_step"]:
                 total_loss = total_loss + hp["unpair_speech_weight"] * unpair_speech_loss                   # :232-233
         # BaseSolver.backward (src/solver.py:138-151)
-        total_loss.backward()
-        for h in hooks:
-            h.remove()
+        try:
+            total_loss.backward()
+        finally:
+            for h in hooks:
+                h.remove()
         if self.group is not None:
             self._allreduce_grads()
         grad_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
