@@ -532,7 +532,9 @@ static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtenso
     // launched with programmatic stream serialization: the prologue overlaps the predecessor's tail when that kernel
     // signals early (this library's forward does); the kernel waits (griddepcontrol.wait) before its first global read
     kernel_event_begin(s);
-    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(BP_THREADS), smem, s, tx, tg, td, p));
+    static const bool no_pdl = getenv("VQB_BWD_NO_PDL") != nullptr;        // developer A/B
+    if (no_pdl) kern<<<grid, BP_THREADS, smem, s>>>(tx, tg, td, p);
+    else VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(BP_THREADS), smem, s, tx, tg, td, p));
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_pcode_kernel");
     return VQB_OK;

@@ -50,11 +50,11 @@ struct PcP {
 
 #define VQB_PTL(tag) do { if (p.dbg && threadIdx.x == 0 && blockIdx.x == 0 && tl_n < 60) { p.dbg[tl_n++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00FFFFFFFFFFFFFFull); } } while (0)
 
-// exact fp32 score (log2 domain) of one code for one row, read from global memory: the rare re-rank path.
+// exact fp32 score of one code for one row, read from global memory: the rare re-rank path.
 // Same expression and fmaf order as vqb_fwd_simt.cu (dot_chunk + score_of).
 template <int D>
-__device__ __noinline__ float exact_s2(const float* __restrict__ xrow, const float* __restrict__ e, float xx, float b,
-                                       float mul, bool linear) {
+__device__ __noinline__ float exact_score(const float* __restrict__ xrow, const float* __restrict__ e, float xx, float b,
+                                          float tau, bool linear) {
     float dot = 0.f;
 #pragma unroll 4
     for (int c = 0; c < D / 4; ++c) {
@@ -62,8 +62,9 @@ __device__ __noinline__ float exact_s2(const float* __restrict__ xrow, const flo
         dot = fmaf(xv.x, w.x, dot); dot = fmaf(xv.y, w.y, dot);
         dot = fmaf(xv.z, w.z, dot); dot = fmaf(xv.w, w.w, dot);
     }
-    if (linear) return mul * -(dot + b);                             // mul = -log2(e): see the kernel
-    return mul * __fsub_rn(__fadd_rn(xx, b), 2.f * dot);
+    if (linear) return dot + b;                                      // F.linear                   (:190)
+    const float dist = __fsub_rn(__fadd_rn(xx, b), 2.f * dot);       // (|x|^2 + |e|^2) - 2 x.e   (:210-212)
+    return tau * (-dist);                                            // relu(temp) * -dist        (:115, :213)
 }
 
 template <int KP, int D, bool LINEAR>
@@ -205,39 +206,40 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // ---- scores (log2 domain) -> softmax -> p_code, argmax over p_code -----------------------------------------
         //   L2:     score = relu(temp) * -((|x|^2 + |e|^2) - 2 x.e)          (:115, :208-213)
         //   LINEAR: score = x.w + b                                           (:190)
-        // Both as s2 = mul * q with mul <= 0:  q = (|x|^2 + |e|^2) - 2 x.e  (L2: the reference's own association; 2 x.e is
-        // an exact scaling of the accumulator, so one fma rounds like the reference's subtraction) or q = -(x.w + b).
+        // Scores are kept in the natural domain, s = relu(temp) * -dist exactly as the exact kernel forms them (dist in the
+        // reference's own association; 2 x.e is an exact scaling of the accumulator, so one fma rounds like the reference's
+        // subtraction), and the exponent is taken of the exact difference (s - max) * log2(e): two scores that differ by
+        // one ulp stay different in p_code, so its arg-max agrees with the exact kernel's down to the last bit.
         const float tau = fmaxf(temp_raw, 0.f);
-        const float mul = (LINEAR ? -1.f : -tau) * LOG2E;
+        const float ntau = LINEAR ? 1.f : -tau;
         const float emax = *reinterpret_cast<const float*>(sHdr + 4);
-        const float u = pow2i(er) * pow2i(*reinterpret_cast<const int*>(sHdr)) * (LINEAR ? -1.f : -2.f);
+        const float u = pow2i(er) * pow2i(*reinterpret_cast<const int*>(sHdr)) * (LINEAR ? 1.f : -2.f);
         float v[KP];
         auto load_scores = [&]() -> float {
             tmem_ld_cols<KP>(tmem_base + lane_addr, v);
             float m = -INFINITY;
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-                const float q = fmaf(v[k], u, LINEAR ? -sBias[k] : __fadd_rn(xx, sBias[k]));
-                float s2 = mul * q;
-                if (k >= KP - 15) s2 = k < K ? s2 : -INFINITY;      // padded codes
-                v[k] = s2;
-                m = fmaxf(m, s2);
+                float sc = LINEAR ? fmaf(v[k], u, sBias[k]) : ntau * fmaf(v[k], u, __fadd_rn(xx, sBias[k]));
+                if (k >= KP - 15) sc = k < K ? sc : -INFINITY;      // padded codes
+                v[k] = sc;
+                m = fmaxf(m, sc);
             }
             return m;
         };
         float s4[4];
-        auto exp_scores = [&](float m) {            // v <- ex2(v - m): the maximum itself gives ex2(0) = 1 exactly
+        auto exp_scores = [&](float m) {            // v <- exp(v - m): the maximum itself gives ex2(0) = 1 exactly
             s4[0] = s4[1] = s4[2] = s4[3] = 0.f;
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 float e;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m));     // padded codes: ex2(-inf) = 0
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((v[k] - m) * LOG2E));     // padded codes: ex2(-inf) = 0
                 v[k] = e;
                 s4[k & 3] += e;
             }
         };
         float m1 = load_scores();
-        if (mul == 0.f) {                           // temp <= 0: uniform over the K real codes only
+        if (ntau == 0.f) {                          // temp <= 0: uniform over the K real codes only
 #pragma unroll
             for (int k = 0; k < KP; ++k) v[k] = k < K ? 0.f : -INFINITY;
             m1 = 0.f;
@@ -252,12 +254,12 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         {
             const float xn = sqrtf(xx);
             const float wd = LINEAR ? 1e-5f * xn * emax : 2e-5f * xn * emax + 2.4e-7f * (xn + emax) * (xn + emax);
-            const float win = fabsf(mul) * wd;
+            const float win = fabsf(ntau) * wd;
             float thr_e;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(thr_e) : "f"(-win));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(thr_e) : "f"(-win * LOG2E));
             thr_e *= 0.999f;
             unsigned long long cand = 0ull;
-            if (valid && mul != 0.f && ((s4[0] + s4[1]) + (s4[2] + s4[3])) - 1.f >= thr_e) {
+            if (valid && ntau != 0.f && ((s4[0] + s4[1]) + (s4[2] + s4[3])) - 1.f >= thr_e) {
 #pragma unroll
                 for (int k = 0; k < KP; ++k) cand |= v[k] >= thr_e ? (1ull << k) : 0ull;
             }
@@ -270,7 +272,7 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     const float* xrow = p.x + (size_t)(row0 + r) * D;
 #pragma unroll
                     for (int k = 0; k < KP; ++k)
-                        if ((cand >> k) & 1ull) v[k] = exact_s2<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], mul, LINEAR);
+                        if ((cand >> k) & 1ull) v[k] = exact_score<D>(xrow, p.table + (size_t)k * D, xx, sBias[k], tau, LINEAR);
                     m1 = -INFINITY;
 #pragma unroll
                     for (int k = 0; k < KP; ++k) m1 = fmaxf(m1, v[k]);

@@ -159,6 +159,12 @@ extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr,
     if (!has_attr) { n_attr = 0; dim_attr = 0; }
     if (operand_cache && small_table(n_codes, dim) && n_attr <= 63) {
         const size_t dyn = (size_t)(n_codes * n_attr + dim_attr * n_attr + dim_attr) * 4;      // <= 32.5 KB
+        static const bool no_pdl = getenv("VQB_ASM_NO_PDL") != nullptr;    // developer A/B
+        if (no_pdl)
+            assemble_small_kernel<<<1, 512, dyn, (cudaStream_t)stream>>>(
+                learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
+                enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache));
+        else
         VQB_CUDA(launch_pdl(assemble_small_kernel, dim3(1), dim3(512), dyn, (cudaStream_t)stream,
                             learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
                             enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache)));
