@@ -526,6 +526,91 @@ def run_ours(args, rank, world, local_rank):
         os._exit(0)
 
 
+def run_encode(args, rank, world, local_rank):
+    """BASELINE configs[4]: the encode path -- forward-only nearest-codeword search + gather under torch.no_grad() (what
+    VQVAE.speech_to_text does at src/vqvae.py:119 when the caller is bin/train_vqvae.py:343-346 / bin/gen_specgram.py) and the
+    text-side lookup inference(txt) (src/vqvae.py:147, bin/gen_specgram.py:95-108) -- over 10 000 synthetic utterances of 400
+    encoder frames (800 mel frames / time_reduce_factor 2), utterances sharded over the GPUs (dist.shard_bounds), batches of
+    64 utterances issued EAGERLY through the nn.Module exactly as the solver's loop would.  No collective on the data path;
+    the usage histogram is summed once at the end.  value = frames/s over all GPUs (device time, max over ranks)."""
+    import semi_tts_b200 as V
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    utts, frames, text_len, batch, ring_n = 10000, 400, 67, 64, 24      # 24 x 64 x 400 x 64 x 4 B = 157 MB > 126 MB L2
+    torch.manual_seed(0)
+    m = V.L2Embedding(K, False, **_codebook_kwargs()).to(dev).eval()
+    lo, hi = V.dist.shard_bounds(utts, rank, world)
+    n_batches = (hi - lo + batch - 1) // batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ring = [torch.randn(batch, frames, D, device=dev, generator=g) for _ in range(ring_n)]
+    txt = torch.randint(3, K - 1, (batch, text_len), device=dev, generator=g)
+    lib = V._lib.load()
+
+    def run(fused):
+        m.fused_search = fused
+        m.usage.reset()
+        done = 0
+        with torch.no_grad():
+            for b in range(n_batches):
+                nb = min(batch, hi - lo - done)
+                m(ring[b % ring_n][:nb])
+                m.inference(txt[:nb])
+                done += nb
+        return done
+
+    out = {}
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches = 0
+    for name, fused in (("parity_mode", False), ("fused_search", True)):
+        run(fused)                                              # warm-up pass
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.vqb_launch_count()
+        t0 = time.perf_counter()
+        e0.record()
+        done = run(fused)
+        e1.record()
+        host_s = time.perf_counter() - t0                       # time to ISSUE the work (no sync inside the loop)
+        torch.cuda.synchronize()
+        launches = int(lib.vqb_launch_count() - l0)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        ms = float(ms.item())
+        out[name] = {"ms": ms, "utts_per_s": utts / (ms * 1e-3), "frames_per_s": utts * frames / (ms * 1e-3),
+                     "host_issue_us_per_batch": host_s / n_batches * 1e6, "device_us_per_batch": ms * 1e3 / n_batches}
+        assert done == hi - lo
+    if world > 1:
+        V.dist.allreduce_usage(m)
+    total = m.usage.total()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        best = out["parity_mode"]
+        print(json.dumps({"metric": "vq_encode_frames_per_sec", "value": best["frames_per_s"], "unit": "frames/s", "n_gpus": world,
+                          "steps": n_batches, "warmup": n_batches, "ms_per_step": best["ms"] / n_batches,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "configs[4]: no-grad search + gather and inference(txt), %d utterances x %d frames, "
+                                                 "K=%d D=%d, batches of %d utterances issued eagerly through the nn.Module" % (
+                                                     utts, frames, K, D, batch),
+                                     "l2_policy": "ring of %d input batches (157 MB) > 126 MB L2" % ring_n,
+                                     "parallelism": "dp%d (utterances sharded, no data-path collective)" % world},
+                          "gpu_launches": launches, "usage_total": total, "usage_expected": utts * frames,
+                          "parity_mode": out["parity_mode"], "fused_search": out["fused_search"], "clocks": clocks}))
+    sys.stdout.flush()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -533,6 +618,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-3 roofline sweep sub-record (N = 1 only)")
+    ap.add_argument("--workload", default="train", choices=["train", "encode"],
+                    help="train: BASELINE configs[1] fwd+bwd (the bench line); encode: configs[4], no-grad search + gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -545,7 +632,10 @@ def main():
         run_reference(args, rank)
         sys.stdout.flush()
         return
-    run_ours(args, rank, world, local_rank)
+    if args.workload == "encode":
+        run_encode(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
     sys.stdout.flush()
 
 

@@ -191,7 +191,7 @@ typedef struct vqb_bwd_args {
     void*  workspace;
     size_t workspace_bytes;
     const vqb_bwd_tail* tail;    /* optional fused tail (see above); NULL = plain accumulate-into semantics.  Only
-                                    taken on the route vqb_backward_kernel_name() reports as "vqb_bwd_h2_kernel"
+                                    taken on the route vqb_backward_kernel_name() reports as "vqb_bwd_pcode_kernel"
                                     with VQB_SCORE_L2; otherwise vqb_backward fails with VQB_ERR_INVALID */
 } vqb_bwd_args;
 

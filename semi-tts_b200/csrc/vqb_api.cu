@@ -87,16 +87,7 @@ extern "C" __attribute__((visibility("default"))) void vqb_debug_set_timeline(vo
 
 // undocumented developer hook (A/B): force the software-pipelined x_lo of the streamed 3xTF32 search on (1) / off (0);
 // -1 = default (on unless VQB_SEARCH_NOPIPE is set)
-namespace vqb { void set_debug_search_pipe(int v); void set_debug_search_cs2(int v); void set_debug_search_mc2(int v); void set_debug_fwd_x3(int v); }
-// undocumented developer hook: 1 = run the parity-mode (p_code) tensor-core forward with three x slots (bias added by the
-// epilogue, staging sized by K) (experimental, not yet measured on hardware; off by default)
-extern "C" __attribute__((visibility("default"))) void vqb_debug_set_fwd_x3(int v) { vqb::set_debug_fwd_x3(v); }
-// undocumented developer hook: 1 = run the streamed 1xTF32 search (D >= 128) as clusters of two CTAs that share every codebook
-// piece through TMA multicast (experimental, not yet measured on hardware; off by default)
-extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_mc2(int v) { vqb::set_debug_search_mc2(v); }
-// undocumented developer hook: 1 = run the streamed 1xTF32 search (D <= 128) with two epilogue warpgroups that split every
-// chunk's columns (experimental, not yet measured on hardware; off by default)
-extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_cs2(int v) { vqb::set_debug_search_cs2(v); }
+namespace vqb { void set_debug_search_pipe(int v); }
 extern "C" __attribute__((visibility("default"))) void vqb_debug_set_search_pipe(int v) { vqb::set_debug_search_pipe(v); }
 
 namespace vqb {
@@ -130,10 +121,6 @@ extern "C" int vqb_device_count(void) {
     return ok;
 }
 
-// developer A/B switches (first GPU visit of round 2): VQB_FWD_OLD=1 / VQB_BWD_KERNEL=h2 select the second-generation kernels
-static bool fwd_old() { static const bool v = getenv("VQB_FWD_OLD") != nullptr; return v; }
-static bool bwd_old() { const char* pick = getenv("VQB_BWD_KERNEL"); return pick && strcmp(pick, "h2") == 0; }
-
 static int validate_fwd(const vqb_fwd_args* a) {
     if (!a || a->struct_size != sizeof(vqb_fwd_args)) return invalid("vqb_forward: struct_size mismatch (ABI %d)", VQB_ABI_VERSION);
     const bool l2 = a->flags & VQB_SCORE_L2, lin = a->flags & VQB_SCORE_LINEAR;
@@ -156,10 +143,8 @@ extern "C" int vqb_forward_workspace(const vqb_fwd_args* a, size_t* bytes) {
     int rc = validate_fwd(a);
     if (rc) return rc;
     if ((a->flags & VQB_TENSOR_CORES) && a->n_rows > 0) {
-        if (forward_pcode_supported(a) && !fwd_old()) { *bytes = forward_pcode_workspace(a); return VQB_OK; }
-        vqb_fwd_args b = *a;
-        b.operand_cache = nullptr;                     // the operand cache is in the fp16x2 image format
-        return forward_tensor_workspace(&b, bytes);
+        if (forward_pcode_supported(a)) { *bytes = forward_pcode_workspace(a); return VQB_OK; }
+        return forward_tensor_workspace(a, bytes);
     }
     return VQB_OK;
 }
@@ -169,20 +154,15 @@ extern "C" int vqb_forward(const vqb_fwd_args* a, void* stream) {
     if (rc) return rc;
     if ((rc = require_device())) return rc;
     if (a->n_rows == 0) return VQB_OK;
-    if ((a->flags & VQB_TENSOR_CORES) && forward_pcode_supported(a) && !fwd_old()) return launch_forward_pcode(a, (cudaStream_t)stream);
-    if ((a->flags & VQB_TENSOR_CORES) && forward_tensor_supported(a)) {
-        vqb_fwd_args b = *a;
-        b.operand_cache = nullptr;
-        b.flags &= ~VQB_AFTER_ASSEMBLE;
-        return launch_forward_tensor(&b, (cudaStream_t)stream);
-    }
+    if ((a->flags & VQB_TENSOR_CORES) && forward_pcode_supported(a)) return launch_forward_pcode(a, (cudaStream_t)stream);
+    if ((a->flags & VQB_TENSOR_CORES) && forward_tensor_supported(a)) return launch_forward_tensor(a, (cudaStream_t)stream);
     if (a->dim > 256) return invalid("vqb_forward: the exact-fp32 path supports D <= 256 (got %lld)", (long long)a->dim);
     return launch_forward_simt(a, (cudaStream_t)stream);
 }
 
 extern "C" const char* vqb_forward_kernel_name(const vqb_fwd_args* a) {
     if (validate_fwd(a) != VQB_OK) return "invalid";
-    if ((a->flags & VQB_TENSOR_CORES) && forward_pcode_supported(a) && !fwd_old()) return "vqb_fwd_pcode_kernel";
+    if ((a->flags & VQB_TENSOR_CORES) && forward_pcode_supported(a)) return "vqb_fwd_pcode_kernel";
     if ((a->flags & VQB_TENSOR_CORES) && forward_tensor_supported(a)) return "vqb_fwd_tc_kernel";
     return a->n_codes <= 64 ? "vqb_fwd_simt_small_kernel" : "vqb_fwd_simt_generic_kernel";
 }
@@ -205,10 +185,7 @@ extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
     int rc = validate_bwd(a);
     if (rc) return rc;
     if (a->n_rows > 0) {
-        size_t b2 = 0;
-        backward_h2_workspace(a, &b2);
-        const size_t b3 = backward_pcode_workspace(a);
-        *bytes = b3 > b2 ? b3 : b2;
+        *bytes = backward_pcode_workspace(a);
         if (!a->g_p && (a->flags & VQB_STOP_GRAD)) *bytes = scatter_workspace_bytes(a->n_rows, a->n_codes, a->dim);
         else if (backward_generic_needed(a)) *bytes = backward_generic_workspace(a);
     }
@@ -270,7 +247,7 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
         if (tl->world > 1 && (!tl->peer_bufs || tl->rank < 0 || tl->rank >= tl->world || tl->world > VQB_MAX_WORLD))
             return invalid("vqb_backward: tail.world=%d rank=%d needs peer_bufs and world <= %d", tl->world, tl->rank, VQB_MAX_WORLD);
     }
-    if (backward_pcode_supported(a)) return bwd_old() ? launch_backward_h2(a, s) : launch_backward_pcode(a, s);
+    if (backward_pcode_supported(a)) return launch_backward_pcode(a, s);
     if (backward_generic_needed(a)) return launch_backward_generic(a, s);
     return launch_backward_simt(a, s);
 }
@@ -278,7 +255,7 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
 extern "C" const char* vqb_backward_kernel_name(const vqb_bwd_args* a) {
     if (validate_bwd(a) != VQB_OK) return "invalid";
     if (!a->g_p && (a->flags & VQB_STOP_GRAD)) return "scatter_hist_kernel";
-    if (backward_pcode_supported(a)) return bwd_old() ? "vqb_bwd_h2_kernel" : "vqb_bwd_pcode_kernel";
+    if (backward_pcode_supported(a)) return "vqb_bwd_pcode_kernel";
     if (backward_generic_needed(a)) return "bwdg_dx_kernel";
     return "vqb_bwd_simt_kernel";
 }

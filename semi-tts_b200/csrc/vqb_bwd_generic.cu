@@ -11,7 +11,7 @@
 // tiled contraction writes it into C before the coefficient kernel runs (G = g_p + g_q @ T^T).  A learnable temperature
 // (temp < 0 in the config, src/embed.py:70-74) gets  d temp = sum Gs * (-dist) = (1/tau) sum Gs * log P  -- the two are
 // equal because -dist_k = (log P_k + logsumexp) / tau and sum_k Gs_k = 0 -- so no distance is recomputed here.
-// The small-codebook kernels (vqb_bwd_h2.cu, vqb_bwd_tc.cu, vqb_bwd_simt.cu) keep a row's K coefficients in registers
+// The small-codebook kernels (vqb_bwd_pc.cu, vqb_bwd_simt.cu) keep a row's K coefficients in registers
 // and the whole codebook in shared memory; here C[N,K] goes through HBM once (as the reference's own autograd graph
 // does) and the K x D contractions are shared-memory tiled.
 #include "vqb_common.cuh"

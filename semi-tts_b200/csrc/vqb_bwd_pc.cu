@@ -22,7 +22,7 @@
 // their raw TMA tiles.  Scales:  C'[r] = C[r] 2^-e_r (row maximum in [2^14, 2^15)),  x''[r] = x[r] 2^(e_r - t),
 // gq'' = gq 2^-g  with  t, g  per tile;  C @ E = D1 2^(e_r + gE),  x^T C = D2 2^t,  scatter = D3 2^g.
 // D2 / D3 are folded into registers once per tile (the scales differ from tile to tile); the K x D sums leave the CTA once,
-// as plain stores into a per-CTA partial record that the tail / reduce kernel (vqb_bwd_h2.cu) adds in a fixed order --
+// as plain stores into a per-CTA partial record that the tail / reduce kernel (vqb_bwd_tail.cu) adds in a fixed order --
 // no atomics, gradients are bit-reproducible.
 #include <cudaTypedefs.h>
 #include <limits.h>
@@ -38,7 +38,7 @@ constexpr int TR = 96;                  // rows per tile (a multiple of 16: GEMM
 constexpr int TBLK = TR * 128;          // one [TR rows][128 B] block = 12 KB
 constexpr int BP_THREADS = 128;
 constexpr int BP_KD = 64 * 64;
-constexpr int BP_PARTIAL_FLOATS = 2 * BP_KD + 64;   // same record as vqb_bwd_h2.cu: [0] d_score_w part, [1] scatter part (LINEAR) /
+constexpr int BP_PARTIAL_FLOATS = 2 * BP_KD + 64;   // same record as vqb_bwd_tail.cu: [0] d_score_w part, [1] scatter part (LINEAR) /
                                                     // transposed projected columns (L2 + fused tail), [2] column sums
 
 struct BwdPcP {
@@ -109,10 +109,6 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const uint32_t d1 = tmem_base, d2 = tmem_base + 64, d3 = tmem_base + 64 + KP;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
 
-    // PDL, other direction: this kernel is launched with programmatic stream serialization as well, so its prologue above
-    // (barriers, TMEM, descriptor prefetch) may run under the tail of whatever precedes it in the stream; nothing that
-    // kernel produced is touched before this point.  (A predecessor that never signals simply completes first.)
-    pdl_wait();
     const float tau = L2 ? fmaxf(__ldg(p.temp), 0.f) : 1.f;
     const float cmul = L2 ? -tau : 1.f;
     const int gE = __ldg(reinterpret_cast<const int*>(p.img + IMG_HDR));
@@ -529,12 +525,12 @@ static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtenso
     auto kern = vqb_bwd_pcode_kernel<KP, L2>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    // launched with programmatic stream serialization: the prologue overlaps the predecessor's tail when that kernel
-    // signals early (this library's forward does); the kernel waits (griddepcontrol.wait) before its first global read
+    // a plain stream-ordered launch: what precedes the backward in the stream (the producer of g_p / g_q, possibly a copy)
+    // is not ours to overlap -- and chaining it behind this library's own forward with programmatic serialization was
+    // measured SLOWER (61.8 vs 57.9 us per step at config 2, profiles/r2_pdl_ab.txt).  The kernel still releases its own
+    // successor early (the fused tail).
     kernel_event_begin(s);
-    static const bool no_pdl = getenv("VQB_BWD_NO_PDL") != nullptr;        // developer A/B
-    if (no_pdl) kern<<<grid, BP_THREADS, smem, s>>>(tx, tg, td, p);
-    else VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(BP_THREADS), smem, s, tx, tg, td, p));
+    kern<<<grid, BP_THREADS, smem, s>>>(tx, tg, td, p);
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_pcode_kernel");
     return VQB_OK;

@@ -85,11 +85,6 @@ __device__ __forceinline__ float tf32_rn(float v) {      // round to tf32 (10-bi
 }
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// operand cache layout (vqb_operand_cache_bytes): fwd_hi [Kp][D+32] | fwd_lo [Kp][D] | bwd_hi [Kp][D+32] | bwd_lo [Kp][D]
-static inline int64_t cache_rows(int64_t K) { return (K + 127) / 128 * 128; }
-static inline size_t cache_hi_bytes(int64_t K, int64_t D) { return ((size_t)cache_rows(K) * (D + 32) * 4 + 255) & ~(size_t)255; }
-static inline size_t cache_lo_bytes(int64_t K, int64_t D) { return ((size_t)cache_rows(K) * D * 4 + 255) & ~(size_t)255; }
-
 // entry points implemented in the individual .cu files (host side, return VQB_* codes)
 int launch_forward_simt(const vqb_fwd_args* a, cudaStream_t s);
 int launch_backward_simt(const vqb_bwd_args* a, cudaStream_t s);
@@ -99,11 +94,6 @@ size_t scatter_workspace_bytes(int64_t n, int64_t K, int64_t D);
 bool forward_tensor_supported(const vqb_fwd_args* a);
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
 int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
-// fp16x2 generation of the parity-mode backward (vqb_bwd_h2.cu); VQB_BWD_KERNEL=tf32 in the environment selects the
-// first-generation tf32 kernel instead (kept as a comparator)
-bool backward_h2_supported(const vqb_bwd_args* a);
-int backward_h2_workspace(const vqb_bwd_args* a, size_t* bytes);
-int launch_backward_h2(const vqb_bwd_args* a, cudaStream_t s);
 size_t exchange_bytes(int64_t n_flat, int world);
 int launch_bwd_reduce(const vqb_bwd_args* a, const float* partial, int grid, cudaStream_t s, unsigned long long* dbg);
 // third generation of the parity-mode kernels (vqb_fwd_pc.cu, vqb_bwd_pc.cu): one tile per CTA at a time, several CTAs per SM

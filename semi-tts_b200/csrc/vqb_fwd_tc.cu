@@ -1,18 +1,14 @@
-// Forward of the quantizer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), two epilogues:
-//
-//   SEARCH  (fused mode, no p_code)   nearest-codeword search + exact re-rank + gather + straight-through;
-//           the N x K distance matrix never leaves TMEM.  Replaces neg_batch_l2 + argmax + F.embedding +
-//           straight-through of src/embed.py:208-213, :130, :134, :145.
-//   PCODE   (parity mode, K <= 64)    scores -> softmax -> p_code, argmax over p_code, gather, straight-through,
-//           usage histogram: the whole of L2Embedding.forward (src/embed.py:105-147) or
-//           SeperateEmbedding.forward (:187-205, LINEAR score) in one kernel.
+// Fused-mode forward of the quantizer (no p_code: the large-codebook search of BASELINE config 3) on the 5th-generation
+// tensor cores (tcgen05 + TMEM + TMA): nearest-codeword search + exact re-rank + gather + straight-through; the N x K
+// distance matrix never leaves TMEM.  Replaces neg_batch_l2 + argmax + F.embedding + straight-through of
+// src/embed.py:208-213, :130, :134, :145.  (The parity-mode forward, where p_code is part of the result, is vqb_fwd_pc.cu.)
 //
 // Anatomy (one persistent CTA per SM, 6 warps, warp-specialised):
 //   warp 0  TMA producer   x tile [128 rows][D] fp32 (double-buffered when it fits); codebook K-blocks
 //                          [BN codes][32 floats]: resident in shared memory when the codebook is one chunk,
 //                          otherwise streamed through a ring
 //   warp 1  MMA issuer     tcgen05.mma kind::tf32, M=128, N=BN, K=8; accumulators double-buffered in TMEM
-//   warps 2-5 epilogue     tcgen05.ld 32x32b: thread = row, so soft-max / arg-max / top-k are thread-local
+//   warps 2-5 epilogue     tcgen05.ld 32x32b: thread = row, so the running minimum / candidate list are thread-local
 //
 // Precision.  kind::tf32 reads the top 19 bits of each fp32 operand.  PASSES = 3 ("3xTF32") adds the two
 // cross terms with the operands' low parts: x = x_hi + x_lo (x_hi = hardware truncation of the raw tile, x_lo
@@ -39,7 +35,6 @@ struct TcP {
     const float* bias;         // [K]    |e|^2 (L2) or b (LINEAR)
     const float* temp;         // [1]
     const float* emax;         // [1]    max_k |e_k|
-    float* pcode;
     long long* idx;
     float* q;
     unsigned long long* hist;
@@ -158,41 +153,20 @@ __device__ __forceinline__ float prep_tile(const uint8_t* sX, uint8_t* sXlo, uin
 // NOAUG (streamed 1xTF32 search at D = 256 only): the |e|^2 term is not folded into the GEMM as an extra K-step but
 // added by the epilogue from a per-chunk copy of enorm in shared memory; this frees the 16 KB A block and one piece
 // per chunk, which buys a fifth ring slot where shared memory is otherwise full.
-// CS = 2 (experimental, streamed 1xTF32 search, selected only by vqb_debug_set_search_cs2 / VQB_SEARCH_CS2): a second
-// epilogue warpgroup takes the other half of every chunk's columns (same TMEM lanes, i.e. the same rows) with its own
-// running minimum and candidate list; the two are merged after the last chunk with the threshold of the smaller minimum
-// (each list is a superset of what that threshold admits from its columns, so the re-rank sees every admissible code).
-// MC = 2 (experimental, streamed 1xTF32 search, selected only by vqb_debug_set_search_mc2): launched as thread-block
-// clusters of two.  CTA (piece & 1) of the pair loads a codebook piece ONCE with TMA multicast into the same ring slot of
-// both CTAs; each CTA arms its own b_full with the full piece size; b_empty counts the tcgen05.commit of BOTH MMA warps
-// (multicast arrive), so a slot is refilled only when both consumers have retired it.  Both CTAs run the same number of
-// tiles (a tile index >= num_tiles is an empty tile: TMA zero-fills its load and clips its store).  Every SM then requests
-// half of the codebook bytes for the same MMA work -- the streamed search at D = 256 is bound by the bytes in flight.
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG, bool NOAUG, int CS, int MC>
-__global__ void __launch_bounds__(64 + 128 * NWG * CS, 1)
+// (Measured and dropped in round 2, profiles/r2_search_experiments.txt: a column-split second epilogue warpgroup, clusters
+// of two with the codebook pieces multicast, and the one-pass kernel below K = 1024 -- none was faster.)
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG>
+__global__ void __launch_bounds__(192, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
     constexpr int PIECES = (PASSES == 3 ? 2 * KB : KB) + (NOAUG ? 0 : 1);      // per chunk: hi/lo per K-block + the bias block
-    // NOAUG with PCODE (experimental, vqb_debug_set_fwd_x3): the bias is added by the epilogue from a 64-float copy in shared
-    // memory, which frees the 16 KB A block and the bias piece; with the p_code staging sized by K instead of 64 that
-    // leaves room for a THIRD x slot, so the load of a CTA's third tile no longer waits for its first tile to drain
-    // (profiles/r1e_timeline_fwd.txt: 3.5 us of x_full wait on the third tile)
-    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT && !PCODE && NWG == 1) || (PCODE && RESIDENT && PASSES == 3),
-                  "NOAUG: streamed 1xTF32 search, or the resident p_code kernel");
+    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT), "NOAUG: streamed 1xTF32 search");
     constexpr int TMEM_COLS = 2 * BN;
     constexpr int CAP = NOAUG ? 15 : 16;                          // per-row candidate list capacity (SEARCH); 15: fits 227 KB
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
-    static_assert(!PCODE || BN == 64, "the p_code epilogue keeps one 64-column accumulator in registers");
-    // NWG epilogue warpgroups work on alternate tiles (tile t -> group t % NWG, x slot t % XS, TMEM buffer t & 1,
-    // its own p_code staging); with NWG = 2 the x_lo tile is single-buffered (XLS = 1) and handed back by the
-    // MMA warp through xlo_free as soon as the third MMA pass of a tile has been issued.
-    static_assert(NWG == 1 || (PCODE && XS >= 2 && RESIDENT && PASSES == 3), "two warpgroups: p_code mode only");
-    static_assert(CS == 1 || (CS == 2 && !PCODE && !RESIDENT && PASSES == 1 && !NOAUG && NWG == 1), "column split: streamed 1xTF32 search only");
-    static_assert(MC == 1 || (MC == 2 && !PCODE && !RESIDENT && PASSES == 1 && NWG == 1 && CS == 1), "multicast pair: streamed 1xTF32 search only");
-    constexpr int NTHREADS = 64 + 128 * NWG * CS;
-    constexpr int XLS = NWG == 2 ? 1 : XS;                        // x_lo slots
-    constexpr int SP_FLOATS = BM * 65;
+    constexpr int NTHREADS = 192;
+    constexpr int XLS = XS;                                       // x_lo slots
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
@@ -200,10 +174,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sXlo = sX + (size_t)XS * KB * XBLK;                               // [XS][KB][16 KB]  (PASSES == 3)
     uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0);        // [16 KB] A block [1,1,1,0,...]
     uint8_t* sB = sAug + (NOAUG ? 0 : XBLK);                                   // [BS][PIECE]
-    float* sP = reinterpret_cast<float*>(sB + (size_t)BS * PIECE);             // [128][65] p_code staging (PCODE)
-    uint2* sCand = reinterpret_cast<uint2*>(sP);                               // [CAP][128] (value, code)  (SEARCH)
-    const int sp_floats = (PCODE && NOAUG) ? BM * (p.K | 1) : SP_FLOATS;      // staging of one warpgroup
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP) + (PCODE ? NWG * sp_floats * 4 : CS * CAP * BM * 8));
+    uint2* sCand = reinterpret_cast<uint2*>(sB + (size_t)BS * PIECE);          // [CAP][128] (value, code)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sCand) + CAP * BM * 8);
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
     uint64_t* xlo_full = x_empty + XS;
@@ -224,8 +196,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (PASSES == 3) tma_prefetch_desc(&tm_lo);
         tma_prefetch_desc(&tm_q);
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
-        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], MC); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * CS); }
+        for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
         mbar_init(xlo_free, 1);
         fence_barrier_init();
     }
@@ -241,9 +213,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    if constexpr (MC == 2) cluster_sync_all();                     // the peer's barriers are initialised before anything is multicast
-    // one past the last tile index of this CTA; MC == 2: every CTA runs ceil(num_tiles / grid) tiles, the surplus ones empty
-    const int tile_end = MC == 2 ? (int)(blockIdx.x + ((p.num_tiles + gridDim.x - 1) / gridDim.x) * gridDim.x) : p.num_tiles;
+    const int tile_end = p.num_tiles;
     const uint32_t tmem_base = *tmem_slot;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[122] = globaltimer_ns();
     constexpr uint32_t IDESC = umma_idesc(2u, BM, BN);
@@ -275,10 +245,6 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         mbar_arrive_expect_tx(&b_full[bs], PIECE);
                         const bool is_lo = PASSES == 3 && j < 2 * KB && (j & 1);
                         const int kb = PASSES == 3 ? (j >> 1) : j;                 // the bias block has kb == KB
-                        if constexpr (MC == 2) {
-                            if ((b_it & 1u) == cluster_ctarank())
-                                tma_load_2d_mc(sB + (size_t)bs * PIECE, &tm_hi, kb * 32, chunk * BN, &b_full[bs], (uint16_t)3);
-                        } else
                         tma_load_2d(sB + (size_t)bs * PIECE, is_lo ? &tm_lo : &tm_hi, kb * 32, chunk * BN, &b_full[bs]);
                         ++b_it;
                     }
@@ -293,7 +259,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
                 const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
                 const uint8_t* xt = sX + (size_t)xs * KB * XBLK;
-                const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
+                const uint32_t xls = xs, xlph = xph;
                 const uint8_t* xlt = sXlo + (size_t)xls * KB * XBLK;
                 mbar_wait(&x_full[xs], xph);
                 if (PASSES == 3 && !RESIDENT) mbar_wait(&xlo_full[xls], xlph);
@@ -336,7 +302,6 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a + 2 * k, b + 2 * k, IDESC, true);
                             }
-                            if (NWG == 2) umma_commit(xlo_free);    // the single x_lo tile may be rewritten
                         }
                     } else {
                         for (int j = 0; j < PIECES; ++j) {
@@ -359,8 +324,6 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                     for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + 2 * k, b + 2 * k, IDESC, true);
                                 }
                             }
-                            if constexpr (MC == 2) umma_commit_mc(&b_empty[bs], (uint16_t)3);   // ... in both CTAs of the pair
-                            else
                             umma_commit(&b_empty[bs]);              // frees the ring slot when these MMAs retire
                             ++b_it;
                         }
@@ -375,16 +338,14 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // =============================== epilogue (thread = row) ==========================================
         const int q4 = warp & 3;                                    // TMEM lane quadrant this warp may read
         const int r = q4 * 32 + lane;                               // row within the tile == TMEM lane
-        const int wg = CS == 2 ? 0 : (warp - 2) >> 2;               // epilogue warpgroup for the tile rotation (0 .. NWG-1)
-        const int cg = CS == 2 ? (warp - 2) >> 2 : 0;               // column group of this warpgroup (CS == 2)
+        constexpr int wg = 0, cg = 0;                               // (one epilogue warpgroup; names kept for the timeline macro)
         const int et = ((warp - 2) & 3) * 32 + lane;                // 0..127 within the warpgroup
         const uint32_t bar_id = 1 + wg;                             // named barrier of this warpgroup
-        float* sPg = sP + (PCODE ? wg * sp_floats : 0);
         const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
         const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
-        const float emax = PCODE ? 0.f : __ldg(p.emax);
+        const float emax = __ldg(p.emax);
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-        uint32_t x_it = wg, c_it = wg;                              // tile counter of this warpgroup (c_it: chunks)
+        uint32_t x_it = 0, c_it = 0;                                // tile / chunk counters
         float se_acc = 0.f;
         int tl_n = 0;
         VQB_TL(1);
@@ -397,21 +358,15 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // piece of tile t, the ring frees slots only as the MMA consumes them, and the MMA can run two chunks ahead of
         // the epilogue (two TMEM buffers) -- with more chunks the wait for x(t+1) at the top of tile t would close a
         // cycle (measured: it does; B200, K = 1024).  Measured at N = 2^20, K = 256, D = 64: 0.719 -> 0.658 ms.
-        float* sBias = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);   // [64] (PCODE && NOAUG)
-        if constexpr (PCODE && NOAUG) {
-            // both warpgroups write the same values; each waits for its own copy pass only
-            if (et < 64) sBias[et] = et < p.K ? __ldg(p.bias + et) : (linear ? -1e30f : 1e30f);
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        }
-        constexpr bool PIPE_OK = !PCODE && !RESIDENT && PASSES == 3 && XS == 2 && NWG == 1;
+        constexpr bool PIPE_OK = !RESIDENT && PASSES == 3 && XS == 2;
         const bool pipe = PIPE_OK && p.num_chunks <= 2 && (p.flags & 0x40000000u) != 0;
         float xx_next = 0.f;
         if constexpr (PIPE_OK) {
             if (pipe && (int)blockIdx.x < p.num_tiles) xx_next = prep_tile<KB, XS>(sX, sXlo, x_full, xlo_full, r, lane, x_it);
         }
-        for (int tile = blockIdx.x + wg * gridDim.x; tile < tile_end; tile += NWG * gridDim.x) {
+        for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
             const uint32_t xs = x_it % XS, xph = (x_it / XS) & 1;
-            const uint32_t xls = NWG == 2 ? 0 : xs, xlph = NWG == 2 ? (x_it & 1) : xph;
+            const uint32_t xls = xs;
             uint8_t* sXt = sX + (size_t)xs * KB * XBLK;
             uint8_t* sXl = sXlo + (size_t)xls * KB * XBLK;
             VQB_TL(2);
@@ -430,7 +385,6 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int rows = min(BM, p.N - row0);
             const bool valid = r < rows;
             // |x|^2 in the exact kernel's fmaf order; x_lo = x - trunc_tf32(x) for the third MMA pass
-            if (NWG == 2) mbar_wait(xlo_free, xlph ^ 1);            // previous tile's third MMA pass has read x_lo
             float xx = 0.f;
             if (PIPE_OK && prepped) xx = xx_pipe;
 #pragma unroll 1
@@ -462,71 +416,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             VQB_TL(4);
 
             int best = 0;
-            if (PCODE) {
-                // ---------------- scores -> softmax -> p_code, argmax over p_code ----------------------------
-                const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
-                mbar_wait(&t_full[buf], tph);
-                tcgen05_fence_after();
-                VQB_TL(5);
-                float v[64];
-                {
-                    float t0[32], t1[32];                            // both halves in flight, one wait
-                    tmem_ld_32x32_nowait(tmem_base + lane_addr + buf * BN, t0);
-                    tmem_ld_32x32_nowait(tmem_base + lane_addr + buf * BN + 32, t1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] = t0[j]; v[32 + j] = t1[j]; }
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&t_empty[buf]);          // TMEM buffer free: next tile's MMA may start
-                c_it += NWG;
-                // scores in the log2 domain: s2 = log2(e) * score, so that exp(score - max) = ex2(s2 - max2)
-                //   L2:     score = relu(temp) * -(|x|^2 + acc),  acc = |e|^2 - 2 x.e     (:115, :208-213)
-                //   LINEAR: score = acc = x.w + b                                          (:190)
-                const float LOG2E = 1.4426950408889634f;
-                const float mul = linear ? LOG2E : -tau * LOG2E;
-                const float add = linear ? 0.f : xx;
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-                for (int k = 0; k < 64; ++k) {
-                    // NOAUG: acc = -2 x.e (or x.w) only; (|x|^2 + |e|^2) - 2 x.e in the reference's own association (:210-212)
-                    const float s2 = (PCODE && NOAUG) ? mul * ((add + sBias[k]) + v[k])
-                                                      : mul * (add + v[k]);            // padded codes: acc = +-1e30 -> s2 = -huge
-                    v[k] = s2;
-                    m4[k & 3] = fmaxf(m4[k & 3], s2);
-                }
-                if (mul == 0.f) {                                   // temp <= 0: uniform over the K real codes only
-#pragma unroll
-                    for (int k = 0; k < 64; ++k) if (k >= p.K) v[k] = -INFINITY;
-                }
-                const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                // four interleaved chains (k mod 4) for the sum and for the first-index arg-max of exp(score - max)
-                float s4[4] = {0.f, 0.f, 0.f, 0.f};
-                float bv4[4] = {-1.f, -1.f, -1.f, -1.f};
-                int bi4[4] = {0, 1, 2, 3};
-#pragma unroll
-                for (int k = 0; k < 64; ++k) {
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[k] - m));     // padded codes: ex2(-huge) = 0
-                    v[k] = e;
-                    s4[k & 3] += e;
-                    if (e > bv4[k & 3]) { bv4[k & 3] = e; bi4[k & 3] = k; }
-                }
-                // argmax over p_code = e * inv (monotone in e), first index on ties (:130)
-                float bv = bv4[0];
-                best = bi4[0];
-#pragma unroll
-                for (int j = 1; j < 4; ++j)
-                    if (bv4[j] > bv || (bv4[j] == bv && bi4[j] < best)) { bv = bv4[j]; best = bi4[j]; }
-                const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-                // staging row stride: K itself when K is odd (conflict-free and contiguous -> one bulk store per
-                // tile), K+1 when K is even (conflict-free; copied out by the threads)
-                float* prow = sPg + r * (p.K | 1);
-#pragma unroll
-                for (int k = 0; k < 64; ++k)
-                    if (k < p.K) prow[k] = v[k] * inv;              // softmax (:127)
-            } else {
+            {
                 // ---------------- running minimum + candidate list over the codebook chunks ----------------
                 // |approx - exact| <= eps for every code of this row (see header), so the exact arg-min lies
                 // among the codes whose approximate value is within W = 2 eps of the approximate minimum.
@@ -538,7 +428,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 float mn = INFINITY, thr = INFINITY;
                 int cnt = 0;
                 bool overflow = false;
-                uint2* sCandG = sCand + (CS == 2 ? cg * CAP * BM : 0);     // this warpgroup's list
+                uint2* sCandG = sCand;
                 // NOAUG: |e|^2 of the chunk's codes, staged by the row threads themselves (thread et <-> code), double-buffered;
                 // the value of the next chunk is fetched one iteration ahead.  Codes beyond K get +1e30 (never the minimum).
                 float* sEn = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);     // [2][BN]
@@ -555,7 +445,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     mbar_wait(&t_full[buf], tph);
                     tcgen05_fence_after();
 #pragma unroll 1
-                    for (int c = cg * (BN / 32 / CS); c < (cg + 1) * (BN / 32 / CS); ++c) {
+                    for (int c = 0; c < BN / 32; ++c) {
                         float v[32];
                         tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
@@ -596,33 +486,13 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                     ++c_it;
                 }
-                int cnt_o = 0;                                      // entries of the other warpgroup's list (CS == 2)
-                if constexpr (CS == 2) {
-                    // merge the two column groups: group 1 publishes (minimum, count | overflow); group 0 tightens the
-                    // window to the smaller minimum and re-ranks over both lists; group 1 goes on to the next tile once
-                    // group 0 has finished reading its list (barrier 4)
-                    float* sMn = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);   // [BM]
-                    int* sCo = reinterpret_cast<int*>(sMn + BM);                                               // [BM]
-                    if (cg == 1) { sMn[r] = mn; sCo[r] = cnt | (overflow ? 0x10000 : 0); }
-                    asm volatile("bar.sync 3, 256;" ::: "memory");
-                    if (cg == 1) {
-                        asm volatile("bar.sync 4, 256;" ::: "memory");
-                        x_it += NWG;
-                        continue;
-                    }
-                    mn = fminf(mn, sMn[r]);
-                    thr = mn + W;
-                    const int co = sCo[r];
-                    cnt_o = co & 0xFFFF;
-                    overflow = overflow || (co & 0x10000) != 0;
-                }
-                const int ctot = cnt + cnt_o;
+                const int ctot = cnt;
                 // survivors of the final window -> exact fp32 re-rank (same expression / fmaf order as the SIMT kernel)
                 int ncand = 0;
                 float bs_ = -INFINITY;
                 int first = 0;
                 for (int c2 = 0; c2 < ctot; ++c2) {
-                    const uint2 e = sCand[((CS == 2 && c2 >= cnt) ? CAP + (c2 - cnt) : c2) * BM + r];
+                    const uint2 e = sCand[c2 * BM + r];
                     if (__uint_as_float(e.x) <= thr) { if (ncand == 0) first = (int)e.y; ++ncand; }
                 }
                 const bool full_scan = valid && overflow;
@@ -635,7 +505,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     }
                 } else if (rerank) {
                     for (int c2 = 0; c2 < ctot; ++c2) {
-                        const uint2 e = sCand[((CS == 2 && c2 >= cnt) ? CAP + (c2 - cnt) : c2) * BM + r];
+                        const uint2 e = sCand[c2 * BM + r];
                         if (__uint_as_float(e.x) <= thr) {
                             const int k = (int)e.y;
                             const float sc = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
@@ -650,14 +520,13 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         if (m2) atomicAdd(p.stats + 1, (unsigned)__popc(m2));
                     }
                 }
-                if constexpr (CS == 2) asm volatile("bar.sync 4, 256;" ::: "memory");   // group 1 may reuse its list / merge words
             }
 
             VQB_TL(6);
             // ---- gather + straight-through, in place over the x tile -------------------------------------------
             // Coalesced mapping: 16 consecutive threads handle the 16 sixteen-byte chunks of one row, so the
             // codeword reads (all chunks of ONE code row) and the tile accesses are free of bank conflicts.
-            int* sIdxG = reinterpret_cast<int*>(tmem_slot + 4) + wg * BM;
+            int* sIdxG = reinterpret_cast<int*>(tmem_slot + 4);
             sIdxG[r] = valid ? best : -1;
             if (valid) p.idx[row0 + r] = best;
             VQB_TL(11);
@@ -728,35 +597,14 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 // new_latent tile: TMA store straight from the swizzled tile (rows beyond N are clipped by TMA)
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) tma_store_2d(&tm_q, sXt + kb * XBLK, kb * 32, row0);
-                if (PCODE && (p.K & 1)) {
-                    const uint32_t bytes = (uint32_t)(rows * p.K * 4) & ~15u;
-                    if (bytes) bulk_store_1d(p.pcode + (size_t)row0 * p.K, sPg, bytes);
-                }
                 tma_store_commit();
-            }
-            if (PCODE) {
-                float* dst = p.pcode + (size_t)row0 * p.K;
-                const int n = rows * p.K;
-                if (p.K & 1) {
-                    const int done = (int)(((uint32_t)(n * 4) & ~15u) >> 2);   // < 16 bytes of a ragged last tile
-                    if (et < n - done) dst[done + et] = sPg[done + et];
-                } else {
-                    const int KP = p.K | 1;
-                    int rr = et / p.K, k = et - rr * p.K;           // running (row, code) of element i
-                    const int step_r = 128 / p.K, step_k = 128 - step_r * p.K;
-                    for (int i = et; i < n; i += 128) {
-                        __stcs(dst + i, sPg[rr * KP + k]);
-                        rr += step_r; k += step_k;
-                        if (k >= p.K) { k -= p.K; ++rr; }
-                    }
-                }
             }
             VQB_TL(8);
             if (et == 0) tma_store_wait_read();                     // shared memory may be overwritten from here on
             VQB_TL(9);
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // sP / x tile fully drained before reuse
             if (lane == 0) mbar_arrive(&x_empty[xs]);               // the x slot may be refilled by TMA
-            x_it += NWG;
+            ++x_it;
         }
         if (p.sqerr) {
             se_acc = warp_sum(se_acc);
@@ -769,7 +617,6 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ---- teardown ----------------------------------------------------------------------------------------
     tcgen05_fence_before();
     __syncthreads();
-    if constexpr (MC == 2) cluster_sync_all();                     // no CTA leaves while its peer may still signal its barriers
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[123] = globaltimer_ns();
 }
@@ -809,35 +656,22 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 static int g_search_pipe = -1;                 // -1: default (on unless VQB_SEARCH_NOPIPE); 0 / 1: forced (vqb_debug_set_search_pipe)
 void set_debug_search_pipe(int v) { g_search_pipe = v; }
-// experimental kernel variants, all OFF unless a developer asks for them: -1 = follow the environment variable named
-// below (unset = off), 0 / 1 = forced by the matching vqb_debug_set_* hook
-static int g_fwd_x3 = -1;                      // VQB_FWD_X3: three-slot p_code forward
-void set_debug_fwd_x3(int v) { g_fwd_x3 = v; }
-static int g_search_mc2 = -1;                  // VQB_SEARCH_MC2: cluster-of-2 multicast codebook stream
-void set_debug_search_mc2(int v) { g_search_mc2 = v; }
-static int g_search_cs2 = -1;                  // VQB_SEARCH_CS2: column-split epilogue of the streamed 1xTF32 search
-void set_debug_search_cs2(int v) { g_search_cs2 = v; }
-static bool experiment_on(int forced, const char* env) { return forced < 0 ? getenv(env) != nullptr : forced > 0; }
 static unsigned long long* g_timeline = nullptr;
 void set_debug_timeline(void* p) { g_timeline = reinterpret_cast<unsigned long long*>(p); }
 unsigned long long* get_debug_timeline() { return g_timeline; }
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static int64_t pad_codes(int64_t K, int64_t bn) { return (K + bn - 1) / bn * bn; }
-static size_t hi_bytes(int64_t K, int64_t D) { return cache_hi_bytes(K, D); }
-static size_t lo_bytes(int64_t K, int64_t D) { return cache_lo_bytes(K, D); }
+// tf32 hi / lo operand copies of the codebook (workspace): hi [Kpad][D + 32] (the last block carries the bias), lo [Kpad][D]
+static size_t hi_bytes(int64_t K, int64_t D) { return ((size_t)pad_codes(K, 128) * (D + 32) * 4 + 255) & ~(size_t)255; }
+static size_t lo_bytes(int64_t K, int64_t D) { return ((size_t)pad_codes(K, 128) * D * 4 + 255) & ~(size_t)255; }
 
 // which kernel configuration serves this call (0 = none: use the exact SIMT path)
-enum TcMode { TC_NONE = 0, TC_PCODE, TC_SEARCH3, TC_SEARCH1 };
+enum TcMode { TC_NONE = 0, TC_SEARCH3, TC_SEARCH1 };
 static TcMode tc_mode(const vqb_fwd_args* a) {
     const int64_t K = a->n_codes, D = a->dim;
-    if (a->p_code) return (K <= 64 && (D == 32 || D == 64)) ? TC_PCODE : TC_NONE;
+    if (a->p_code) return TC_NONE;                               // parity mode: vqb_fwd_pc.cu
     if (!(a->flags & VQB_SCORE_L2)) return TC_NONE;
     if (D != 32 && D != 64 && D != 128 && D != 256) return TC_NONE;
-    // developer A/B (VQB_SEARCH_MODE=1): the streamed 1xTF32 search with its wider re-rank window also below K = 1024 --
-    // extrapolating the K = 4096 row of the config-3 sweep it should beat the three-pass kernel at D = 64 (unmeasured)
-    static const char* force = getenv("VQB_SEARCH_MODE");
-    if (force && force[0] == '1' && K > 128) return TC_SEARCH1;
     if (K <= 1024 && D <= 128) return TC_SEARCH3;
     return TC_SEARCH1;
 }
@@ -845,44 +679,22 @@ static TcMode tc_mode(const vqb_fwd_args* a) {
 bool forward_tensor_supported(const vqb_fwd_args* a) { return tc_mode(a) != TC_NONE; }
 
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
-    const TcMode mode = tc_mode(a);
-    const bool cached = a->operand_cache && (a->flags & VQB_SCORE_L2) && mode == TC_PCODE;
-    *bytes = mode == TC_NONE ? 0 : (cached ? 0 : hi_bytes(a->n_codes, a->dim) + lo_bytes(a->n_codes, a->dim)) + (mode == TC_PCODE ? 0 : 256);
+    *bytes = tc_mode(a) == TC_NONE ? 0 : hi_bytes(a->n_codes, a->dim) + lo_bytes(a->n_codes, a->dim) + 256;
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool PCODE, int NWG = 1, bool NOAUG = false, int CS = 1, int MC = 1>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG = false>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
-                     cudaStream_t s, bool pdl) {
-    constexpr int XLS = NWG == 2 ? 1 : XS;
-    const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
-                        (size_t)BS * BN * 128 + (PCODE ? NWG * BM * ((PCODE && NOAUG) ? (p.K | 1) : 65) * 4 : CS * (NOAUG ? 15 : 16) * BM * 8) + 1024 + 256 + 2 * BM * 4 +
-                        ((NOAUG || CS == 2) ? 2 * BN * 4 : 0);
+                     cudaStream_t s) {
+    const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
+                        (size_t)BS * BN * 128 + (NOAUG ? 15 : 16) * BM * 8 + 1024 + 256 + 2 * BM * 4 + (NOAUG ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, PCODE, NWG, NOAUG, CS, MC>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, NOAUG>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    if (MC == 2) {
-        // clusters of two: an even grid (a CTA whose tile indices all lie beyond num_tiles runs empty tiles only)
-        grid = (grid + 1) & ~1;
-        if (grid > sm_count()) grid = sm_count() & ~1;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * NWG * CS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        kernel_event_begin(s);
-        VQB_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, th, tl, tq, p));
-        kernel_event_end(s);
-        VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
-        return VQB_OK;
-    }
-    // PDL (only when the caller vouches for the predecessor, VQB_AFTER_ASSEMBLE, or when this call itself has just
-    // launched build_operands_kernel): the prologue and the first x tile overlap the operand-preparation kernel
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    // PDL: this call has just launched build_operands_kernel; the prologue and the first x tile overlap it
     kernel_event_begin(s);
-    if (pdl) VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * NWG * CS), smem, s, tx, th, tl, tq, p));
-    else kern<<<grid, 64 + 128 * NWG * CS, smem, s>>>(tx, th, tl, tq, p);
+    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, s, tx, th, tl, tq, p));
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
@@ -892,38 +704,23 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     const int64_t N = a->n_rows, K = a->n_codes, D = a->dim;
     if (N == 0) return VQB_OK;
     const TcMode mode = tc_mode(a);
-    if (mode == TC_NONE) return invalid("vqb_forward: shape not supported by the tensor-core path");
-    const bool linear = !(a->flags & VQB_SCORE_L2);
-    const bool cached = a->operand_cache && !linear && mode == TC_PCODE;   // the cache carries no |e|_max: p_code mode only
-    const size_t need = (cached ? 0 : hi_bytes(K, D) + lo_bytes(K, D)) + (mode == TC_PCODE ? 0 : 256);
-    if (need && (!a->workspace || a->workspace_bytes < need)) {
+    if (mode == TC_NONE) return invalid("vqb_forward: shape not supported by the tensor-core search");
+    const size_t need = hi_bytes(K, D) + lo_bytes(K, D) + 256;
+    if (!a->workspace || a->workspace_bytes < need) {
         set_error("vqb_forward: workspace too small (%zu < %zu bytes)", a->workspace_bytes, need);
         return VQB_ERR_WORKSPACE;
     }
     uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
-    float* hi;
-    float* lo;
-    uint8_t* tail;
-    if (cached) {
-        uint8_t* oc = reinterpret_cast<uint8_t*>(const_cast<void*>(a->operand_cache));
-        hi = reinterpret_cast<float*>(oc);
-        lo = reinterpret_cast<float*>(oc + hi_bytes(K, D));
-        tail = ws;
-    } else {
-        hi = reinterpret_cast<float*>(ws);
-        lo = reinterpret_cast<float*>(ws + hi_bytes(K, D));
-        tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
-    }
+    float* hi = reinterpret_cast<float*>(ws);
+    float* lo = reinterpret_cast<float*>(ws + hi_bytes(K, D));
+    uint8_t* tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
     float* emax = reinterpret_cast<float*>(tail);
     unsigned int* stats = a->search_stats ? a->search_stats : reinterpret_cast<unsigned int*>(tail + 16);
-    if (mode != TC_PCODE) VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));   // emax / stats are only used by the search epilogue
-    const int BN = mode == TC_PCODE ? 64 : 128;
+    VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));                  // |e|_max (atomicMax) and the re-rank counters
+    constexpr int BN = 128;
     const int64_t Kpad = pad_codes(K, BN);
-    if (!cached) {
-        launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, linear ? 1.f : -2.f, linear ? -1e30f : 1e30f,
-                              hi, mode == TC_SEARCH1 ? nullptr : lo, mode == TC_PCODE ? nullptr : emax, s);
-        VQB_CHECK_LAUNCH("build_operands_kernel");
-    }
+    launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, -2.f, 1e30f, hi, mode == TC_SEARCH1 ? nullptr : lo, emax, s);
+    VQB_CHECK_LAUNCH("build_operands_kernel");
 
     CUtensorMap tx, th, tl, tq;
     int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM);
@@ -934,7 +731,7 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
 
     TcP p;
     p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.emax = emax;
-    p.pcode = a->p_code; p.idx = (long long*)a->idx; p.q = a->new_latent;
+    p.idx = (long long*)a->idx; p.q = a->new_latent;
     p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum; p.stats = stats; p.dbg = g_timeline;
     p.N = (int)N; p.K = (int)K; p.D = (int)D;
     p.num_tiles = (int)ceil_div(N, BM); p.num_chunks = (int)ceil_div(K, BN);
@@ -944,53 +741,24 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     // VQB_SEARCH_NOPIPE=1 or vqb_debug_set_search_pipe(0) turns it off (developer A/B)
     { static const bool nopipe_env = getenv("VQB_SEARCH_NOPIPE") != nullptr; if (g_search_pipe < 0 ? !nopipe_env : g_search_pipe > 0) p.flags |= 0x40000000u; }
 
-    const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
-    //                      KB  BN  XS BS PASSES RESIDENT PCODE
-    if (mode == TC_PCODE && experiment_on(g_fwd_x3, "VQB_FWD_X3")) {
-        // experimental (vqb_debug_set_fwd_x3): bias added by the epilogue (no A block, no bias piece), staging sized by K,
-        // three x slots.  Taken only when it fits: K = 64 at D = 64 is 768 bytes over and stays on the default kernel.
-        const size_t need = (size_t)3 * (D / 32) * XBLK + (size_t)(D / 32) * XBLK + (size_t)2 * (D / 32) * 64 * 128 +
-                            (size_t)2 * BM * (K | 1) * 4 + 1024 + 256 + 2 * BM * 4 + 2 * 64 * 4;
-        if ((int)need <= max_optin_smem()) {
-            if (D == 32) return launch_tc<1, 64, 3, 2, 3, true, true, 2, true>(tx, th, tl, tq, p, s, pdl);
-            return launch_tc<2, 64, 3, 4, 3, true, true, 2, true>(tx, th, tl, tq, p, s, pdl);
-        }
-    }
-    if (mode == TC_PCODE) {
-        if (D == 32) return launch_tc<1, 64, 2, 3, 3, true, true, 2>(tx, th, tl, tq, p, s, pdl);
-        return launch_tc<2, 64, 2, 5, 3, true, true, 2>(tx, th, tl, tq, p, s, pdl);
-    }
+    //                      KB  BN  XS BS PASSES RESIDENT
     if (mode == TC_SEARCH3) {
         if (K <= 128) {                                            // whole codebook resident in shared memory
-            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true, false>(tx, th, tl, tq, p, s, pdl);
-            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true, false>(tx, th, tl, tq, p, s, pdl);
+            if (D == 32) return launch_tc<1, 128, 2, 3, 3, true>(tx, th, tl, tq, p, s);
+            if (D == 64) return launch_tc<2, 128, 1, 5, 3, true>(tx, th, tl, tq, p, s);
         }
         // The codebook ring is as deep as shared memory allows: the streamed search is bound by the bytes in flight
         // from L2 (one 16 KB piece per slot; the tensor pipe consumes ~100 GB/s per SM at the tf32 peak, i.e. needs
         // ~150 KB in flight at ~1.5 us of loaded L2 latency -- profiles/r1e_ncu_full_search.csv: nothing else is busy).
-        if (D == 32) return launch_tc<1, 128, 2, 8, 3, false, false>(tx, th, tl, tq, p, s, pdl);
-        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
-        return launch_tc<4, 128, 1, 4, 3, false, false>(tx, th, tl, tq, p, s, pdl);
-    }
-    if (experiment_on(g_search_mc2, "VQB_SEARCH_MC2") && D >= 128) {
-        // experimental (vqb_debug_set_search_mc2): clusters of two with the codebook pieces multicast into both CTAs
-        if (D == 128) return launch_tc<4, 128, 1, 8, 1, false, false, 1, false, 1, 2>(tx, th, tl, tq, p, s, pdl);
-        return launch_tc<8, 128, 1, 5, 1, false, false, 1, true, 1, 2>(tx, th, tl, tq, p, s, pdl);
-    }
-    if (experiment_on(g_search_cs2, "VQB_SEARCH_CS2") && D <= 128) {
-        // experimental (vqb_debug_set_search_cs2): two epilogue warpgroups, each on half of every chunk's columns; one ring
-        // slot less where the second candidate list needs the room
-        switch (D) {
-            case 32:  return launch_tc<1, 128, 2, 8, 1, false, false, 1, false, 2>(tx, th, tl, tq, p, s, pdl);
-            case 64:  return launch_tc<2, 128, 2, 7, 1, false, false, 1, false, 2>(tx, th, tl, tq, p, s, pdl);
-            default:  return launch_tc<4, 128, 1, 7, 1, false, false, 1, false, 2>(tx, th, tl, tq, p, s, pdl);
-        }
+        if (D == 32) return launch_tc<1, 128, 2, 8, 3, false>(tx, th, tl, tq, p, s);
+        if (D == 64) return launch_tc<2, 128, 2, 4, 3, false>(tx, th, tl, tq, p, s);
+        return launch_tc<4, 128, 1, 4, 3, false>(tx, th, tl, tq, p, s);
     }
     switch (D) {
-        case 32:  return launch_tc<1, 128, 2, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);
-        case 64:  return launch_tc<2, 128, 2, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);
-        case 128: return launch_tc<4, 128, 1, 8, 1, false, false>(tx, th, tl, tq, p, s, pdl);
-        default:  return launch_tc<8, 128, 1, 5, 1, false, false, 1, true>(tx, th, tl, tq, p, s, pdl);
+        case 32:  return launch_tc<1, 128, 2, 8, 1, false>(tx, th, tl, tq, p, s);
+        case 64:  return launch_tc<2, 128, 2, 8, 1, false>(tx, th, tl, tq, p, s);
+        case 128: return launch_tc<4, 128, 1, 8, 1, false>(tx, th, tl, tq, p, s);
+        default:  return launch_tc<8, 128, 1, 5, 1, false, true>(tx, th, tl, tq, p, s);
     }
 }
 

@@ -58,7 +58,6 @@ assemble_small_kernel(const float* __restrict__ learnable, const float* __restri
     const int Dl = D - Da;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     pdl_launch();                                      // the forward kernel may start its prologue (it waits before reading)
-    pdl_wait();                                        // ... and this kernel's own launch may overlap its predecessor's tail
     for (int i = threadIdx.x; i < K * Dl; i += blockDim.x) {
         const int k = i / Dl, d = i - k * Dl;
         s_tab[k * D + d] = learnable[i];
@@ -159,15 +158,9 @@ extern "C" int vqb_assemble_table(const float* learnable, const float* phn_attr,
     if (!has_attr) { n_attr = 0; dim_attr = 0; }
     if (operand_cache && small_table(n_codes, dim) && n_attr <= 63) {
         const size_t dyn = (size_t)(n_codes * n_attr + dim_attr * n_attr + dim_attr) * 4;      // <= 32.5 KB
-        static const bool no_pdl = getenv("VQB_ASM_NO_PDL") != nullptr;    // developer A/B
-        if (no_pdl)
-            assemble_small_kernel<<<1, 512, dyn, (cudaStream_t)stream>>>(
-                learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
-                enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache));
-        else
-        VQB_CUDA(launch_pdl(assemble_small_kernel, dim3(1), dim3(512), dyn, (cudaStream_t)stream,
-                            learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
-                            enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache)));
+        assemble_small_kernel<<<1, 512, dyn, (cudaStream_t)stream>>>(
+            learnable, phn_attr, proj_w, proj_b, (int)n_codes, (int)dim, (int)n_attr, (int)dim_attr, table,
+            enorm, (__nv_bfloat16*)table_bf16, reinterpret_cast<uint8_t*>(operand_cache));
         VQB_CHECK_LAUNCH("assemble_small_kernel");
         return VQB_OK;
     }

@@ -74,6 +74,8 @@ class _QuantizerBase(nn.Module):
         self.last_idx = None
         # fused backward tail (partial sums + table backward [+ cross-GPU sum] in one kernel); see functional.FusedTail
         self.fused_tail = VF.FusedTail()
+        # no-grad fast path (validation / encode loops): cached table + operand image, direct C-ABI call
+        self._nograd = VF.NoGradCache()
 
     def _init_attr(self, latent_dim, phn_attr_pth, proj_attr):
         self.use_phn_attr = phn_attr_pth is not None and phn_attr_pth != ""
@@ -138,6 +140,8 @@ class L2Embedding(_QuantizerBase):
         return nn.Embedding.from_pretrained(table)
 
     def inference(self, txt):
+        if not torch.is_grad_enabled():
+            return VF.lookup_nograd(self._nograd, txt, self.learnable_table, *self._attr_params())
         return VF.codebook_lookup(txt, self.learnable_table, *self._attr_params(), tail=self.fused_tail)
 
     def forward(self, enc_embs, first_n_real_mel=0):
@@ -146,6 +150,12 @@ class L2Embedding(_QuantizerBase):
         skip = bool(self.training and self.skip_prob > 0 and np.random.rand() < self.skip_prob)
         want_losses = self.vq_weight > 0 or self.commit_weight > 0
         attr, pw, pb = self._attr_params()
+        if not torch.is_grad_enabled() and not want_losses:
+            # bin/train_vqvae.py:343 (validate) and the encode path: nothing to differentiate, nothing to save
+            p_code, new_latent, idx = VF.forward_nograd(self._nograd, enc_embs, self.learnable_table, attr, pw, pb, self.temp,
+                                                        skip, not self.fused_search, self._hist(enc_embs), self.tensor_cores)
+            self.last_idx = idx
+            return p_code, new_latent, 0, 0
         p_code, new_latent, idx, vq, commit = VF.vq_l2(
             enc_embs, self.learnable_table, attr, pw, pb, self.temp, stop_grad=self.stop_grad, skip=skip,
             n_real_rows=first_n_real_mel * S if first_n_real_mel > 0 else 0,

@@ -115,6 +115,99 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
     return p_code, idx, q, sq
 
 
+class NoGradCache:
+    """Per-module state of the no-grad fast path (validation and encode loops: bin/train_vqvae.py:343-346, bin/gen_specgram.py:
+    95-108): the assembled table, |e|^2 and the operand image are kept until a parameter changes (data pointer or in-place
+    version counter), the argument struct is built once, and the call goes straight to the C ABI -- no autograd.Function,
+    no per-call table assembly, no workspace query.  What is left per call is three output allocations and one launch."""
+
+    def __init__(self):
+        self.key = None
+        self.table = self.enorm = self.image = None
+        self.args = None
+        self.ws = None
+
+    def __deepcopy__(self, memo):
+        return NoGradCache()                      # a copied module rebuilds its cache (the struct holds raw device pointers)
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    @staticmethod
+    def _key(tensors):
+        return tuple((t.data_ptr(), t._version, t.device.index) for t in tensors if t is not None)
+
+    def tables(self, learnable, phn_attr, proj_w, proj_b, want_image):
+        key = self._key((learnable, phn_attr, proj_w, proj_b)) + (bool(want_image),)
+        if key != self.key:
+            res = assemble_table(learnable, phn_attr, proj_w, proj_b, want_cache=want_image)
+            self.table, self.enorm = res[0], res[1]
+            self.image = res[3] if want_image else None
+            self.key = key
+            self.args = None
+        return self.table, self.enorm, self.image
+
+
+def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, want_pcode, hist, tensor_cores):
+    """L2 quantizer forward without autograd (src/embed.py:105-147 under torch.no_grad()).
+    Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S])."""
+    _require(x, "enc_embs")
+    if x.dim() != 3:
+        raise RuntimeError("semi-tts_b200: enc_embs must be [B, S, D]")
+    lib = _lib.load()
+    B, S, D = x.shape
+    x2d = _c(x).view(B * S, D)
+    use_image = bool(tensor_cores and want_pcode)
+    table, enorm, image = cache.tables(learnable, phn_attr, proj_w, proj_b, use_image)
+    K = table.shape[0]
+    if table.shape[1] != D:
+        raise RuntimeError("semi-tts_b200: enc_embs has D=%d but the codebook has D=%d" % (D, table.shape[1]))
+    dev = x.device
+    N = B * S
+    p_code = torch.empty(N, K, device=dev, dtype=torch.float32) if want_pcode else None
+    idx = torch.empty(N, device=dev, dtype=torch.int64)
+    q = torch.empty(N, D, device=dev, dtype=torch.float32)
+    a = cache.args
+    if a is None:
+        a = _lib.FwdArgs()
+        a.struct_size = ctypes.sizeof(_lib.FwdArgs)
+        a.dim, a.n_codes = D, K
+        a.score_w, a.score_b, a.gather_table = ptr(table), ptr(enorm), ptr(table)
+        a.operand_cache = ptr(image)
+        cache.args = a
+        cache.ws = None
+    a.flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SKIP if skip else 0) | (_lib.TENSOR_CORES if tensor_cores else 0)
+    a.n_rows = N
+    a.x, a.temp, a.p_code, a.idx, a.new_latent, a.hist = ptr(x2d), ptr(temp), ptr(p_code), ptr(idx), ptr(q), ptr(hist)
+    with torch.cuda.device(dev):
+        if not (use_image and image is not None):
+            # shapes outside the cached-image route (fused search, CUDA-core kernels) may need scratch: sized once per module
+            if cache.ws is None:
+                nbytes = ctypes.c_size_t(0)
+                _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
+                cache.ws = torch.empty(max(nbytes.value, 1), device=dev, dtype=torch.uint8)
+            a.workspace, a.workspace_bytes = ptr(cache.ws), cache.ws.numel()
+        _lib.check(lib.vqb_forward(ctypes.byref(a), _stream(x2d)))
+    return (p_code.view(B, S, K) if want_pcode else None), q.view(B, S, D), idx.view(B, S)
+
+
+def lookup_nograd(cache, txt, learnable, phn_attr, proj_w, proj_b):
+    """inference(txt) without autograd (src/embed.py:96-103 under torch.no_grad()): a gather from the cached table."""
+    _require(txt, "txt", torch.int64)
+    lib = _lib.load()
+    want_image = cache.key[-1] if cache.key is not None else False
+    table, _, _ = cache.tables(learnable, phn_attr, proj_w, proj_b, want_image)
+    K, D = table.shape
+    t = _c(txt)
+    out = torch.empty(*t.shape, D, device=t.device, dtype=torch.float32)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.vqb_inference_gather(ptr(t), t.numel(), ptr(table), K, D, ptr(out), _stream(t)))
+    return out
+
+
 class FusedTail:
     """Per-module state of the fused backward tail (include/vqb.h: vqb_bwd_tail): the ticket / epoch words and, in
     data-parallel runs, the peer-mapped exchange buffers (dist.enable_fused_allreduce).  `fused` records whether the
@@ -159,7 +252,7 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.operand_cache = ptr(operand_cache)
     use_tail = bool(tail is not None and tail.enabled and (flags & _lib.SCORE_L2) and not separate_gather
-                    and (lib.vqb_backward_kernel_name(ctypes.byref(a)) in (b"vqb_bwd_pcode_kernel", b"vqb_bwd_h2_kernel")
+                    and (lib.vqb_backward_kernel_name(ctypes.byref(a)) == b"vqb_bwd_pcode_kernel"
                          or (N == 0 and tail.exchange is not None)))      # an empty shard still joins its peers' exchange
     flat = tl = None
     if use_tail:

@@ -74,16 +74,6 @@ def main(quiet=False):
                 ab["fwd_ms_search_nopipe"] = timed_fwd()
                 lib.vqb_debug_set_search_pipe(-1)
                 assert torch.equal(idx, idx_ref), "the pipelined search and the plain one disagree"
-            if os.environ.get("VQB_SWEEP_MC2_AB") and D >= 128 and (K > 1024 or D == 256):   # experimental cluster-of-2 multicast stream
-                lib.vqb_debug_set_search_mc2(1)
-                ab["fwd_ms_search_mc2"] = timed_fwd()
-                lib.vqb_debug_set_search_mc2(0)
-                assert torch.equal(idx, idx_ref), "the multicast search changed the indices"
-            if os.environ.get("VQB_SWEEP_CS2_AB"):               # experimental column-split epilogue (streamed 1xTF32 search, D <= 128)
-                lib.vqb_debug_set_search_cs2(1)
-                ab["fwd_ms_search_cs2"] = timed_fwd()
-                lib.vqb_debug_set_search_cs2(0)
-                assert torch.equal(idx, idx_ref), "the column-split search changed the indices"
             # scatter-add backward (codebook gradient + histogram), idx from the last forward
             dtab = torch.zeros(K, D, device="cuda"); hist = torch.zeros(K, dtype=torch.int64, device="cuda")
             nbs = ctypes.c_size_t(0)

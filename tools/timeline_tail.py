@@ -1,4 +1,4 @@
-"""Timeline of the fused backward tail (bwd_tail_h2_kernel), one process per GPU under torchrun (or alone):
+"""Timeline of the fused backward tail (bwd_tail_kernel), one process per GPU under torchrun (or alone):
 %globaltimer marks of block 0 / the elected last block, relative to the end of the main backward kernel's CTA 0."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
