@@ -44,7 +44,7 @@ def reduce_route_output(flat, tail, group=None):
     attached: the route's flat parameter gradient is summed over the group right here, with one NCCL all-reduce, before
     autograd accumulates it into p.grad.  With an exchange attached every contribution to p.grad is therefore already a
     global sum -- whatever mixture of routes a step takes -- and allreduce_codebook_grads() has nothing left to add."""
-    if tail is None or tail.exchange is None or flat is None:
+    if tail is None or tail.exchange is None or flat is None or isinstance(tail.exchange, LoopbackExchange):
         return
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(tail.exchange.group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=tail.exchange.group)
@@ -76,6 +76,29 @@ class PeerExchange:
     def peer_ptrs_dev(self, n_flat):
         if n_flat > self.max_floats:
             raise RuntimeError("semi-tts_b200: exchange buffer holds %d floats, the gradient has %d" % (self.max_floats, n_flat))
+        return self.ptrs.data_ptr()
+
+
+class LoopbackExchange:
+    """Single-GPU emulation of a `world`-rank exchange for tests: every emulated rank's exchange buffer lives in THIS GPU's
+    memory and the `peer` pointers are plain device pointers, so the same tail kernel, the same (value, epoch) words and the
+    same polling loop run as over NVLink.  One instance per emulated rank, all built from one shared buffer set:
+        bufs = LoopbackExchange.make_buffers(world, n_floats, device)
+        ex_r = LoopbackExchange(bufs, rank=r)            # attach to module replica r: m_r.fused_tail.exchange = ex_r
+    The replicas' backward passes must run CONCURRENTLY (different streams): each tail polls for the other's push."""
+    group = None
+
+    @staticmethod
+    def make_buffers(world, n_floats, device):
+        from . import _lib
+        nbytes = _lib.load().vqb_exchange_bytes(int(n_floats), world)
+        return [torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=device) for _ in range(world)]
+
+    def __init__(self, bufs, rank):
+        self.bufs, self.world, self.rank = bufs, len(bufs), rank
+        self.ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=bufs[0].device)
+
+    def peer_ptrs_dev(self, n_flat):
         return self.ptrs.data_ptr()
 
 

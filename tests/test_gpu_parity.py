@@ -502,6 +502,54 @@ def test_fused_backward_tail_matches_the_three_kernel_route(name):
         assert int(m.fused_tail.counter[0].item()) == 0     # ticket word handed back
 
 
+def test_fused_exchange_loopback_on_one_gpu(monkeypatch):
+    """The in-kernel gradient exchange of the backward tail (push (value, epoch) words into every rank's buffer, poll,
+    rank-ordered sum) exercised on ONE GPU: two replicas of the module on two streams, their exchange buffers in this GPU's
+    memory (dist.LoopbackExchange).  Both replicas must end with the bit-identical sum of the two shards' gradients --
+    three steps in a row (both slots, growing epochs) -- and the status flag must stay clear."""
+    import copy
+    import semi_tts_b200 as V
+    monkeypatch.setenv("VQB_EXCHANGE_TIMEOUT_MS", "5000")
+    g = load_golden("l2_config1_16x200")
+    m0 = build_module(g, "l2")
+    m1 = copy.deepcopy(m0)
+    gen = torch.Generator().manual_seed(3)
+    B, S, K, D = 8, 200, 43, 64
+
+    def shard():
+        return [torch.randn(B, S, D, generator=gen).cuda().requires_grad_(True), torch.randn(B, S, K, generator=gen).cuda(),
+                torch.randn(B, S, D, generator=gen).cuda()]
+
+    def grads(m, s):
+        for p_ in m.parameters():
+            p_.grad = None
+        p, q, _, _ = m(s[0])
+        torch.autograd.backward([p, q], [s[1], s[2]])
+        return torch.cat([p_.grad.reshape(-1) for p_ in m.parameters() if p_.requires_grad])
+
+    n = sum(p_.numel() for p_ in m0.parameters() if p_.requires_grad)
+    bufs = V.dist.LoopbackExchange.make_buffers(2, n, torch.device("cuda"))
+    st = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for step in range(3):
+        sh = [shard(), shard()]
+        m0.fused_tail.exchange = m1.fused_tail.exchange = None
+        want = grads(m0, sh[0]).clone() + grads(m1, sh[1]).clone()          # unfused, summed on the host side of the test
+        m0.fused_tail.exchange = V.dist.LoopbackExchange(bufs, 0)
+        m1.fused_tail.exchange = V.dist.LoopbackExchange(bufs, 1)
+        torch.cuda.synchronize()
+        got = [None, None]
+        for r, m in enumerate((m0, m1)):
+            st[r].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st[r]):
+                got[r] = grads(m, sh[r]).clone()
+        torch.cuda.synchronize()
+        assert m0.fused_tail.fused and m1.fused_tail.fused
+        assert torch.equal(got[0], got[1])                                   # rank-ordered sum: identical bits on both ranks
+        assert rel_err(got[0].cpu().numpy(), want.cpu().numpy()) < 2e-6
+        V.dist.check_exchange(m0); V.dist.check_exchange(m1)
+        assert int(m0.fused_tail.counter[1].item()) == step + 1              # epoch of the exchange
+
+
 def test_fused_exchange_over_peer_memory_two_gpus():
     """2+ GPUs only: tools/dist_check.py under torchrun (fused one-shot all-reduce vs NCCL, graph replay)."""
     import json, os, subprocess, sys
