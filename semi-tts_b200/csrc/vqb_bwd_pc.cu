@@ -523,8 +523,7 @@ static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtenso
     const size_t smem = (size_t)p.pg_bytes + 2 * 2 * TBLK + TBLK + 8 * 4 + 3 * 8 + 16 + 1024;
     if ((int)smem > max_optin_smem()) return invalid("vqb_backward: the parity-mode kernel needs %zu B of shared memory", smem);
     auto kern = vqb_bwd_pcode_kernel<KP, L2>;
-    VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    { const int rc_ = ensure_smem(kern, smem, true); if (rc_) return rc_; }
     // a plain stream-ordered launch: what precedes the backward in the stream (the producer of g_p / g_q, possibly a copy)
     // is not ours to overlap -- and chaining it behind this library's own forward with programmatic serialization was
     // measured SLOWER (61.8 vs 57.9 us per step at config 2, profiles/r2_pdl_ab.txt).  The kernel still releases its own

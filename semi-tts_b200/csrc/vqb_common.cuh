@@ -46,6 +46,22 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize, PreferredSharedMemoryCarveout) once per (kernel instantiation, device,
+// size) instead of on every launch: the attribute calls cost more than the launch itself on the eager encode path
+template <typename Kern>
+static inline int ensure_smem(Kern kern, size_t smem, bool max_carveout) {
+    static thread_local struct { Kern k; int dev; size_t smem; } memo[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto& m : memo)
+        if (m.k == kern && m.dev == dev && m.smem >= smem) return VQB_OK;
+    VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (max_carveout) VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (auto& m : memo)
+        if (m.k == nullptr || (m.k == kern && m.dev == dev)) { m.k = kern; m.dev = dev; m.smem = smem; break; }
+    return VQB_OK;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

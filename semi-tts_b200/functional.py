@@ -32,6 +32,22 @@ def _c(t):
     return None if t is None else t.contiguous()
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _on(dev):
+    """context that makes `dev` current for the C-ABI call; free when it already is (the usual case)"""
+    return _NULL if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+
 # ------------------------------------------------------------------------------------------------
 # raw (non-differentiable) table assembly: src/embed.py:109-112
 # ------------------------------------------------------------------------------------------------
@@ -182,7 +198,7 @@ def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, wa
     a.flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SKIP if skip else 0) | (_lib.TENSOR_CORES if tensor_cores else 0)
     a.n_rows = N
     a.x, a.temp, a.p_code, a.idx, a.new_latent, a.hist = ptr(x2d), ptr(temp), ptr(p_code), ptr(idx), ptr(q), ptr(hist)
-    with torch.cuda.device(dev):
+    with _on(dev):
         if not (use_image and image is not None):
             # shapes outside the cached-image route (fused search, CUDA-core kernels) may need scratch: sized once per module
             if cache.ws is None:
@@ -203,7 +219,7 @@ def lookup_nograd(cache, txt, learnable, phn_attr, proj_w, proj_b):
     K, D = table.shape
     t = _c(txt)
     out = torch.empty(*t.shape, D, device=t.device, dtype=torch.float32)
-    with torch.cuda.device(t.device):
+    with _on(t.device):
         _lib.check(lib.vqb_inference_gather(ptr(t), t.numel(), ptr(table), K, D, ptr(out), _stream(t)))
     return out
 

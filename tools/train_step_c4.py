@@ -286,6 +286,8 @@ def main():
             if "dx" in b:
                 p["dx_rel_err_vs_fp64_oracle"] = rel(b["dx"].cpu(), torch.from_numpy(ob["dx"]))
             par[name] = p
+            if name == "speech_first":                          # both upstream gradients cross the boundary in this step
+                boundary = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in drop.boundary.items()}
         res["boundary_parity"] = par
         # codebook gradients of the whole step, stock vs drop-in (they include the inference() route of text_to_speech)
         g_s = stock.model.codebook.learnable_table.grad
@@ -321,7 +323,6 @@ def main():
         torch.cuda.synchronize()
         h1.remove(); h2.remove()
         res["quantizer_forward_ms_in_step_stock"] = ev[0].elapsed_time(ev[1])
-        boundary = {k: v for k, v in drop.boundary.items()}
         del stock
     # ---------------- N GPUs: the batch sharded by utterance, codebook replicated ----------------------------------------
     if world > 1:
