@@ -38,7 +38,6 @@ struct PcP {
     const float* temp;         // [1]
     const uint8_t* img;        // operand image of the score table (vqb_f16x2.cuh)
     float* pcode;
-    float* q;
     long long* idx;
     unsigned long long* hist;
     double* sqerr;
@@ -336,37 +335,7 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         __syncwarp();
         VQB_PTL(7);
         const int rows_w = min(32, rows - 32 * warp);        // rows of this warp's slab inside the tensor (<= 0: none)
-        if (rows_w > 0 && (p.flags & 0x20000000u)) {
-            // direct stores: the slab goes out as coalesced 128-bit stores issued by the warp itself (fire and forget: the
-            // warp does not wait for a bulk engine to drain its shared memory before the CTA may retire)
-            constexpr int CH = D / 4;                                      // 16-byte chunks per row
-            float* qdst = p.q + (size_t)(row0 + 32 * warp) * D;
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const int i = lane + 32 * j;
-                const int rl = i / CH, cc = i - rl * CH;                   // row of the slab, chunk of the row
-                if (rl < rows_w) {
-                    const float4 o = *reinterpret_cast<const float4*>(sX + (cc >> 3) * PBLK + sw128_offset(32 * warp + rl, cc & 7));
-                    stg4_stream(qdst + (size_t)rl * D + 4 * cc, o);
-                }
-            }
-            float* dst = p.pcode + (size_t)(row0 + 32 * warp) * K;
-            const float* src = sP + 32 * warp * KO;
-            const int n = rows_w * K;
-            if (K & 1) {
-                const int n4 = n >> 2;
-                for (int i = lane; i < n4; i += 32) stg4_stream(dst + 4 * i, *reinterpret_cast<const float4*>(src + 4 * i));
-                if (lane < n - 4 * n4) dst[4 * n4 + lane] = src[4 * n4 + lane];
-            } else {
-                int rr = lane / K, k = lane - rr * K;
-                const int step_r = 32 / K, step_k = 32 - step_r * K;
-                for (int i = lane; i < n; i += 32) {
-                    __stcs(dst + i, src[rr * KO + k]);
-                    rr += step_r; k += step_k;
-                    if (k >= K) { k -= K; ++rr; }
-                }
-            }
-        } else if (rows_w > 0) {
+        if (rows_w > 0) {
             float* dst = p.pcode + (size_t)(row0 + 32 * warp) * K;
             const float* src = sP + 32 * warp * KO;
             const int n = rows_w * K;
@@ -492,10 +461,9 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, 32))) return rc;   // one warp's slab per store
     PcP p;
     p.x = a->x; p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.img = img;
-    p.pcode = a->p_code; p.q = a->new_latent; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
+    p.pcode = a->p_code; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
     p.stats = a->search_stats; p.dbg = get_debug_timeline();
     p.N = (int)N; p.K = (int)K; p.num_tiles = (int)ceil_div(N, PM); p.se_bytes = 0; p.flags = a->flags;
-    { static const bool stg = getenv("VQB_FWD_STG") != nullptr; if (stg) p.flags |= 0x20000000u; }   // developer A/B: direct stores
     // PDL when the kernel enqueued immediately before is ours: the image build above, or (the caller vouches,
     // VQB_AFTER_ASSEMBLE) the table assembly
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);
