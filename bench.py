@@ -42,9 +42,10 @@ def _config(world):
             "launch": "GPU arm: one CUDA graph per step (assemble, forward, backward, tail); reference arm: eager torch CPU ops",
             "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
                 RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
-            "parallelism": "dp%d (frames sharded by batch, codebook replicated; codebook-gradient sum over GPUs inside the "
-                           "backward's tail kernel, one-shot all-reduce over NVLink peer memory; the usage histogram is "
-                           "exchanged once per timed window, where the trainer reads it)" % world}
+            "parallelism": "dp%d (frames sharded by batch, codebook replicated; codebook-gradient sum over GPUs by this library's "
+                           "own kernels over NVLink peer memory: the backward's tail pushes, the rank-ordered sum of step i runs "
+                           "behind step i+1's forward and is joined before its backward; the usage histogram is exchanged once "
+                           "per timed window, where the trainer reads it)" % world}
 
 
 def _peaks():
@@ -322,10 +323,24 @@ def run_ours(args, rank, world, local_rank):
     for s in sets:
         s[0].requires_grad_(True)
 
+    # Deferred exchange (N > 1): the backward's tail kernel pushes this rank's flat gradient into every peer's buffer over
+    # NVLink; the poll + rank-ordered sum of step i runs on a side stream behind step i+1's table assembly and forward, and is
+    # joined before step i+1's backward (grads are consumed by optimizer.step, src/solver.py:149; in a trainer the rest of
+    # the model's backward sits there).  The rank skew and the NVLink round trip are then off the step's critical path.
+    deferred = dist_on and m.fused_tail.exchange is not None and not os.environ.get("VQB_NO_DEFER")
+    m.fused_tail.defer = deferred
+    side_x = torch.cuda.Stream() if deferred else None
+
     def step(s):
+        if deferred:
+            cur = torch.cuda.current_stream()
+            side_x.wait_stream(cur)
+            V.dist.finish_codebook_grads(m, stream=side_x)      # the previous step's exchange, concurrent with this forward
         p, q, _, _ = m(s[0])
+        if deferred:
+            cur.wait_stream(side_x)
         torch.autograd.backward([p, q], [s[1], s[2]])
-        if dist_on:
+        if dist_on and not deferred:
             V.dist.allreduce_codebook_grads(m)
 
     # ---- value: device-resident inputs, whole step (fwd + bwd [+ all-reduce]) captured in CUDA graphs ------
@@ -344,7 +359,10 @@ def run_ours(args, rank, world, local_rank):
     launches_per_step = 0
     try:
         pool = None
-        for s in sets:
+        V.dist.finish_codebook_grads(m)          # nothing pending when the first capture starts
+        # deferred exchange: every graph finishes its ring predecessor's exchange, so set 0 is captured once more at the end
+        # (then with set RING-1's exchange pending) and that second capture is the one replayed
+        for s in (sets + [sets[0]] if deferred else sets):
             l0 = lib_.vqb_launch_count()
             for p_ in m.parameters():
                 p_.grad = None                  # as after optimizer.zero_grad(): backward assigns, it does not accumulate
@@ -356,6 +374,9 @@ def run_ours(args, rank, world, local_rank):
             launches_per_step = int(lib_.vqb_launch_count() - l0)      # this library's kernels in one captured step
             pool = g.pool()
             graphs.append(g)
+        if deferred:
+            _keep_first_capture = graphs[0]                             # its buffers stay valid: set 1's graph finishes into them
+            graphs = [graphs[RING]] + graphs[1:RING]                    # the re-captured set 0, then sets 1 .. RING-1
     except Exception as e:           # noqa: BLE001 -- report and fall back to eager launches of the same kernels
         use_graph = False
         graphs = []
@@ -396,6 +417,7 @@ def run_ours(args, rank, world, local_rank):
     e0.record()
     run_steps(args.steps, first=args.warmup)
     if dist_on:
+        V.dist.finish_codebook_grads(m)    # the last step's exchange (deferred mode) completes inside the timed region
         V.dist.allreduce_usage(m)          # bin/train_vqvae.py:305 reads the histogram once per 500-step window
     e1.record()
     barrier()

@@ -47,7 +47,7 @@ class BwdArgs(ctypes.Structure):
 
 EXPORTS = ["vqb_abi_version", "vqb_last_error", "vqb_device_count", "vqb_operand_cache_bytes", "vqb_assemble_table",
            "vqb_table_backward", "vqb_forward_workspace", "vqb_forward", "vqb_backward_workspace",
-           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_inference_gather", "vqb_scatter_add", "vqb_scatter_workspace", "vqb_loss_backward",
+           "vqb_backward", "vqb_forward_kernel_name", "vqb_backward_kernel_name", "vqb_launch_count", "vqb_exchange_bytes", "vqb_exchange_finish", "vqb_inference_gather", "vqb_scatter_add", "vqb_scatter_workspace", "vqb_loss_backward",
            "vqb_row_argmax", "vqb_segment_plan", "vqb_segment_mean", "vqb_segment_mean_backward", "vqb_ctc_logp", "vqb_ctc_logp_backward"]
 
 _lib = None
@@ -97,6 +97,7 @@ def load():
         lib.vqb_operand_cache_bytes.restype = ctypes.c_size_t
         lib.vqb_launch_count.restype = ctypes.c_uint64
         lib.vqb_exchange_bytes.argtypes = [i64, ctypes.c_int32]
+        lib.vqb_exchange_finish.argtypes = [ctypes.POINTER(BwdTail), i64, _p]
         lib.vqb_exchange_bytes.restype = ctypes.c_size_t
         if lib.vqb_abi_version() != ABI_VERSION:
             raise RuntimeError("semi-tts_b200: libvqb200.so ABI %d != expected %d -- rebuild"

@@ -261,3 +261,12 @@ extern "C" const char* vqb_backward_kernel_name(const vqb_bwd_args* a) {
 }
 
 extern "C" size_t vqb_exchange_bytes(int64_t n_flat, int32_t world) { return vqb::exchange_bytes(n_flat, world); }
+
+extern "C" int vqb_exchange_finish(const vqb_bwd_tail* tail, int64_t n_flat, void* stream) {
+    if (!tail || !tail->d_flat || !tail->counter || n_flat <= 0) return invalid("vqb_exchange_finish: tail.d_flat, tail.counter and n_flat are required");
+    if (tail->world > 1 && (!tail->peer_bufs || tail->rank < 0 || tail->rank >= tail->world || tail->world > VQB_MAX_WORLD))
+        return invalid("vqb_exchange_finish: tail.world=%d rank=%d needs peer_bufs and world <= %d", tail->world, tail->rank, VQB_MAX_WORLD);
+    int rc = require_device();
+    if (rc) return rc;
+    return launch_exchange_finish(tail, n_flat, (cudaStream_t)stream);
+}

@@ -78,6 +78,7 @@ struct TailP {
     unsigned long long* dbg;  // optional timeline buffer (developer hook), slots 100..
     unsigned long long timeout_ns;
     int A, Da, world, rank, n_learn_blocks;
+    int defer;                // world > 1: push only; the poll + rank-ordered sum runs later (exchange_finish_kernel)
 };
 #define VQB_TTL(slot) do { if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100 + (slot)] = globaltimer_ns(); } while (0)
 
@@ -201,7 +202,7 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
         }
     }
     VQB_TTL(3);
-    if (tid < n_mine && s_idx[tid] >= 0) {
+    if (!t.defer && tid < n_mine && s_idx[tid] >= 0) {
         const int i = s_idx[tid];
         const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(t.peer_bufs[t.rank]) + slot_off + i;
         float sum = 0.f;
@@ -230,9 +231,45 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
     }
 }
 
+// Deferred second half of the exchange (vqb_bwd_tail.reserved bit 0 / vqb_exchange_finish): every output polls this rank's
+// buffer for all ranks' words of the LAST published epoch and adds them in rank order.  It runs wherever the caller puts
+// it -- behind the rest of the model's backward in a trainer, behind the next step's forward in the bench -- so the
+// round trip over NVLink and the skew between ranks are off the quantizer's critical path.
+__global__ void __launch_bounds__(256)
+exchange_finish_kernel(float* __restrict__ d_flat, void* const* __restrict__ peer_bufs, int rank, unsigned int* counter,
+                       int n_flat, int world, unsigned long long timeout_ns) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_flat) return;
+    const unsigned long long* own = reinterpret_cast<const unsigned long long*>(peer_bufs[rank]);
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(counter + 1);
+    const int n_pad = (n_flat + 3) & ~3;
+    const unsigned long long* mine = own + (size_t)(epoch & 1u) * world * n_pad + i;
+    float sum = 0.f;
+    const unsigned long long t0 = globaltimer_ns();
+    for (int r = 0; r < world; ++r) {                               // rank order: identical bits on every GPU
+        unsigned long long w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+        bool gave_up = false;
+        while ((unsigned int)(w >> 32) != epoch) {
+            if (globaltimer_ns() - t0 > timeout_ns) { atomicMax(counter + 2, (unsigned int)(r + 1)); gave_up = true; break; }
+            w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+        }
+        if (!gave_up) sum += __uint_as_float((unsigned int)w);
+    }
+    d_flat[i] = sum;
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------
+int launch_exchange_finish(const vqb_bwd_tail* tl, int64_t n_flat, cudaStream_t s) {
+    if (tl->world <= 1) return VQB_OK;
+    const unsigned long long timeout_ns = (unsigned long long)(tl->timeout_ms ? tl->timeout_ms : 120000u) * 1000000ull;
+    exchange_finish_kernel<<<(unsigned)ceil_div(n_flat, 256), 256, 0, s>>>(tl->d_flat, tl->peer_bufs, tl->rank, tl->counter, (int)n_flat,
+                                                                        tl->world, timeout_ns);
+    VQB_CHECK_LAUNCH("exchange_finish_kernel");
+    return VQB_OK;
+}
+
 size_t exchange_bytes(int64_t n_flat, int world) { return exch_words(n_flat, world) * 8; }
 
 // Behind the main backward kernel (vqb_bwd_pcode_kernel): the per-CTA partial records -> gradients.
@@ -249,6 +286,7 @@ int launch_bwd_reduce(const vqb_bwd_args* a, const float* partial, int grid, cud
         t.peer_bufs = tl->peer_bufs; t.dbg = dbg; t.A = (int)tl->n_attr; t.Da = (int)tl->dim_attr; t.world = tl->world; t.rank = tl->rank;
         const int Dl = 64 - t.Da;
         t.n_learn_blocks = (int)ceil_div(K * Dl, 32);
+        t.defer = (tl->world > 1 && (tl->reserved & 1u)) ? 1 : 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(t.n_learn_blocks + t.Da)); cfg.blockDim = dim3(32, 32); cfg.stream = s;
         cfg.dynamicSmemBytes = (size_t)K * t.A * 4;                  // <= 64 * 63 * 4 B

@@ -111,6 +111,7 @@ bool forward_tensor_supported(const vqb_fwd_args* a);
 int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes);
 int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s);
 size_t exchange_bytes(int64_t n_flat, int world);
+int launch_exchange_finish(const vqb_bwd_tail* tl, int64_t n_flat, cudaStream_t s);
 int launch_bwd_reduce(const vqb_bwd_args* a, const float* partial, int grid, cudaStream_t s, unsigned long long* dbg);
 // third generation of the parity-mode kernels (vqb_fwd_pc.cu, vqb_bwd_pc.cu): one tile per CTA at a time, several CTAs per SM
 bool forward_pcode_supported(const vqb_fwd_args* a);

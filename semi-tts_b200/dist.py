@@ -119,6 +119,17 @@ def enable_fused_allreduce(module, group=None):
     return ex
 
 
+def finish_codebook_grads(module, stream=None):
+    """Deferred exchange (module.fused_tail.defer = True): complete the gradient exchange that the last backward started --
+    poll for every rank's contribution and add them in rank order -- on `stream` (default: the current stream).  In a trainer
+    call it (or allreduce_codebook_grads, which does it) after loss.backward(): the rest of the model's backward has run in
+    between, so no rank waits for another.  It must be enqueued before the module's next backward (the module does so
+    itself if the caller forgot)."""
+    tail = getattr(module, "fused_tail", None)
+    if tail is not None:
+        tail.finish(stream)
+
+
 def check_exchange(module):
     """Raise if an in-kernel exchange of this module has timed out waiting for a peer (one host synchronisation; call it
     where the trainer synchronises anyway, e.g. where it reads the loss).  The kernel itself never traps: it records the
@@ -149,6 +160,8 @@ def allreduce_codebook_grads(module, group=None, average=False, include_usage=Fa
         return
     grads = [p.grad for p in module.parameters() if p.requires_grad and p.grad is not None]
     tail = getattr(module, "fused_tail", None)
+    if tail is not None:
+        tail.finish()                      # a deferred exchange completes here at the latest
     if grads and tail is not None and tail.exchange is not None:
         # already summed over the group, route by route
         if average:

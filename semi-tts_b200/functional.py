@@ -235,6 +235,23 @@ class FusedTail:
         self.exchange = None         # dist.PeerExchange or None
         self.fused = False
         self.enabled = not os.environ.get("VQB_NO_TAIL_TEST")     # developer switch
+        # deferred exchange (data-parallel runs): the backward's tail only PUSHES this rank's gradient to its peers; the
+        # poll + rank-ordered sum runs in finish() -- called by dist.allreduce_codebook_grads / dist.finish_codebook_grads,
+        # i.e. behind the rest of the model's backward -- or at the latest before the module's next backward
+        self.defer = False
+        self.pending = None          # (BwdTail struct, flat tensor, n_flat) of the exchange that still has to be finished
+
+    def finish(self, stream=None):
+        """second half of a deferred exchange: after this (stream-ordered) the parameter gradients of the last backward
+        hold the sum over all ranks"""
+        if self.pending is None:
+            return
+        tl, flat, n_flat = self.pending
+        self.pending = None
+        lib = _lib.load()
+        st = stream if stream is not None else torch.cuda.current_stream(flat.device)
+        with _on(flat.device):
+            _lib.check(lib.vqb_exchange_finish(ctypes.byref(tl), n_flat, ctypes.c_void_p(st.cuda_stream)))
 
     def counter_for(self, dev):
         # [0] block ticket, [1] epoch of the exchange, [2] error flag (1 + the rank a timed-out exchange waited for), [3] spare
@@ -284,6 +301,9 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
         ex = tail.exchange
         tl.world, tl.rank, tl.peer_bufs = (ex.world, ex.rank, ex.peer_ptrs_dev(n_flat)) if ex is not None else (1, 0, None)
         tl.timeout_ms = _exchange_timeout_ms()
+        if ex is not None and tail.defer:
+            tail.finish()                                  # (an unfinished exchange of the previous step: finish it first)
+            tl.reserved = 1                                # VQB_TAIL_DEFER: push only
         a.tail = ctypes.pointer(tl)
     else:
         # one zero-filled buffer (one fill kernel) carved into the accumulation targets
@@ -305,6 +325,8 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
         _lib.check(lib.vqb_backward(ctypes.byref(a), _stream(x2d)))
     if tail is not None:
         tail.fused = use_tail
+        if use_tail and tl.reserved:
+            tail.pending = (tl, flat, n_flat)
     return dx, d_w, colsum, d_gather, d_temp, flat
 
 
@@ -554,6 +576,10 @@ class _Lookup(torch.autograd.Function):
             _lib.check(lib.vqb_scatter_workspace(t.numel(), K, D, ctypes.byref(nb)))
             ws = torch.empty(nb.value, device=g2.device, dtype=torch.uint8) if nb.value else None
             _lib.check(lib.vqb_scatter_add(ptr(t), t.numel(), ptr(g2), K, D, ptr(dtab), None, ptr(ws), nb.value, _stream(g2)))
+        if ctx.tail is not None and ctx.tail.exchange is not None and ctx.tail.defer:
+            raise RuntimeError("semi-tts_b200: a deferred gradient exchange (fused_tail.defer) cannot be combined with gradients "
+                               "through inference(): the forward route's flat gradient is incomplete until finish(); "
+                               "set module.fused_tail.defer = False for steps that train the codebook through text")
         d_learn, d_pw, d_pb = _table_backward(dtab, None, None, phn_attr, ctx.Da, ctx.tail)
         return None, d_learn, None, d_pw, d_pb, None
 

@@ -80,6 +80,19 @@ def main():
         dist.all_gather(gathered, got)
         ok = ok and err < 2e-6 and all(torch.equal(gathered[0], t) for t in gathered)
     with_lookup[0] = False
+    # deferred exchange: the tail only pushes, allreduce_codebook_grads() (-> finish) completes the sum later
+    m.fused_tail.defer = True
+    worst_defer = 0.0
+    for rep in range(2):
+        for s, (rg, rdx) in zip(sets, ref):
+            got, dx = step(s)
+            err = float((got - rg).norm() / rg.norm())
+            worst_defer = max(worst_defer, err)
+            gathered = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(gathered, got)
+            ok = ok and err < 2e-6 and all(torch.equal(gathered[0], t) for t in gathered)
+    m.fused_tail.defer = False
+    V.dist.check_exchange(m)
     # an empty shard on the last rank: it still joins the exchange (its tail runs over zero rows); expected = the sum of the
     # other ranks' local gradients
     ex = m.fused_tail.exchange
@@ -138,7 +151,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "ok": bool(flag.item()), "max_rel_err_vs_nccl": worst, "max_abs_dx_diff": worst_dx,
-                          "graph_replay_rel_err": err_g, "mixed_routes_rel_err": worst_mixed, "empty_shard_rel_err": err_empty,
+                          "graph_replay_rel_err": err_g, "mixed_routes_rel_err": worst_mixed, "empty_shard_rel_err": err_empty, "deferred_exchange_rel_err": worst_defer,
                           "fused_step_us_16x200": fused_us}), flush=True)
     dist.barrier(); torch.cuda.synchronize()
     sys.stdout.flush()
