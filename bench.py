@@ -316,7 +316,8 @@ def run_ours(args, rank, world, local_rank):
     m.train()
     if os.environ.get("VQB_NO_TAIL"):
         m.fused_tail.enabled = False             # developer switch: three-kernel backward tail
-    if dist_on and not os.environ.get("VQB_NCCL_ALLREDUCE"):
+    no_exchange = bool(os.environ.get("VQB_BENCH_NO_EXCHANGE"))    # developer A/B: N independent replicas, nothing exchanged
+    if dist_on and not os.environ.get("VQB_NCCL_ALLREDUCE") and not no_exchange:
         V.dist.enable_fused_allreduce(m)         # gradient sum inside the backward's tail kernel (NVLink peer memory)
     # ring of distinct device-resident input sets (weak scaling: every rank owns RING x 64 x 800 frames)
     sets = [_inputs(1000 * rank + i, dev) for i in range(RING)]
@@ -340,7 +341,7 @@ def run_ours(args, rank, world, local_rank):
         if deferred:
             cur.wait_stream(side_x)
         torch.autograd.backward([p, q], [s[1], s[2]])
-        if dist_on and not deferred:
+        if dist_on and not deferred and not no_exchange:
             V.dist.allreduce_codebook_grads(m)
 
     # ---- value: device-resident inputs, whole step (fwd + bwd [+ all-reduce]) captured in CUDA graphs ------

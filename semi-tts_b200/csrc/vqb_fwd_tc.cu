@@ -22,6 +22,7 @@
 #include <math.h>
 #include "vqb_common.cuh"
 #include "vqb_tc.cuh"
+#include "vqb_f16x2.cuh"
 
 namespace vqb {
 using namespace tc;
@@ -35,6 +36,7 @@ struct TcP {
     const float* bias;         // [K]    |e|^2 (L2) or b (LINEAR)
     const float* temp;         // [1]
     const float* emax;         // [1]    max_k |e_k|
+    const int* gexp;           // [1]    F16 mode: scale exponent of the fp16 codebook copy (copy = table * 2^-gexp)
     long long* idx;
     float* q;
     unsigned long long* hist;
@@ -90,6 +92,39 @@ build_operands_kernel(const float* __restrict__ w, const float* __restrict__ bia
 void launch_build_operands(const float* w, const float* bias, int K, int Kpad, int D, float scale, float pad_bias,
                            float* hi, float* lo, float* emax, cudaStream_t s) {
     build_operands_kernel<<<(unsigned)Kpad, 128, 0, s>>>(w, bias, K, D, scale, pad_bias, hi, lo, emax);
+}
+
+// F16 mode, step 1: table-wide |w|_max (for the common power-of-two scale) and max_k |w_k|_2 (for the candidate window)
+__global__ void __launch_bounds__(128)
+table_max_kernel(const float* __restrict__ w, int D, unsigned int* __restrict__ gmax_bits, float* __restrict__ emax) {
+    const int k = blockIdx.x;
+    float sq = 0.f, mx = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float v = w[(size_t)k * D + d];
+        sq = fmaf(v, v, sq);
+        mx = fmaxf(mx, fabsf(v));
+    }
+    __shared__ float red[4];
+    __shared__ unsigned int redm[4];
+    sq = warp_sum(sq);
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));      // non-negative floats order like uints
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = sq; redm[threadIdx.x >> 5] = wm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(red[0] + red[1] + red[2] + red[3])));
+        atomicMax(gmax_bits, max(max(redm[0], redm[1]), max(redm[2], redm[3])));
+    }
+}
+// step 2: e16[k][d] = fp16_rn(w[k][d] * 2^-gE), rows K..Kpad-1 zero (their |e|^2 is +1e30 in the epilogue); gE -> *gexp
+__global__ void __launch_bounds__(128)
+build_f16_operands_kernel(const float* __restrict__ w, int K, int D, const unsigned int* __restrict__ gmax_bits,
+                          __half* __restrict__ e16, int* __restrict__ gexp) {
+    const int k = blockIdx.x;
+    const int gE = scale_exp(__uint_as_float(*gmax_bits));
+    const float sE = pow2i(-gE);
+    if (k == 0 && threadIdx.x == 0) *gexp = gE;
+    for (int d = threadIdx.x; d < D; d += blockDim.x)
+        e16[(size_t)k * D + d] = __float2half_rn(k < K ? w[(size_t)k * D + d] * sE : 0.f);
 }
 
 // exact score of code k for the row held (swizzled) in shared memory -- same expression and fmaf order as
@@ -155,13 +190,24 @@ __device__ __forceinline__ float prep_tile(const uint8_t* sX, uint8_t* sXlo, uin
 // per chunk, which buys a fifth ring slot where shared memory is otherwise full.
 // (Measured and dropped in round 2, profiles/r2_search_experiments.txt: a column-split second epilogue warpgroup, clusters
 // of two with the codebook pieces multicast, and the one-pass kernel below K = 1024 -- none was faster.)
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG>
+// F16 (the one-pass search, K > 1024 or D = 256): operands as single fp16 pieces instead of tf32 -- the same 11 significant
+// bits, so the same candidate window, but kind::f16 runs at twice the tf32 rate and an operand byte carries twice the
+// flops: the x tile is half the size, a 16 KB codebook piece covers 64 dimensions instead of 32, and the ring holds twice
+// the work in flight (the streamed search is bound by the bytes in flight from L2, profiles/r1e_ncu_full_search.csv).
+// The row threads rescale their row by a power of two and convert it IN PLACE over the raw TMA tile (x16 block j takes
+// the place of raw block j, which has been read by then); the codebook copy is converted once per call
+// (build_f16_operands_kernel).  Exactness is untouched: the re-rank, the gather and the straight-through need the raw fp32
+// tile again, so it is simply fetched a second time (from L2) once the tile's last MMA has retired -- 128 KB against the
+// 8 MB of codebook that streamed through meanwhile.
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG, bool F16>
 __global__ void __launch_bounds__(192, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
-    constexpr int PIECES = (PASSES == 3 ? 2 * KB : KB) + (NOAUG ? 0 : 1);      // per chunk: hi/lo per K-block + the bias block
-    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT), "NOAUG: streamed 1xTF32 search");
+    constexpr int KH = KB / 2;                                    // fp16 blocks of 64 dimensions (F16)
+    constexpr int PIECES = F16 ? KH : (PASSES == 3 ? 2 * KB : KB) + (NOAUG ? 0 : 1);   // per chunk: hi/lo per K-block + the bias block
+    static_assert(!NOAUG || (PASSES == 1 && !RESIDENT), "NOAUG: streamed one-pass search");
+    static_assert(!F16 || (NOAUG && KB % 2 == 0), "F16: one-pass streamed search, D a multiple of 64, bias added by the epilogue");
     constexpr int TMEM_COLS = 2 * BN;
     constexpr int CAP = NOAUG ? 15 : 16;                          // per-row candidate list capacity (SEARCH); 15: fits 227 KB
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
@@ -184,7 +230,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint64_t* t_full = b_empty + BS;
     uint64_t* t_empty = t_full + 2;
     uint64_t* xlo_free = t_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xlo_free + 1);
+    uint64_t* xr_full = xlo_free + 1;                             // [XS] F16: the raw x tile has been fetched again
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xr_full + XS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[120] = globaltimer_ns();
@@ -199,6 +246,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
         mbar_init(xlo_free, 1);
+        for (int i = 0; i < XS; ++i) mbar_init(&xr_full[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -216,7 +264,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int tile_end = p.num_tiles;
     const uint32_t tmem_base = *tmem_slot;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[122] = globaltimer_ns();
-    constexpr uint32_t IDESC = umma_idesc(2u, BM, BN);
+    constexpr uint32_t IDESC = umma_idesc(F16 ? 0u : 2u, BM, BN);
     // PDL: let the next kernel in the stream begin its prologue; everything below that depends on the kernel BEFORE
     // this one (the operand / table preparation) sits behind pdl_wait().  x is older than that kernel, so the
     // producer may fetch its first tile before waiting.
@@ -245,7 +293,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         mbar_arrive_expect_tx(&b_full[bs], PIECE);
                         const bool is_lo = PASSES == 3 && j < 2 * KB && (j & 1);
                         const int kb = PASSES == 3 ? (j >> 1) : j;                 // the bias block has kb == KB
-                        tma_load_2d(sB + (size_t)bs * PIECE, is_lo ? &tm_lo : &tm_hi, kb * 32, chunk * BN, &b_full[bs]);
+                        tma_load_2d(sB + (size_t)bs * PIECE, is_lo ? &tm_lo : &tm_hi, F16 ? j * 64 : kb * 32, chunk * BN, &b_full[bs]);
                         ++b_it;
                     }
                 }
@@ -262,7 +310,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const uint32_t xls = xs, xlph = xph;
                 const uint8_t* xlt = sXlo + (size_t)xls * KB * XBLK;
                 mbar_wait(&x_full[xs], xph);
-                if (PASSES == 3 && !RESIDENT) mbar_wait(&xlo_full[xls], xlph);
+                if ((PASSES == 3 && !RESIDENT) || F16) mbar_wait(&xlo_full[xls], xlph);   // x_lo written / x converted to fp16
                 tcgen05_fence_after();
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
                     const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
@@ -312,7 +360,11 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                             const bool is_aug = !NOAUG && j == PIECES - 1;
                             const bool is_lo = PASSES == 3 && !is_aug && (j & 1);
                             const int kb = PASSES == 3 ? (j >> 1) : j;
-                            if (is_aug) {
+                            if constexpr (F16) {
+                                const uint64_t a = umma_desc_sw128(xt + j * XBLK);          // fp16 block j: 64 dimensions
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a + 2 * k, b + 2 * k, IDESC, (j | k) != 0);
+                            } else if (is_aug) {
                                 umma_tf32(d_tmem, umma_desc_sw128(sAug), b, IDESC, true);
                             } else {
                                 const uint64_t a = umma_desc_sw128(xt + kb * XBLK);
@@ -387,8 +439,42 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             // |x|^2 in the exact kernel's fmaf order; x_lo = x - trunc_tf32(x) for the third MMA pass
             float xx = 0.f;
             if (PIPE_OK && prepped) xx = xx_pipe;
+            float u_row = 1.f;                                      // F16: accumulator -> -2 x.e
+            if constexpr (F16) {
+                // pass 1: |x|^2 and the row maximum; pass 2: rescale, convert to fp16 in place (block j <- raw blocks 2j, 2j+1)
+                float mx = 0.f;
 #pragma unroll 1
-            for (int kb = 0; kb < ((PIPE_OK && prepped) ? 0 : KB); ++kb) {
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(sXt + kb * XBLK + sw128_offset(r, c));
+                        xx = fmaf(v4.x, v4.x, xx); xx = fmaf(v4.y, v4.y, xx); xx = fmaf(v4.z, v4.z, xx); xx = fmaf(v4.w, v4.w, xx);
+                        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v4.x), fabsf(v4.y))), fmaxf(fabsf(v4.z), fabsf(v4.w)));
+                    }
+                }
+                const int er = scale_exp(mx);
+                const float sx = pow2i(-er);
+                u_row = -2.f * pow2i(er) * pow2i(__ldg(p.gexp));
+#pragma unroll 1
+                for (int j = 0; j < KH; ++j) {
+                    float4 xv[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)                    // all loads first: the stores below alias raw block j
+                        xv[c] = *reinterpret_cast<const float4*>(sXt + (2 * j + (c >> 3)) * XBLK + sw128_offset(r, c & 7));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 a4 = xv[2 * c], b4 = xv[2 * c + 1];
+                        const uint4 h = make_uint4(pack_h2(a4.x * sx, a4.y * sx), pack_h2(a4.z * sx, a4.w * sx),
+                                                   pack_h2(b4.x * sx, b4.y * sx), pack_h2(b4.z * sx, b4.w * sx));
+                        *reinterpret_cast<uint4*>(sXt + j * XBLK + sw128_offset(r, c)) = h;
+                    }
+                }
+                fence_proxy_async_smem();                           // generic writes -> tcgen05.mma operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xlo_full[xls]);
+            }
+#pragma unroll 1
+            for (int kb = 0; kb < ((F16 || (PIPE_OK && prepped)) ? 0 : KB); ++kb) {
                 float4 xv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c)                         // all loads first: the stores below may alias
@@ -454,7 +540,12 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                             for (int j4 = 0; j4 < 8; ++j4) {
                                 const float4 e4 = en4[j4];                  // same address in every lane: a broadcast
-                                v[4 * j4] += e4.x; v[4 * j4 + 1] += e4.y; v[4 * j4 + 2] += e4.z; v[4 * j4 + 3] += e4.w;
+                                if constexpr (F16) {
+                                    v[4 * j4] = fmaf(v[4 * j4], u_row, e4.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], u_row, e4.y);
+                                    v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], u_row, e4.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], u_row, e4.w);
+                                } else {
+                                    v[4 * j4] += e4.x; v[4 * j4 + 1] += e4.y; v[4 * j4 + 2] += e4.z; v[4 * j4 + 3] += e4.w;
+                                }
                             }
                         }
                         float bm = v[0];
@@ -485,6 +576,15 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                     ++c_it;
+                }
+                if constexpr (F16) {
+                    // every MMA of this tile has retired (the last t_full was consumed above): the fp16 copy is dead, the raw
+                    // fp32 tile comes back for the exact re-rank, the gather and the straight-through
+                    if (et == 0) {
+                        mbar_arrive_expect_tx(&xr_full[xs], KB * XBLK);
+                        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sXt + kb * XBLK, &tm_x, kb * 32, row0, &xr_full[xs]);
+                    }
+                    mbar_wait(&xr_full[xs], xph);
                 }
                 const int ctot = cnt;
                 // survivors of the final window -> exact fp32 re-rank (same expression / fmaf order as the SIMT kernel)
@@ -654,6 +754,35 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     return VQB_OK;
 }
 
+// 2-D fp16 row-major tensor map [rows][cols], box = box_rows x 64 halves (128 bytes), SWIZZLE_128B
+static int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            set_error("libvqb200: cuTensorMapEncodeTiled is not available from the driver");
+            return VQB_ERR_CUDA;
+        }
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("libvqb200: cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols);
+        return VQB_ERR_CUDA;
+    }
+    return VQB_OK;
+}
+
 static int g_search_pipe = -1;                 // -1: default (on unless VQB_SEARCH_NOPIPE); 0 / 1: forced (vqb_debug_set_search_pipe)
 void set_debug_search_pipe(int v) { g_search_pipe = v; }
 static unsigned long long* g_timeline = nullptr;
@@ -666,14 +795,17 @@ static size_t hi_bytes(int64_t K, int64_t D) { return ((size_t)pad_codes(K, 128)
 static size_t lo_bytes(int64_t K, int64_t D) { return ((size_t)pad_codes(K, 128) * D * 4 + 255) & ~(size_t)255; }
 
 // which kernel configuration serves this call (0 = none: use the exact SIMT path)
-enum TcMode { TC_NONE = 0, TC_SEARCH3, TC_SEARCH1 };
+enum TcMode { TC_NONE = 0, TC_SEARCH3, TC_SEARCH1, TC_SEARCH16 };
 static TcMode tc_mode(const vqb_fwd_args* a) {
     const int64_t K = a->n_codes, D = a->dim;
     if (a->p_code) return TC_NONE;                               // parity mode: vqb_fwd_pc.cu
     if (!(a->flags & VQB_SCORE_L2)) return TC_NONE;
     if (D != 32 && D != 64 && D != 128 && D != 256) return TC_NONE;
     if (K <= 1024 && D <= 128) return TC_SEARCH3;
-    return TC_SEARCH1;
+    // one pass + candidate window + exact re-rank: fp16 operands where a row is whole 64-dimension blocks, tf32 otherwise
+    // (developer A/B: VQB_SEARCH_TF32=1 keeps the tf32 one-pass kernel)
+    static const bool tf32_only = getenv("VQB_SEARCH_TF32") != nullptr;
+    return (D % 64 == 0 && !tf32_only) ? TC_SEARCH16 : TC_SEARCH1;
 }
 
 bool forward_tensor_supported(const vqb_fwd_args* a) { return tc_mode(a) != TC_NONE; }
@@ -683,13 +815,13 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG = false>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG = false, bool F16 = false>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s) {
     const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
                         (size_t)BS * BN * 128 + (NOAUG ? 15 : 16) * BM * 8 + 1024 + 256 + 2 * BM * 4 + (NOAUG ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, NOAUG>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, NOAUG, F16>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     // PDL: this call has just launched build_operands_kernel; the prologue and the first x tile overlap it
@@ -716,21 +848,31 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
     uint8_t* tail = ws + hi_bytes(K, D) + lo_bytes(K, D);
     float* emax = reinterpret_cast<float*>(tail);
     unsigned int* stats = a->search_stats ? a->search_stats : reinterpret_cast<unsigned int*>(tail + 16);
-    VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));                  // |e|_max (atomicMax) and the re-rank counters
+    VQB_CUDA(cudaMemsetAsync(tail, 0, 256, s));                  // |e|_max / table maximum (atomicMax) and the re-rank counters
     constexpr int BN = 128;
     const int64_t Kpad = pad_codes(K, BN);
-    launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, -2.f, 1e30f, hi, mode == TC_SEARCH1 ? nullptr : lo, emax, s);
-    VQB_CHECK_LAUNCH("build_operands_kernel");
-
+    int* gexp = reinterpret_cast<int*>(tail + 32);
+    unsigned int* gmax_bits = reinterpret_cast<unsigned int*>(tail + 36);
     CUtensorMap tx, th, tl, tq;
-    int rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM);
-    if (rc) return rc;
+    int rc;
+    if (mode == TC_SEARCH16) {
+        table_max_kernel<<<(unsigned)K, 128, 0, s>>>(a->score_w, (int)D, gmax_bits, emax);
+        VQB_CHECK_LAUNCH("table_max_kernel");
+        build_f16_operands_kernel<<<(unsigned)Kpad, 128, 0, s>>>(a->score_w, (int)K, (int)D, gmax_bits, reinterpret_cast<__half*>(hi), gexp);
+        VQB_CHECK_LAUNCH("build_f16_operands_kernel");
+        if ((rc = make_tmap_2d_f16(&th, hi, (uint64_t)Kpad, (uint64_t)D, BN))) return rc;
+        tl = th;
+    } else {
+        launch_build_operands(a->score_w, a->score_b, (int)K, (int)Kpad, (int)D, -2.f, 1e30f, hi, mode == TC_SEARCH1 ? nullptr : lo, emax, s);
+        VQB_CHECK_LAUNCH("build_operands_kernel");
+        if ((rc = make_tmap_2d_f32(&th, hi, (uint64_t)Kpad, (uint64_t)(D + 32), (uint64_t)(D + 32), BN))) return rc;
+        if ((rc = make_tmap_2d_f32(&tl, lo, (uint64_t)Kpad, (uint64_t)D, (uint64_t)D, BN))) return rc;
+    }
+    if ((rc = make_tmap_2d_f32(&tx, a->x, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM))) return rc;
     if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, BM))) return rc;
-    if ((rc = make_tmap_2d_f32(&th, hi, (uint64_t)Kpad, (uint64_t)(D + 32), (uint64_t)(D + 32), BN))) return rc;
-    if ((rc = make_tmap_2d_f32(&tl, lo, (uint64_t)Kpad, (uint64_t)D, (uint64_t)D, BN))) return rc;
 
     TcP p;
-    p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.emax = emax;
+    p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.emax = emax; p.gexp = gexp;
     p.idx = (long long*)a->idx; p.q = a->new_latent;
     p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum; p.stats = stats; p.dbg = g_timeline;
     p.N = (int)N; p.K = (int)K; p.D = (int)D;
@@ -753,6 +895,12 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
         if (D == 32) return launch_tc<1, 128, 2, 8, 3, false>(tx, th, tl, tq, p, s);
         if (D == 64) return launch_tc<2, 128, 2, 4, 3, false>(tx, th, tl, tq, p, s);
         return launch_tc<4, 128, 1, 4, 3, false>(tx, th, tl, tq, p, s);
+    }
+    if (mode == TC_SEARCH16) {
+        //                                KB  BN  XS BS PASSES RESIDENT NOAUG F16
+        if (D == 64)  return launch_tc<2, 128, 2, 8, 1, false, true, true>(tx, th, tl, tq, p, s);
+        if (D == 128) return launch_tc<4, 128, 1, 8, 1, false, true, true>(tx, th, tl, tq, p, s);
+        return launch_tc<8, 128, 1, 5, 1, false, true, true>(tx, th, tl, tq, p, s);
     }
     switch (D) {
         case 32:  return launch_tc<1, 128, 2, 8, 1, false>(tx, th, tl, tq, p, s);

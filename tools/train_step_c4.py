@@ -236,6 +236,10 @@ def boundary_parity(stock, drop):
 
 
 def main():
+    # libraries (NCCL prints its version banner) must not pollute stdout: ONE JSON line there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
@@ -384,11 +388,11 @@ def main():
         res["sharded_vs_unsharded_codebook_grad_rel_err"] = rel(part, full)
         V.dist.check_exchange(cbm)
     if rank == 0:
-        print(json.dumps(res), flush=True)
+        print(json.dumps(res), file=out, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); torch.cuda.synchronize()
-        sys.stdout.flush()
+        out.flush()
         os._exit(0)
 
 
