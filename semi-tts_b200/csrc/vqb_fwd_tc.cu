@@ -232,6 +232,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint64_t* xlo_free = t_empty + 2;
     uint64_t* xr_full = xlo_free + 1;                             // [XS] F16: the raw x tile has been fetched again
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xr_full + XS);
+    // per-row index words [128] and (NOAUG) the |e|^2 staging [2][BN] behind the barriers, 16-byte aligned (float4 reads)
+    int* sAfterBars = reinterpret_cast<int*>(smem + ((reinterpret_cast<uint8_t*>(tmem_slot + 4) - smem + 15) & ~(size_t)15));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[120] = globaltimer_ns();
@@ -517,7 +519,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 uint2* sCandG = sCand;
                 // NOAUG: |e|^2 of the chunk's codes, staged by the row threads themselves (thread et <-> code), double-buffered;
                 // the value of the next chunk is fetched one iteration ahead.  Codes beyond K get +1e30 (never the minimum).
-                float* sEn = reinterpret_cast<float*>(reinterpret_cast<int*>(tmem_slot + 4) + 2 * BM);     // [2][BN]
+                float* sEn = reinterpret_cast<float*>(sAfterBars + 2 * BM);     // [2][BN]
                 float en_next = 0.f;
                 if (NOAUG) en_next = et < p.K ? __ldg(p.bias + et) : 1e30f;
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
@@ -626,7 +628,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             // ---- gather + straight-through, in place over the x tile -------------------------------------------
             // Coalesced mapping: 16 consecutive threads handle the 16 sixteen-byte chunks of one row, so the
             // codeword reads (all chunks of ONE code row) and the tile accesses are free of bank conflicts.
-            int* sIdxG = reinterpret_cast<int*>(tmem_slot + 4);
+            int* sIdxG = sAfterBars;
             sIdxG[r] = valid ? best : -1;
             if (valid) p.idx[row0 + r] = best;
             VQB_TL(11);
@@ -819,7 +821,7 @@ template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG 
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s) {
     const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
-                        (size_t)BS * BN * 128 + (NOAUG ? 15 : 16) * BM * 8 + 1024 + 256 + 2 * BM * 4 + (NOAUG ? 2 * BN * 4 : 0);
+                        (size_t)BS * BN * 128 + (NOAUG ? 15 : 16) * BM * 8 + 1024 + 320 + 2 * BM * 4 + (NOAUG ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
     auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, NOAUG, F16>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
