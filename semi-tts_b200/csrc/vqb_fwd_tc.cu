@@ -804,10 +804,13 @@ static TcMode tc_mode(const vqb_fwd_args* a) {
     if (!(a->flags & VQB_SCORE_L2)) return TC_NONE;
     if (D != 32 && D != 64 && D != 128 && D != 256) return TC_NONE;
     if (K <= 1024 && D <= 128) return TC_SEARCH3;
-    // one pass + candidate window + exact re-rank: fp16 operands where a row is whole 64-dimension blocks, tf32 otherwise
-    // (developer A/B: VQB_SEARCH_TF32=1 keeps the tf32 one-pass kernel)
-    static const bool tf32_only = getenv("VQB_SEARCH_TF32") != nullptr;
-    return (D % 64 == 0 && !tf32_only) ? TC_SEARCH16 : TC_SEARCH1;
+    // one pass + candidate window + exact re-rank.  fp16 operands at D = 256, where the tf32 kernel is bound by the codebook
+    // bytes in flight (K = 8192: 9.6 vs 11.5 ms, 459 vs 381 TFLOP/s); tf32 at D <= 128, where the single epilogue warpgroup is
+    // the bound and the in-place conversion + second fetch of the x tile only add to it (K = 8192, D = 64: 7.7 vs 6.6 ms) --
+    // profiles/r2_sweep_f16_vs_tf32.txt.  Developer A/B: VQB_SEARCH_TF32=1 / VQB_SEARCH_F16=1 force one or the other.
+    static const bool tf32_only = getenv("VQB_SEARCH_TF32") != nullptr, f16_all = getenv("VQB_SEARCH_F16") != nullptr;
+    if (tf32_only || D % 64 != 0) return TC_SEARCH1;
+    return (D == 256 || f16_all) ? TC_SEARCH16 : TC_SEARCH1;
 }
 
 bool forward_tensor_supported(const vqb_fwd_args* a) { return tc_mode(a) != TC_NONE; }
