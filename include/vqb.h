@@ -116,6 +116,13 @@ typedef struct vqb_fwd_args {
     const void* operand_cache;   /* from vqb_assemble_table (L2 score only), or NULL                    */
     void*    workspace;          /* vqb_forward_workspace() bytes, or NULL if that is 0                 */
     size_t   workspace_bytes;
+    const int64_t* row_lengths;  /* [n_rows / frames_per_utt] or NULL.  Length-aware rows (the padded
+                                    batches of src/vqvae.py:106-126,259-271): frame s of utterance b is a PAD row when
+                                    s >= row_lengths[b].  Pad rows are not searched: their p_code / new_latent rows are
+                                    zero, their index is 0, they are not counted in hist; tiles that hold only pad rows
+                                    are neither loaded nor computed.  Valid rows are bit-identical to the dense call.
+                                    Parity-mode tensor-core route only (p_code given, K <= 64, D in {32,64}). */
+    int64_t  frames_per_utt;     /* S; required (> 0, dividing n_rows) when row_lengths is given        */
 } vqb_fwd_args;
 
 VQB_API int vqb_forward_workspace(const vqb_fwd_args* args, size_t* bytes);
@@ -198,6 +205,9 @@ typedef struct vqb_bwd_args {
     const void* operand_cache;   /* from vqb_assemble_table (L2 score only), or NULL */
     void*  workspace;
     size_t workspace_bytes;
+    const int64_t* row_lengths;  /* as in vqb_fwd_args: pad rows contribute nothing (their dx rows are zero, whatever g_p / g_q
+                                    hold there); vqb_bwd_pcode_kernel route only */
+    int64_t  frames_per_utt;
     const vqb_bwd_tail* tail;    /* optional fused tail (see above); NULL = plain accumulate-into semantics.  Only
                                     taken on the route vqb_backward_kernel_name() reports as "vqb_bwd_pcode_kernel"
                                     with VQB_SCORE_L2; otherwise vqb_backward fails with VQB_ERR_INVALID */

@@ -134,6 +134,12 @@ static int validate_fwd(const vqb_fwd_args* a) {
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->new_latent) ||
         (a->p_code && !aligned16(a->p_code)))
         return invalid("vqb_forward: tensor pointers must be 16-byte aligned");
+    if (a->row_lengths) {
+        if (a->frames_per_utt <= 0 || a->n_rows % a->frames_per_utt != 0)
+            return invalid("vqb_forward: row_lengths needs frames_per_utt > 0 dividing n_rows");
+        if (!((a->flags & VQB_TENSOR_CORES) && forward_pcode_supported(a)))
+            return invalid("vqb_forward: row_lengths is served by the parity-mode tensor-core kernel only (p_code, K <= 64, D in {32, 64})");
+    }
     return VQB_OK;
 }
 
@@ -176,6 +182,12 @@ static int validate_bwd(const vqb_bwd_args* a) {
     if (a->n_rows == 0) return VQB_OK;
     if (!a->idx) return invalid("vqb_backward: idx is required");
     if (!a->g_p && !a->g_q) return invalid("vqb_backward: at least one of g_p / g_q is required");
+    if (a->row_lengths) {
+        if (a->frames_per_utt <= 0 || a->n_rows % a->frames_per_utt != 0)
+            return invalid("vqb_backward: row_lengths needs frames_per_utt > 0 dividing n_rows");
+        if (!backward_pcode_supported(a))
+            return invalid("vqb_backward: row_lengths is served by the vqb_bwd_pcode_kernel route only");
+    }
     return VQB_OK;
 }
 

@@ -53,6 +53,9 @@ struct BwdPcP {
     int N, K, n_real, num_tiles;
     int t_first;              // L2 + fused tail: columns d >= t_first are also stored transposed (record plane 1), else 64
     int pg_bytes, stage_bytes;
+    const long long* lens;    // [N / S] valid frames per utterance, or NULL (length-aware rows, vqb_bwd_args.row_lengths)
+    int S;
+    float* dx;                // [N][64] (pad-only tiles are zero-filled directly)
     unsigned flags;
 };
 
@@ -138,14 +141,43 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             tma_load_2d(sG + TBLK, &tm_g, 32, row0, in_full);
         }
     };
-    if (r == 0 && n_my > 0) issue_loads(0);
-    VQB_BTL(1);
-
-    for (int it = 0; it < n_my; ++it) {
-        const uint32_t ph = it & 1;
+    // length-aware rows: does tile `it` of this CTA hold any real frame?  (a tile spans at most TR / S + 2 utterances)
+    auto tile_live = [&](int it) -> bool {
+        if (!p.lens) return true;
         const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TR;
         const int rows = min(TR, p.N - row0);
-        const bool valid = r < rows;
+        for (int b = row0 / p.S; b * p.S < row0 + rows; ++b) {
+            const long long lo = max(row0, b * p.S), hi = min((long long)(row0 + rows), (long long)b * p.S + __ldg(p.lens + b));
+            if (hi > lo) return true;
+        }
+        return false;
+    };
+    auto next_live = [&](int it) -> int {           // first live tile of this CTA at or after `it` (n_my if none)
+        while (it < n_my && !tile_live(it)) ++it;
+        return it;
+    };
+    {
+        const int first = next_live(0);
+        if (r == 0 && first < n_my) issue_loads(first);
+    }
+    VQB_BTL(1);
+
+    int lt = 0;                                      // live tiles processed so far (drives the mbarrier phases)
+    for (int it = 0; it < n_my; ++it) {
+        const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TR;
+        const int rows = min(TR, p.N - row0);
+        if (!tile_live(it)) {
+            // only padding: nothing is loaded or computed; the dx rows are zero
+            float4* d4 = reinterpret_cast<float4*>(p.dx + (size_t)row0 * D);
+            for (int i = r; i < rows * (D / 4); i += BP_THREADS) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const uint32_t ph = lt & 1;
+        bool valid = r < rows;
+        if (p.lens && valid) {
+            const int b = (row0 + r) / p.S;
+            valid = (row0 + r) - b * p.S < __ldg(p.lens + b);       // a pad row inside a live tile contributes nothing
+        }
         const bool real = valid && (p.n_real <= 0 || row0 + r < p.n_real);
         // the table image, on its way to shared memory through registers (it lands behind the C tiles once the staging
         // area has been consumed)
@@ -395,6 +427,10 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         tcgen05_fence_after();
         VQB_BTL(6);
         if (r < TR) {
+            if (p.lens && !valid) {
+#pragma unroll
+                for (int d = 0; d < 64; ++d) gr[d] = 0.f;          // pad row: dx = 0 whatever g_q holds there
+            }
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -427,9 +463,10 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             tma_store_2d(&tm_dx, sG, 0, row0);
             tma_store_2d(&tm_dx, sG + TBLK, 32, row0);
             tma_store_commit();
-            if (it + 1 < n_my) {
+            const int nit = next_live(it + 1);
+            if (nit < n_my) {
                 // next tile: p_code / g_p / x may land now; g_q only once dx has left its tile
-                const int nrow0 = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * TR;
+                const int nrow0 = ((int)blockIdx.x + nit * (int)gridDim.x) * TR;
                 const int nrows = min(TR, p.N - nrow0);
                 const uint32_t bulk = (uint32_t)(nrows * K * 4) & ~15u;
                 mbar_arrive_expect_tx(in_full, 2 * bulk + TILE + (have_gq ? TILE : 0));
@@ -449,6 +486,7 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
         }
         VQB_BTL(8);
+        ++lt;
     }
     __syncthreads();                                               // dx of the last tile has left shared memory (thread 0 waited)
     VQB_BTL(9);
@@ -568,6 +606,7 @@ int launch_backward_pcode(const vqb_bwd_args* a, cudaStream_t s) {
     p.flags = a->flags;
     p.t_first = (a->tail && l2) ? 64 - (int)a->tail->dim_attr : 64;
     p.pg_bytes = p.stage_bytes = 0;
+    p.lens = (const long long*)a->row_lengths; p.S = (int)a->frames_per_utt; p.dx = a->dx;
     const int KP = (int)((K + 15) / 16 * 16);
     if (l2) {
         switch (KP) {

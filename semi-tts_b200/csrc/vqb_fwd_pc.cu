@@ -38,11 +38,14 @@ struct PcP {
     const float* temp;         // [1]
     const uint8_t* img;        // operand image of the score table (vqb_f16x2.cuh)
     float* pcode;
+    float* q;
     long long* idx;
     unsigned long long* hist;
     double* sqerr;
     unsigned int* stats;       // [0] += rows re-ranked in exact fp32 (may be NULL)
     unsigned long long* dbg;   // optional timeline buffer (vqb_debug_set_timeline), NULL in production
+    const long long* lens;     // [N / S] valid frames per utterance, or NULL (length-aware rows, vqb_fwd_args.row_lengths)
+    int S;                     // frames per utterance
     int N, K, num_tiles;
     int se_bytes;              // shared-memory bytes of the table region (image, later the fp32 gather table)
     unsigned flags;
@@ -120,12 +123,34 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     float temp_raw = 1.f;
     constexpr uint32_t IDESC = umma_idesc(0u, PM, KP);
 
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
+    uint32_t it = 0;                                // tiles this CTA has COMPUTED (drives the mbarrier phases)
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int row0 = tile * PM;
         const int rows = min(PM, p.N - row0);
-        const bool valid = r < rows;
+        bool valid = r < rows;
+        bool live = valid;                          // length-aware rows: this row is a real frame, not padding
+        if (p.lens) {
+            // does the tile hold any real frame?  (a tile spans at most PM / S + 2 utterances)
+            bool any = false;
+            for (int b = row0 / p.S; b * p.S < row0 + rows; ++b) {
+                const long long lo = max(row0, b * p.S), hi = min((long long)(row0 + rows), (long long)b * p.S + __ldg(p.lens + b));
+                any = any || hi > lo;
+            }
+            if (!any) {
+                // only padding: nothing is loaded or computed; the outputs of these rows are zero
+                float4* q4 = reinterpret_cast<float4*>(p.q + (size_t)row0 * D);
+                for (int i = r; i < rows * (D / 4); i += PM) q4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float* pc = p.pcode + (size_t)row0 * K;
+                for (int i = r; i < rows * K; i += PM) pc[i] = 0.f;
+                if (valid) p.idx[row0 + r] = 0;
+                continue;
+            }
+            if (valid) {
+                const int b = (row0 + r) / p.S;
+                live = (row0 + r) - b * p.S < __ldg(p.lens + b);
+            }
+        }
+        const uint32_t ph = it & 1;
         // ---- loads: the x tile (older than the previous kernel), then -- behind pdl_wait -- the table image ---------
         if (r == 0) {
             mbar_arrive_expect_tx(x_full, KB * PBLK);
@@ -286,7 +311,8 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         int best = 0;
 #pragma unroll
         for (int k = KP - 1; k >= 0; --k) best = v[k] >= 1.f ? k : best;
-        const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+        const float inv = live || !valid ? 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3])) : 0.f;    // pad rows: p_code = 0
+        if (valid && !live) best = 0;
         {
             float* prow = sP + r * KO;
 #pragma unroll
@@ -296,8 +322,8 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         if (valid) p.idx[row0 + r] = best;
         if (p.hist) {
             // warp-aggregated histogram: one atomic per distinct code per warp
-            const unsigned peers = __match_any_sync(0xffffffffu, valid ? best : -1);
-            if (valid && lane == (__ffs(peers) - 1)) atomicAdd(p.hist + best, (unsigned long long)__popc(peers));
+            const unsigned peers = __match_any_sync(0xffffffffu, live ? best : -1);
+            if (live && lane == (__ffs(peers) - 1)) atomicAdd(p.hist + best, (unsigned long long)__popc(peers));
         }
         VQB_PTL(6);
         mbar_wait(t_full, ph);                      // the gather table is complete in shared memory
@@ -321,7 +347,8 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                         o.z = __fsub_rn(__fadd_rn(x2, cv.z), x2); o.w = __fsub_rn(__fadd_rn(x3, cv.w), x3);
                         if (skip) o = make_float4(x0, x1, x2, x3);                      // (:142)
                     }
-                    if (want_se && valid) {
+                    if (valid && !live) o = make_float4(0.f, 0.f, 0.f, 0.f);               // pad row
+                    if (want_se && live) {
                         const float d0 = x0 - cv.x, d1 = x1 - cv.y, d2 = x2 - cv.z, d3 = x3 - cv.w;
                         se_acc = fmaf(d0, d0, se_acc); se_acc = fmaf(d1, d1, se_acc);
                         se_acc = fmaf(d2, d2, se_acc); se_acc = fmaf(d3, d3, se_acc);
@@ -365,6 +392,7 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         VQB_PTL(8);
         if (tile + (int)gridDim.x < p.num_tiles) __syncthreads();       // another tile follows: the buffers are free
+        ++it;
     }
     if (p.sqerr) {
         se_acc = warp_sum(se_acc);
@@ -461,9 +489,10 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     if ((rc = make_tmap_2d_f32(&tq, a->new_latent, (uint64_t)N, (uint64_t)D, (uint64_t)D, 32))) return rc;   // one warp's slab per store
     PcP p;
     p.x = a->x; p.table = a->score_w; p.gtab = a->gather_table; p.bias = a->score_b; p.temp = a->temp; p.img = img;
-    p.pcode = a->p_code; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
+    p.pcode = a->p_code; p.q = a->new_latent; p.idx = (long long*)a->idx; p.hist = (unsigned long long*)a->hist; p.sqerr = a->sq_err_sum;
     p.stats = a->search_stats; p.dbg = get_debug_timeline();
     p.N = (int)N; p.K = (int)K; p.num_tiles = (int)ceil_div(N, PM); p.se_bytes = 0; p.flags = a->flags;
+    p.lens = (const long long*)a->row_lengths; p.S = (int)a->frames_per_utt;
     // PDL when the kernel enqueued immediately before is ours: the image build above, or (the caller vouches,
     // VQB_AFTER_ASSEMBLE) the table assembly
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);

@@ -144,7 +144,12 @@ class L2Embedding(_QuantizerBase):
             return VF.lookup_nograd(self._nograd, txt, self.learnable_table, *self._attr_params())
         return VF.codebook_lookup(txt, self.learnable_table, *self._attr_params(), tail=self.fused_tail)
 
-    def forward(self, enc_embs, first_n_real_mel=0):
+    def forward(self, enc_embs, first_n_real_mel=0, lengths=None):
+        """`lengths` (extension; None = the reference's behaviour): valid encoder frames per utterance of
+        the zero-padded batch (src/vqvae.py:106-126,259-271).  Frames beyond them are PAD rows: they are not searched, their
+        p_code / new_latent rows are zero, they take no part in the histogram or in any gradient, and tiles that hold
+        nothing else are skipped; valid rows are bit-identical to the dense call.  (With `--actual_len` the reference's CTC
+        already ignores those frames, bin/train_vqvae.py:436-439; the unpaired branch keeps using every frame.)"""
         B, S, _ = enc_embs.shape
         # numpy's global RNG is consumed exactly when the reference consumes it (src/embed.py:140)
         skip = bool(self.training and self.skip_prob > 0 and np.random.rand() < self.skip_prob)
@@ -153,14 +158,15 @@ class L2Embedding(_QuantizerBase):
         if not torch.is_grad_enabled() and not want_losses:
             # bin/train_vqvae.py:343 (validate) and the encode path: nothing to differentiate, nothing to save
             p_code, new_latent, idx = VF.forward_nograd(self._nograd, enc_embs, self.learnable_table, attr, pw, pb, self.temp,
-                                                        skip, not self.fused_search, self._hist(enc_embs), self.tensor_cores)
+                                                        skip, not self.fused_search, self._hist(enc_embs), self.tensor_cores,
+                                                        lengths)
             self.last_idx = idx
             return p_code, new_latent, 0, 0
         p_code, new_latent, idx, vq, commit = VF.vq_l2(
             enc_embs, self.learnable_table, attr, pw, pb, self.temp, stop_grad=self.stop_grad, skip=skip,
             n_real_rows=first_n_real_mel * S if first_n_real_mel > 0 else 0,
             want_pcode=not self.fused_search, hist=self._hist(enc_embs), want_losses=want_losses,
-            tensor_cores=self.tensor_cores, tail=self.fused_tail)
+            tensor_cores=self.tensor_cores, tail=self.fused_tail, lengths=lengths)
         self.last_idx = idx
         return (p_code, new_latent) + self._losses(vq, commit)
 

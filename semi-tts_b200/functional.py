@@ -103,8 +103,18 @@ def _table_backward(dtable, table, colsum, phn_attr, Da, tail=None):
     return d_learn, d_w, d_b
 
 
+def _lengths_arg(lengths, n_utts, dev):
+    """[B] int64 on `dev` (accepts a CPU / int32 tensor or a list), checked against the batch"""
+    if lengths is None:
+        return None
+    t = torch.as_tensor(lengths)
+    if t.numel() != n_utts:
+        raise RuntimeError("semi-tts_b200: `lengths` must hold one entry per utterance (%d), got %d" % (n_utts, t.numel()))
+    return t.to(device=dev, dtype=torch.int64).contiguous()
+
+
 def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, hist, want_sqerr,
-                 score_w_bf16=None, search_stats=None, operand_cache=None):
+                 score_w_bf16=None, search_stats=None, operand_cache=None, lengths=None, frames=0):
     lib = _lib.load()
     N, D = x2d.shape
     K = score_w.shape[0]
@@ -122,6 +132,7 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
     a.temp, a.p_code, a.idx, a.new_latent = ptr(temp), ptr(p_code), ptr(idx), ptr(q)
     a.hist, a.sq_err_sum, a.search_stats = ptr(hist), ptr(sq), ptr(search_stats)
     a.operand_cache = ptr(operand_cache)
+    a.row_lengths, a.frames_per_utt = ptr(lengths), (frames if lengths is not None else 0)
     with torch.cuda.device(dev):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
@@ -167,7 +178,7 @@ class NoGradCache:
         return self.table, self.enorm, self.image
 
 
-def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, want_pcode, hist, tensor_cores):
+def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, want_pcode, hist, tensor_cores, lengths=None):
     """L2 quantizer forward without autograd (src/embed.py:105-147 under torch.no_grad()).
     Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S])."""
     _require(x, "enc_embs")
@@ -198,6 +209,8 @@ def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, wa
     a.flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SKIP if skip else 0) | (_lib.TENSOR_CORES if tensor_cores else 0)
     a.n_rows = N
     a.x, a.temp, a.p_code, a.idx, a.new_latent, a.hist = ptr(x2d), ptr(temp), ptr(p_code), ptr(idx), ptr(q), ptr(hist)
+    lens = _lengths_arg(lengths, B, dev)
+    a.row_lengths, a.frames_per_utt = ptr(lens), (S if lens is not None else 0)
     with _on(dev):
         if not (use_image and image is not None):
             # shapes outside the cached-image route (fused search, CUDA-core kernels) may need scratch: sized once per module
@@ -269,7 +282,7 @@ def _exchange_timeout_ms():
 
 
 def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp, p_code, idx, g_p, g_q,
-                  want_dx_buffer, separate_gather, operand_cache=None, tail=None, phn_attr=None, Da=0):
+                  want_dx_buffer, separate_gather, operand_cache=None, tail=None, phn_attr=None, Da=0, lengths=None, frames=0):
     """Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None, flat or None).
     `flat` is set when the fused tail ran: [d_learnable | d_proj_w | d_proj_b], already summed over the group."""
     lib = _lib.load()
@@ -284,6 +297,7 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.x, a.score_w, a.score_b, a.gather_table, a.temp = ptr(x2d), ptr(score_w), ptr(score_b), ptr(gather_table), ptr(temp)
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.operand_cache = ptr(operand_cache)
+    a.row_lengths, a.frames_per_utt = ptr(lengths), (frames if lengths is not None else 0)
     use_tail = bool(tail is not None and tail.enabled and (flags & _lib.SCORE_L2) and not separate_gather
                     and (lib.vqb_backward_kernel_name(ctypes.byref(a)) == b"vqb_bwd_pcode_kernel"
                          or (N == 0 and tail.exchange is not None)))      # an empty shard still joins its peers' exchange
@@ -341,11 +355,12 @@ def _loss_backward(x2d, table, idx, g_vq, g_commit, dx, dx_accumulate, dtable):
 
 class _Cfg:
     """Per-call options (plain Python, not a tensor)."""
-    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores", "tail")
+    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores", "tail", "lengths")
 
     def __init__(self, stop_grad=True, skip=False, n_real_rows=0, want_pcode=True, hist=None,
-                 want_losses=False, tensor_cores=True, tail=None):
+                 want_losses=False, tensor_cores=True, tail=None, lengths=None):
         self.tail = tail
+        self.lengths = lengths
         self.stop_grad, self.skip, self.n_real_rows = bool(stop_grad), bool(skip), int(n_real_rows)
         self.want_pcode, self.hist, self.want_losses = bool(want_pcode), hist, bool(want_losses)
         self.tensor_cores = bool(tensor_cores)
@@ -384,8 +399,12 @@ class _VQL2(torch.autograd.Function):
         if want_cache:
             # only kernels (the assembly above, at most a one-element fill) sit between here and the forward kernel
             flags |= _lib.AFTER_ASSEMBLE
+        lens = _lengths_arg(cfg.lengths, B, x2d.device)
+        if lens is not None and (cfg.want_losses or not cfg.want_pcode):
+            raise RuntimeError("semi-tts_b200: `lengths` is served by the parity-mode route only (p_code on, no loss extensions)")
         p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
-                                          cfg.want_losses, tbf, None, cache)
+                                          cfg.want_losses, tbf, None, cache, lens, S)
+        ctx.lens = lens
         ctx.op_cache = cache
         ctx.set_materialize_grads(False)                    # an unused output must arrive as None, not zeros
         ctx.cfg, ctx.shape = cfg, (B, S, D, K)
@@ -431,15 +450,18 @@ class _VQL2(torch.autograd.Function):
                 d_w = torch.zeros(K, D, device=dev, dtype=torch.float32)
         elif g_p2 is None and g_q2 is None:
             dx, d_w = None, torch.zeros(K, D, device=dev, dtype=torch.float32)
-        elif g_p2 is None and cfg.stop_grad:
+        elif g_p2 is None and cfg.stop_grad and ctx.lens is None:
             # scatter-only: dx = g_q, the straight-through identity, returned as the same tensor (zero bytes)
             _, d_w, _, _, _, _ = _run_backward(flags & ~_lib.TEMP_GRAD, cfg.n_real_rows, x2d, table, enorm, table, temp,
                                                None, idx, None, g_q2, False, False)
             dx = g_q2
         else:
+            if ctx.lens is not None and g_p2 is None:
+                # (the tensor-core backward is keyed on g_p; a step that only back-propagates through new_latent gets a zero g_p)
+                g_p2 = torch.zeros(N, K, device=dev, dtype=torch.float32)
             dx, d_w, colsum, _, d_temp, flat = _run_backward(
                 flags, cfg.n_real_rows, x2d, table, enorm, table, temp, p_code, idx, g_p2, g_q2, True, False,
-                ctx.op_cache, tail=None if have_loss else cfg.tail, phn_attr=phn_attr, Da=ctx.Da)
+                ctx.op_cache, tail=None if have_loss else cfg.tail, phn_attr=phn_attr, Da=ctx.Da, lengths=ctx.lens, frames=S)
         if flat is not None:
             # fused tail: table backward (and the sum over GPUs) already done behind the main kernel
             Da, A = (ctx.Da, phn_attr.shape[1]) if phn_attr is not None else (0, 0)
@@ -465,10 +487,10 @@ class _VQL2(torch.autograd.Function):
 
 
 def vq_l2(x, learnable_table, phn_attr, proj_w, proj_b, temp, stop_grad=True, skip=False, n_real_rows=0,
-          want_pcode=True, hist=None, want_losses=False, tensor_cores=True, tail=None):
+          want_pcode=True, hist=None, want_losses=False, tensor_cores=True, tail=None, lengths=None):
     """L2 quantizer (src/embed.py:105-147).
     Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S] int64, vq_loss or None, commit_loss or None)."""
-    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores, tail)
+    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores, tail, lengths)
     return _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
 
 

@@ -631,3 +631,54 @@ def test_parity_forward_resolves_near_ties_in_exact_fp32():
         assert torch.equal(q_t, q_e)
         assert torch.equal(idx_t, p_t.argmax(-1))
         assert rel_err(p_t.cpu().numpy(), p_e.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("B,S", [(6, 400), (5, 77), (3, 128)])
+def test_length_aware_rows_match_the_dense_call_on_valid_frames(B, S):
+    """SURVEY 8f rank 4 (src/vqvae.py:106-126,259-271): `lengths` marks the zero-padded tail of every utterance.  Valid frames
+    must be bit-identical to the dense call; pad frames give zero rows, take no part in the histogram and in no gradient;
+    the gradients equal those of the dense call with the upstream gradients zeroed on the pad frames (and the fp64 oracle's)."""
+    g = load_golden("l2_attr_stopgrad")
+    K, D = 43, 64
+    gen = torch.Generator().manual_seed(B * 1000 + S)
+    x = torch.randn(B, S, D, generator=gen).cuda()
+    gp = torch.randn(B, S, K, generator=gen).cuda()
+    gq = torch.randn(B, S, D, generator=gen).cuda()
+    lens = torch.randint(1, S + 1, (B,), generator=gen)
+    lens[0] = S
+    if B > 2:
+        lens[1] = 3                                           # a nearly empty utterance: whole tiles of padding
+    mask = (torch.arange(S)[None, :] < lens[:, None]).cuda()
+
+    def run(lengths, gp_, gq_):
+        m = build_module(g, "l2")
+        xi = x.clone().requires_grad_(True)
+        p, q, _, _ = m(xi, 0, lengths=lengths) if lengths is not None else m(xi)
+        torch.autograd.backward([p, q], [gp_, gq_])
+        return dict(p=p.detach(), q=q.detach(), idx=m.last_idx.clone(), dx=xi.grad.clone(), hist=m.usage.counts.clone(),
+                    dl=m.learnable_table.grad.clone(), dw=m.proj_attr.weight.grad.clone(), db=m.proj_attr.bias.grad.clone())
+
+    dense = run(None, gp * mask[..., None], gq * mask[..., None])
+    la = run(lens, gp, gq)                                    # garbage upstream gradients on the pad frames must not matter
+    assert torch.equal(la["p"][mask], dense["p"][mask]) and torch.equal(la["q"][mask], dense["q"][mask])
+    assert torch.equal(la["idx"][mask], dense["idx"][mask])
+    assert float(la["p"][~mask].abs().sum()) == 0.0 and float(la["q"][~mask].abs().sum()) == 0.0
+    assert int(la["idx"][~mask].abs().sum()) == 0
+    assert float(la["dx"][~mask].abs().sum()) == 0.0
+    assert torch.equal(la["hist"], torch.bincount(dense["idx"][mask].flatten(), minlength=K))
+    for k in ("dx", "dl", "dw", "db"):
+        assert torch.allclose(la[k], dense[k], rtol=2e-6, atol=2e-6 * float(dense[k].abs().max())), k
+    # fp64 oracle on the dense problem with masked upstream gradients
+    E = _table64(g)
+    f = O.l2_forward(x.cpu().numpy(), E, 1.0)
+    mk = mask.cpu().numpy()
+    ob = O.l2_backward(x.cpu().numpy(), E, 1.0, f["p_code"], f["idx"], (gp.cpu().numpy() * mk[..., None]),
+                       (gq.cpu().numpy() * mk[..., None]))
+    assert rel_err(la["dx"].cpu().numpy(), ob["dx"]) < TOL
+    tb = O.table_backward(ob["dtable"], g["sd.phn_attr.weight"], g["sd.proj_attr.weight"])
+    assert rel_err(la["dl"].cpu().numpy(), tb["d_learnable"]) < TOL
+    # the no-grad path takes lengths too
+    m = build_module(g, "l2").eval()
+    with torch.no_grad():
+        p2, q2, _, _ = m(x, 0, lengths=lens)
+    assert torch.equal(p2, la["p"]) and torch.equal(q2, la["q"])
