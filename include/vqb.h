@@ -122,7 +122,11 @@ typedef struct vqb_fwd_args {
                                     zero, their index is 0, they are not counted in hist; tiles that hold only pad rows
                                     are neither loaded nor computed.  Valid rows are bit-identical to the dense call.
                                     Parity-mode tensor-core route only (p_code given, K <= 64, D in {32,64}). */
-    int64_t  frames_per_utt;     /* S; required (> 0, dividing n_rows) when row_lengths is given        */
+    int64_t  frames_per_utt;     /* S; required (> 0, dividing n_rows) when row_lengths or ctc_logp is given */
+    float*   ctc_logp;           /* [S, B, K] or NULL: log(p_code + ctc_eps) transposed to the layout nn.CTCLoss consumes,
+                                    written by the forward epilogue itself (replaces `(p + EPS).transpose(0,1).log()`,
+                                    bin/train_vqvae.py:430-432 and :236).  Parity-mode tensor-core route. */
+    float    ctc_eps;            /* EPS of bin/train_vqvae.py:18 (1e-10) */
 } vqb_fwd_args;
 
 VQB_API int vqb_forward_workspace(const vqb_fwd_args* args, size_t* bytes);
@@ -208,6 +212,11 @@ typedef struct vqb_bwd_args {
     const int64_t* row_lengths;  /* as in vqb_fwd_args: pad rows contribute nothing (their dx rows are zero, whatever g_p / g_q
                                     hold there); vqb_bwd_pcode_kernel route only */
     int64_t  frames_per_utt;
+    const float* g_logp;         /* [S, B, K] or NULL: upstream gradient of the forward's ctc_logp output.  Folded into the
+                                    softmax backward: G = g_p + g_logp^T / (p_code + ctc_eps), staged row by row by the kernel
+                                    itself -- no [N, K] gradient tensor is materialised.  Give EITHER g_p or g_logp (g_p may be
+                                    NULL then); vqb_bwd_pcode_kernel route, frames_per_utt required. */
+    float    ctc_eps;
     const vqb_bwd_tail* tail;    /* optional fused tail (see above); NULL = plain accumulate-into semantics.  Only
                                     taken on the route vqb_backward_kernel_name() reports as "vqb_bwd_pcode_kernel"
                                     with VQB_SCORE_L2; otherwise vqb_backward fails with VQB_ERR_INVALID */

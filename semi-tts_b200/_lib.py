@@ -26,7 +26,7 @@ class FwdArgs(ctypes.Structure):
                 ("x", _p), ("score_w", _p), ("score_b", _p), ("score_w_bf16", _p), ("gather_table", _p),
                 ("temp", _p), ("p_code", _p), ("idx", _p), ("new_latent", _p), ("hist", _p),
                 ("sq_err_sum", _p), ("search_stats", _p), ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t),
-                ("row_lengths", _p), ("frames_per_utt", ctypes.c_int64)]
+                ("row_lengths", _p), ("frames_per_utt", ctypes.c_int64), ("ctc_logp", _p), ("ctc_eps", ctypes.c_float)]
 
 
 class BwdTail(ctypes.Structure):
@@ -43,7 +43,7 @@ class BwdArgs(ctypes.Structure):
                 ("p_code", _p), ("idx", _p), ("g_p", _p), ("g_q", _p),
                 ("dx", _p), ("d_score_w", _p), ("colsum", _p), ("d_gather", _p), ("d_temp", _p),
                 ("operand_cache", _p), ("workspace", _p), ("workspace_bytes", ctypes.c_size_t),
-                ("row_lengths", _p), ("frames_per_utt", ctypes.c_int64),
+                ("row_lengths", _p), ("frames_per_utt", ctypes.c_int64), ("g_logp", _p), ("ctc_eps", ctypes.c_float),
                 ("tail", ctypes.POINTER(BwdTail))]
 
 

@@ -134,11 +134,11 @@ static int validate_fwd(const vqb_fwd_args* a) {
     if (!aligned16(a->x) || !aligned16(a->score_w) || !aligned16(a->gather_table) || !aligned16(a->new_latent) ||
         (a->p_code && !aligned16(a->p_code)))
         return invalid("vqb_forward: tensor pointers must be 16-byte aligned");
-    if (a->row_lengths) {
+    if (a->row_lengths || a->ctc_logp) {
         if (a->frames_per_utt <= 0 || a->n_rows % a->frames_per_utt != 0)
-            return invalid("vqb_forward: row_lengths needs frames_per_utt > 0 dividing n_rows");
+            return invalid("vqb_forward: row_lengths / ctc_logp need frames_per_utt > 0 dividing n_rows");
         if (!((a->flags & VQB_TENSOR_CORES) && forward_pcode_supported(a)))
-            return invalid("vqb_forward: row_lengths is served by the parity-mode tensor-core kernel only (p_code, K <= 64, D in {32, 64})");
+            return invalid("vqb_forward: row_lengths / ctc_logp are served by the parity-mode tensor-core kernel only (p_code, K <= 64, D in {32, 64})");
     }
     return VQB_OK;
 }
@@ -181,12 +181,13 @@ static int validate_bwd(const vqb_bwd_args* a) {
     if (rc) return rc;
     if (a->n_rows == 0) return VQB_OK;
     if (!a->idx) return invalid("vqb_backward: idx is required");
-    if (!a->g_p && !a->g_q) return invalid("vqb_backward: at least one of g_p / g_q is required");
-    if (a->row_lengths) {
+    if (!a->g_p && !a->g_q && !a->g_logp) return invalid("vqb_backward: at least one of g_p / g_q / g_logp is required");
+    if (a->g_p && a->g_logp) return invalid("vqb_backward: give either g_p or g_logp (add the two upstream with vqb_ctc_logp_backward)");
+    if (a->row_lengths || a->g_logp) {
         if (a->frames_per_utt <= 0 || a->n_rows % a->frames_per_utt != 0)
-            return invalid("vqb_backward: row_lengths needs frames_per_utt > 0 dividing n_rows");
+            return invalid("vqb_backward: row_lengths / g_logp need frames_per_utt > 0 dividing n_rows");
         if (!backward_pcode_supported(a))
-            return invalid("vqb_backward: row_lengths is served by the vqb_bwd_pcode_kernel route only");
+            return invalid("vqb_backward: row_lengths / g_logp are served by the vqb_bwd_pcode_kernel route only");
     }
     return VQB_OK;
 }
@@ -198,7 +199,7 @@ extern "C" int vqb_backward_workspace(const vqb_bwd_args* a, size_t* bytes) {
     if (rc) return rc;
     if (a->n_rows > 0) {
         *bytes = backward_pcode_workspace(a);
-        if (!a->g_p && (a->flags & VQB_STOP_GRAD)) *bytes = scatter_workspace_bytes(a->n_rows, a->n_codes, a->dim);
+        if (!a->g_p && !a->g_logp && (a->flags & VQB_STOP_GRAD)) *bytes = scatter_workspace_bytes(a->n_rows, a->n_codes, a->dim);
         else if (backward_generic_needed(a)) *bytes = backward_generic_workspace(a);
     }
     return VQB_OK;
@@ -223,7 +224,7 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
     const bool skip = a->flags & VQB_SKIP;
     const size_t nd_bytes = (size_t)a->n_rows * a->dim * sizeof(float);
 
-    if (!a->g_p && stop_grad) {
+    if (!a->g_p && !a->g_logp && stop_grad) {
         // scatter-only backward: nothing reaches the softmax route.
         //   L2:     dx = g_q (straight-through identity; zero bytes when the caller aliases it)
         //   LINEAR: dx = 0   (no path from new_latent to x with stop_grad, src/embed.py:194-197)
@@ -266,7 +267,7 @@ extern "C" int vqb_backward(const vqb_bwd_args* a, void* stream) {
 
 extern "C" const char* vqb_backward_kernel_name(const vqb_bwd_args* a) {
     if (validate_bwd(a) != VQB_OK) return "invalid";
-    if (!a->g_p && (a->flags & VQB_STOP_GRAD)) return "scatter_hist_kernel";
+    if (!a->g_p && !a->g_logp && (a->flags & VQB_STOP_GRAD)) return "scatter_hist_kernel";
     if (backward_pcode_supported(a)) return "vqb_bwd_pcode_kernel";
     if (backward_generic_needed(a)) return "bwdg_dx_kernel";
     return "vqb_bwd_simt_kernel";

@@ -53,6 +53,10 @@ struct BwdPcP {
     int N, K, n_real, num_tiles;
     int t_first;              // L2 + fused tail: columns d >= t_first are also stored transposed (record plane 1), else 64
     int pg_bytes, stage_bytes;
+    const float* glogp;       // [S][B][K] upstream gradient of log(p_code + eps), or NULL (then gp is given)
+    float eps;
+    int gl_rb;                // glogp by TMA: rows per box (8 or 32; needs S % gl_rb == 0); 0 = staged with cp.async
+    int gl_ld;                // row stride of the staged g_logp rows in shared memory, floats (TMA: box width, else K)
     const long long* lens;    // [N / S] valid frames per utterance, or NULL (length-aware rows, vqb_bwd_args.row_lengths)
     int S;
     float* dx;                // [N][64] (pad-only tiles are zero-filled directly)
@@ -64,7 +68,7 @@ struct BwdPcP {
 template <int KP, bool L2>
 __global__ void __launch_bounds__(BP_THREADS, 2)
 vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
-                     const __grid_constant__ CUtensorMap tm_dx, BwdPcP p) {
+                     const __grid_constant__ CUtensorMap tm_dx, const __grid_constant__ CUtensorMap tm_gl, BwdPcP p) {
     constexpr int D = 64;
     constexpr int TILE = 2 * TBLK;                   // one [TR][64] fp32 tile = two blocks
     constexpr int EV = KP / 8;                       // 16-byte words per thread that cover the table image (2 * KP * 128 B)
@@ -98,6 +102,7 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
     if (r == 0) {
         tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_dx);
+        if (p.gl_rb) tma_prefetch_desc(&tm_gl);
         mbar_init(in_full, 1); mbar_init(d1_done, 1); mbar_init(mma_done, 1);
         fence_barrier_init();
     }
@@ -125,15 +130,28 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     for (int k = 0; k < (L2 ? 1 : KP); ++k) accg[k] = 0.f;
     float cs0 = 0.f, cs1 = 0.f;                      // two column sums per lane (see the butterfly below)
 
+    // g_logp [S][B][K] seen as a 2-D tensor [S][B * K]: the rows of a tile that belong to utterance b sit in the box
+    // (columns (b * K & ~3) .. + gl_ld, frames sf .. + gl_rb) -- TMA wants the box to start on a 16-byte boundary, so it
+    // starts up to three words early and the row thread skips them; boxes never straddle an utterance
+    // (S % gl_rb == 0 == TR % gl_rb)
+    const uint32_t gl_box_bytes = (uint32_t)(p.gl_rb * p.gl_ld * 4);
+    auto glogp_bytes = [&](int rows) -> uint32_t { return p.gl_rb ? (uint32_t)((rows + p.gl_rb - 1) / p.gl_rb) * gl_box_bytes : 0u; };
+    auto issue_glogp = [&](int row0, int rows) {
+        for (int j = 0; j * p.gl_rb < rows; ++j) {
+            const int g0 = row0 + j * p.gl_rb, b = g0 / p.S;
+            tma_load_2d(reinterpret_cast<uint8_t*>(stG) + j * gl_box_bytes, &tm_gl, (b * K) & ~3, g0 - b * p.S, in_full);
+        }
+    };
     auto issue_loads = [&](int it) {
         const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * TR;
         const int rows = min(TR, p.N - row0);
         const uint32_t bulk = (uint32_t)(rows * K * 4) & ~15u;
-        mbar_arrive_expect_tx(in_full, 2 * bulk + TILE + (have_gq ? TILE : 0));
+        mbar_arrive_expect_tx(in_full, (p.gp ? 2 : 1) * bulk + TILE + (have_gq ? TILE : 0) + glogp_bytes(rows));
         if (bulk) {
             bulk_load_1d(stP, p.p + (size_t)row0 * K, bulk, in_full);
-            bulk_load_1d(stG, p.gp + (size_t)row0 * K, bulk, in_full);
+            if (p.gp) bulk_load_1d(stG, p.gp + (size_t)row0 * K, bulk, in_full);
         }
+        if (p.gl_rb) issue_glogp(row0, rows);
         tma_load_2d(sX, &tm_x, 0, row0, in_full);
         tma_load_2d(sX + TBLK, &tm_x, 32, row0, in_full);
         if (have_gq) {
@@ -190,14 +208,32 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         long long code = 0;
         if (do_scatter && valid) code = __ldg(p.idx + row0 + r);
+        const bool gl_staged = p.glogp && !p.gl_rb;
+        if (gl_staged) {
+            // Gradient of the CTC input folded in, general shapes (the boxes of the TMA route need S % 8 == 0 and 16-byte
+            // aligned rows of [S][B * K]): the rows of g_logp [S][B][K] that belong to this tile are staged where the bulk
+            // copy would have put g_p, one row per warp step, the lanes along its K codes (contiguous 4 K-byte runs), with
+            // 4-byte cp.async: no registers held, every element of the tile in flight at once.
+            const int B_ = p.N / p.S;
+            int b = (row0 + warp) / p.S, sf = (row0 + warp) - b * p.S;
+            for (int rl = warp; rl < rows; rl += BP_THREADS / 32) {
+                const float* grow = p.glogp + ((size_t)sf * B_ + b) * K;
+                const uint32_t dst = smem_u32(stG + rl * K);
+                for (int k = lane; k < K; k += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * k), "l"(grow + k) : "memory");
+                sf += BP_THREADS / 32;
+                while (sf >= p.S) { sf -= p.S; ++b; }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
         mbar_wait(in_full, ph);
         VQB_BTL(2);
         {
             const int nfl = rows * K, nbulk = ((nfl * 4) & ~15) >> 2;
-            if (nbulk != nfl) {                                    // last < 16 bytes of a ragged tile
-                if (r < nfl - nbulk) {
+            if (nbulk != nfl || gl_staged) {                       // last < 16 bytes of a ragged tile; the staged g_logp rows
+                if (nbulk != nfl && r < nfl - nbulk) {
                     stP[nbulk + r] = p.p[(size_t)row0 * K + nbulk + r];
-                    stG[nbulk + r] = p.gp[(size_t)row0 * K + nbulk + r];
+                    if (p.gp) stG[nbulk + r] = p.gp[(size_t)row0 * K + nbulk + r];
                 }
                 __syncthreads();
             }
@@ -212,7 +248,41 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             if (valid) {
 #pragma unroll
                 for (int k = 0; k < KP; ++k) {
-                    if (k < KP - 15 || k < K) { c[k] = stP[r * K + k]; gg[k] = stG[r * K + k]; }
+                    if (k < KP - 15 || k < K) c[k] = stP[r * K + k];
+                }
+                if (!p.glogp) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        if (k < KP - 15 || k < K) gg[k] = stG[r * K + k];
+                    }
+                } else {
+                    if (p.gl_rb) {
+                        // rows of gl_ld floats (gl_ld / 4 odd: conflict-free 128-bit reads); the row's K words start `sh`
+                        // words into it (see issue_glogp), what lies beyond them belongs to the next utterance
+                        const float4* g4 = reinterpret_cast<const float4*>(stG + r * p.gl_ld);
+                        const int sh = (((row0 + r) / p.S) * K) & 3;
+                        const bool s1 = sh == 1, s2 = sh == 2, s3 = sh == 3;
+                        float4 a = g4[0];
+#pragma unroll
+                        for (int k4 = 0; k4 < KP / 4; ++k4) {
+                            if (4 * k4 < KP - 15 || 4 * k4 < K) {
+                                const float4 n = g4[k4 + 1];
+                                gg[4 * k4] = s3 ? a.w : (s2 ? a.z : (s1 ? a.y : a.x));
+                                gg[4 * k4 + 1] = s3 ? n.x : (s2 ? a.w : (s1 ? a.z : a.y));
+                                gg[4 * k4 + 2] = s3 ? n.y : (s2 ? n.x : (s1 ? a.w : a.z));
+                                gg[4 * k4 + 3] = s3 ? n.z : (s2 ? n.y : (s1 ? n.x : a.w));
+                                a = n;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) {
+                            if (k < KP - 15 || k < K) gg[k] = stG[r * K + k];
+                        }
+                    }
+                    // d log(p + eps) / dp  (MUFU.RCP + multiply: 2 ulp)
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) gg[k] = (k < KP - 15 || k < K) ? __fdividef(gg[k], c[k] + p.eps) : 0.f;
                 }
             }
 #pragma unroll
@@ -469,11 +539,12 @@ vqb_bwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 const int nrow0 = ((int)blockIdx.x + nit * (int)gridDim.x) * TR;
                 const int nrows = min(TR, p.N - nrow0);
                 const uint32_t bulk = (uint32_t)(nrows * K * 4) & ~15u;
-                mbar_arrive_expect_tx(in_full, 2 * bulk + TILE + (have_gq ? TILE : 0));
+                mbar_arrive_expect_tx(in_full, (p.gp ? 2 : 1) * bulk + TILE + (have_gq ? TILE : 0) + glogp_bytes(nrows));
                 if (bulk) {
                     bulk_load_1d(stP, p.p + (size_t)nrow0 * K, bulk, in_full);
-                    bulk_load_1d(stG, p.gp + (size_t)nrow0 * K, bulk, in_full);
+                    if (p.gp) bulk_load_1d(stG, p.gp + (size_t)nrow0 * K, bulk, in_full);
                 }
+                if (p.gl_rb) issue_glogp(nrow0, nrows);
                 tma_load_2d(sX, &tm_x, 0, nrow0, in_full);
                 tma_load_2d(sX + TBLK, &tm_x, 32, nrow0, in_full);
                 tma_store_wait_read();
@@ -537,9 +608,9 @@ unsigned long long* get_debug_timeline();
 
 bool backward_pcode_supported(const vqb_bwd_args* a) {
     if (!(a->flags & VQB_TENSOR_CORES)) return false;
-    if (!a->g_p || !(a->flags & VQB_STOP_GRAD) || (a->flags & VQB_TEMP_GRAD)) return false;
+    if ((!a->g_p && !a->g_logp) || !(a->flags & VQB_STOP_GRAD) || (a->flags & VQB_TEMP_GRAD)) return false;
     if (a->n_codes > 64 || a->dim != 64) return false;
-    return aligned16(a->p_code) && aligned16(a->g_p);
+    return aligned16(a->p_code) && (!a->g_p || aligned16(a->g_p));
 }
 
 static int bp_grid(int64_t N) {
@@ -554,10 +625,12 @@ size_t backward_pcode_workspace(const vqb_bwd_args* a) {
 }
 
 template <int KP, bool L2>
-static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtensorMap& td, BwdPcP p, int grid, cudaStream_t s) {
+static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtensorMap& td, const CUtensorMap& tgl, BwdPcP p, int grid,
+                     cudaStream_t s) {
     p.stage_bytes = (TR * p.K * 4 + 127) & ~127;
     const int ops = 2 * TBLK + 2 * KP * 128;
-    p.pg_bytes = ((2 * p.stage_bytes > ops ? 2 * p.stage_bytes : ops) + 1023) & ~1023;
+    const int stage2 = p.stage_bytes + (p.gl_rb ? TR * p.gl_ld * 4 : p.stage_bytes);    // p_code rows + (g_p | g_logp boxes)
+    p.pg_bytes = ((stage2 > ops ? stage2 : ops) + 1023) & ~1023;
     const size_t smem = (size_t)p.pg_bytes + 2 * 2 * TBLK + TBLK + 8 * 4 + 3 * 8 + 16 + 1024;
     if ((int)smem > max_optin_smem()) return invalid("vqb_backward: the parity-mode kernel needs %zu B of shared memory", smem);
     auto kern = vqb_bwd_pcode_kernel<KP, L2>;
@@ -567,7 +640,7 @@ static int launch_bp(const CUtensorMap& tx, const CUtensorMap& tg, const CUtenso
     // measured SLOWER (61.8 vs 57.9 us per step at config 2, profiles/r2_pdl_ab.txt).  The kernel still releases its own
     // successor early (the fused tail).
     kernel_event_begin(s);
-    kern<<<grid, BP_THREADS, smem, s>>>(tx, tg, td, p);
+    kern<<<grid, BP_THREADS, smem, s>>>(tx, tg, td, tgl, p);
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_bwd_pcode_kernel");
     return VQB_OK;
@@ -607,20 +680,37 @@ int launch_backward_pcode(const vqb_bwd_args* a, cudaStream_t s) {
     p.t_first = (a->tail && l2) ? 64 - (int)a->tail->dim_attr : 64;
     p.pg_bytes = p.stage_bytes = 0;
     p.lens = (const long long*)a->row_lengths; p.S = (int)a->frames_per_utt; p.dx = a->dx;
+    p.glogp = a->g_logp; p.eps = a->ctc_eps;
+    p.gl_rb = 0; p.gl_ld = (int)K;
+    CUtensorMap tgl = tx;
+    if (a->g_logp) {
+        // the TMA route of g_logp: [S][B * K] with 16-byte aligned rows, boxes of 8 or 32 frames that never straddle an
+        // utterance; any other shape is staged by the kernel itself (cp.async)
+        const int64_t S = a->frames_per_utt, B = N / S;
+        static const bool no_tma = getenv("VQB_GLOGP_NO_TMA") != nullptr;      // developer A/B
+        if (!no_tma && S % 8 == 0 && (B * K) % 4 == 0 && aligned16(a->g_logp)) {
+            p.gl_rb = S % 32 == 0 ? 32 : 8;
+            int w4 = (int)((K + 3) / 4) + 1;               // K words that may start up to 3 words into the box ...
+            w4 += (w4 & 1) ^ 1;                            // ... and an odd number of 16-byte words per row (bank spread)
+            p.gl_ld = 4 * w4;
+            if ((rc = make_tmap_2d_plain_f32(&tgl, a->g_logp, (uint64_t)(B * K), (uint64_t)S, (uint64_t)(B * K * 4),
+                                             (uint32_t)p.gl_ld, (uint32_t)p.gl_rb))) return rc;
+        }
+    }
     const int KP = (int)((K + 15) / 16 * 16);
     if (l2) {
         switch (KP) {
-            case 16: rc = launch_bp<16, true>(tx, tg, td, p, grid, s); break;
-            case 32: rc = launch_bp<32, true>(tx, tg, td, p, grid, s); break;
-            case 48: rc = launch_bp<48, true>(tx, tg, td, p, grid, s); break;
-            default: rc = launch_bp<64, true>(tx, tg, td, p, grid, s); break;
+            case 16: rc = launch_bp<16, true>(tx, tg, td, tgl, p, grid, s); break;
+            case 32: rc = launch_bp<32, true>(tx, tg, td, tgl, p, grid, s); break;
+            case 48: rc = launch_bp<48, true>(tx, tg, td, tgl, p, grid, s); break;
+            default: rc = launch_bp<64, true>(tx, tg, td, tgl, p, grid, s); break;
         }
     } else {
         switch (KP) {
-            case 16: rc = launch_bp<16, false>(tx, tg, td, p, grid, s); break;
-            case 32: rc = launch_bp<32, false>(tx, tg, td, p, grid, s); break;
-            case 48: rc = launch_bp<48, false>(tx, tg, td, p, grid, s); break;
-            default: rc = launch_bp<64, false>(tx, tg, td, p, grid, s); break;
+            case 16: rc = launch_bp<16, false>(tx, tg, td, tgl, p, grid, s); break;
+            case 32: rc = launch_bp<32, false>(tx, tg, td, tgl, p, grid, s); break;
+            case 48: rc = launch_bp<48, false>(tx, tg, td, tgl, p, grid, s); break;
+            default: rc = launch_bp<64, false>(tx, tg, td, tgl, p, grid, s); break;
         }
     }
     if (rc) return rc;

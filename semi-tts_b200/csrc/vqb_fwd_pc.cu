@@ -44,6 +44,8 @@ struct PcP {
     double* sqerr;
     unsigned int* stats;       // [0] += rows re-ranked in exact fp32 (may be NULL)
     unsigned long long* dbg;   // optional timeline buffer (vqb_debug_set_timeline), NULL in production
+    float* logp;               // [S][B][K] log(p_code + eps) for nn.CTCLoss, or NULL (vqb_fwd_args.ctc_logp)
+    float eps;
     const long long* lens;     // [N / S] valid frames per utterance, or NULL (length-aware rows, vqb_fwd_args.row_lengths)
     int S;                     // frames per utterance
     int N, K, num_tiles;
@@ -94,6 +96,8 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     uint64_t* mma_done = bars + 2;
     uint64_t* t_full = bars + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    // (only with p.logp) per row: offset of its [S][B][K] output row (int64), its arg-max code, log(p_top + eps)
+    int4* sRow = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(bars) + 64);
 
     const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
     int tl_n = 0;
@@ -143,6 +147,12 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 float* pc = p.pcode + (size_t)row0 * K;
                 for (int i = r; i < rows * K; i += PM) pc[i] = 0.f;
                 if (valid) p.idx[row0 + r] = 0;
+                if (p.logp && valid) {
+                    const int b = (row0 + r) / p.S, sf = (row0 + r) - b * p.S;
+                    float* orow = p.logp + ((size_t)sf * (p.N / p.S) + b) * K;
+                    const float lz = logf(p.eps);
+                    for (int k = 0; k < K; ++k) orow[k] = lz;
+                }
                 continue;
             }
             if (valid) {
@@ -320,6 +330,13 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 if (k < KP - 15 || k < K) prow[k] = v[k] * inv;    // softmax (:127)
         }
         if (valid) p.idx[row0 + r] = best;
+        if (p.logp) {
+            // the one probability of the row that can be close to 1 (its e is exactly 1, so p = inv) gets the full-precision
+            // logarithm here; every other code has p <= 1/2 and is served by the fast one in the emission loop below
+            const int gr_ = min(row0 + r, p.N - 1), b = gr_ / p.S, sf = gr_ - b * p.S;
+            const long long off = ((long long)sf * (p.N / p.S) + b) * K;
+            sRow[r] = make_int4((int)(off & 0xffffffffll), (int)(off >> 32), best, __float_as_int(logf(inv + p.eps)));
+        }
         if (p.hist) {
             // warp-aggregated histogram: one atomic per distinct code per warp
             const unsigned peers = __match_any_sync(0xffffffffu, live ? best : -1);
@@ -384,6 +401,26 @@ vqb_fwd_pcode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 const int step_r = 32 / K, step_k = 32 - step_r * K;
                 for (int i = lane; i < n; i += 32) {
                     __stcs(dst + i, src[rr * KO + k]);
+                    rr += step_r; k += step_k;
+                    if (k >= K) { k -= K; ++rr; }
+                }
+            }
+            if (p.logp) {
+                // CTC input, emitted from the staged rows: out[s][b][:] = log(p[b][s][:] + eps) (bin/train_vqvae.py:430-432).
+                // The warp walks its slab element by element; the row's output offset, its arg-max code and that code's
+                // precise logarithm come from sRow (written by the row's thread above, same warp).
+                // lane = consecutive codes of a row, so every store instruction is one or two contiguous runs of the
+                // [S][B][K] tensor.  log = MUFU.LG2 * ln 2 (|error| < 2 ulp for p <= 1/2, where |log| >= 0.69).
+                int rr = lane / K, k = lane - rr * K;
+                const int step_r = 32 / K, step_k = 32 - step_r * K;
+                const int4* rowinfo = sRow + 32 * warp;
+#pragma unroll 4
+                for (int i = lane; i < n; i += 32) {
+                    const int4 ri = rowinfo[rr];
+                    float lg;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(src[rr * KO + k] + p.eps));
+                    const long long off = ((long long)ri.y << 32) | (unsigned int)ri.x;
+                    __stcs(p.logp + off + k, k == ri.z ? __int_as_float(ri.w) : lg * 0.693147181f);
                     rr += step_r; k += step_k;
                     if (k >= K) { k -= K; ++rr; }
                 }
@@ -457,7 +494,7 @@ template <int KP, int D, bool LINEAR>
 static int launch_pc(const CUtensorMap& tx, const CUtensorMap& tq, PcP p, cudaStream_t s, bool pdl) {
     const int tab_bytes = p.K * (D + 4) * 4, img_bytes = 2 * KP * 128;
     p.se_bytes = ((tab_bytes > img_bytes ? tab_bytes : img_bytes) + 1023) & ~1023;
-    const size_t smem = (size_t)2 * PBLK + p.se_bytes + (size_t)PM * (p.K | 1) * 4 + 320 + 4 * 4 + 4 * 8 + 16 + 1024;
+    const size_t smem = (size_t)2 * PBLK + p.se_bytes + (size_t)PM * (p.K | 1) * 4 + 320 + 4 * 4 + 64 + (p.logp ? PM * 16 : 0) + 1024;
     auto kern = vqb_fwd_pcode_kernel<KP, D, LINEAR>;
     { const int rc_ = ensure_smem(kern, smem, true); if (rc_) return rc_; }
     const int slots = 3 * sm_count();
@@ -493,6 +530,7 @@ int launch_forward_pcode(const vqb_fwd_args* a, cudaStream_t s) {
     p.stats = a->search_stats; p.dbg = get_debug_timeline();
     p.N = (int)N; p.K = (int)K; p.num_tiles = (int)ceil_div(N, PM); p.se_bytes = 0; p.flags = a->flags;
     p.lens = (const long long*)a->row_lengths; p.S = (int)a->frames_per_utt;
+    p.logp = a->ctc_logp; p.eps = a->ctc_eps;
     // PDL when the kernel enqueued immediately before is ours: the image build above, or (the caller vouches,
     // VQB_AFTER_ASSEMBLE) the table assembly
     const bool pdl = !cached || (a->flags & VQB_AFTER_ASSEMBLE);

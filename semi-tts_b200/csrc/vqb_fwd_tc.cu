@@ -726,6 +726,41 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // -----------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 tmap_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            set_error("libvqb200: cuTensorMapEncodeTiled is not available from the driver");
+            return nullptr;
+        }
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    return encode;
+}
+
+int make_tmap_2d_plain_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                           uint32_t box0, uint32_t box1) {
+    auto encode = tmap_encoder();
+    if (!encode) return VQB_ERR_CUDA;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {stride1_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("libvqb200: cuTensorMapEncodeTiled (plain) failed with CUresult %d (dims %llu x %llu, box %u x %u)", (int)r,
+                  (unsigned long long)dim0, (unsigned long long)dim1, box0, box1);
+        return VQB_ERR_CUDA;
+    }
+    return VQB_OK;
+}
+
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                      uint32_t box_rows, bool atom32b) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;

@@ -262,5 +262,9 @@ __device__ __forceinline__ bool elect_one() {
 // host: build a 2-D fp32 row-major tensor map [rows][cols], box = box_rows x 32 floats, SWIZZLE_128B
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                      uint32_t box_rows, bool atom32b = false);
+// plain (unswizzled) 2-D fp32 map: dims {dim0 (contiguous), dim1}, dim1 stride in bytes (a multiple of 16), box {box0, box1}
+// with box0 * 4 a multiple of 16; out-of-bounds elements read as zero
+int make_tmap_2d_plain_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                           uint32_t box0, uint32_t box1);
 
 }  // namespace vqb

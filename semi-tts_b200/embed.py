@@ -118,6 +118,20 @@ class _QuantizerBase(nn.Module):
         return (vq if self.vq_weight > 0 else 0), (commit if self.commit_weight > 0 else 0)
 
 
+class _Transient:
+    """holder of a per-step graph tensor that must not travel with copy.deepcopy / pickle of the module"""
+    __slots__ = ("value",)
+
+    def __init__(self):
+        self.value = None
+
+    def __deepcopy__(self, memo):
+        return _Transient()
+
+    def __reduce__(self):
+        return (_Transient, ())
+
+
 class L2Embedding(_QuantizerBase):
     """Nearest-codeword quantizer with an L2 score (reference: src/embed.py:57-147)."""
 
@@ -133,6 +147,16 @@ class L2Embedding(_QuantizerBase):
         self.learnable_table = nn.Parameter(torch.randn((vocab_size, latent_dim - d_attr)))
         # large-codebook option: do not materialise p_code (slot 1 of the return tuple is None)
         self.fused_search = False
+        # extension: set to EPS of bin/train_vqvae.py:18 and every grad-mode forward also leaves
+        # `self.ctc_logp` = log(p_code + EPS) as contiguous [S, B, K], the tensor compute_ctc_loss builds at :430-432 with a
+        # transpose + add + log -- written by the forward kernel's epilogue, its gradient folded into the backward kernel
+        self.ctc_eps = None
+        self._ctc_out = _Transient()
+
+    @property
+    def ctc_logp(self):
+        """log(p_code + ctc_eps) [S, B, K] of the last grad-mode forward (None unless `ctc_eps` is set)"""
+        return self._ctc_out.value
 
     @property
     def embedding(self):
@@ -162,11 +186,14 @@ class L2Embedding(_QuantizerBase):
                                                         lengths)
             self.last_idx = idx
             return p_code, new_latent, 0, 0
-        p_code, new_latent, idx, vq, commit = VF.vq_l2(
+        ctc_eps = self.ctc_eps if not self.fused_search else None
+        out = VF.vq_l2(
             enc_embs, self.learnable_table, attr, pw, pb, self.temp, stop_grad=self.stop_grad, skip=skip,
             n_real_rows=first_n_real_mel * S if first_n_real_mel > 0 else 0,
             want_pcode=not self.fused_search, hist=self._hist(enc_embs), want_losses=want_losses,
-            tensor_cores=self.tensor_cores, tail=self.fused_tail, lengths=lengths)
+            tensor_cores=self.tensor_cores, tail=self.fused_tail, lengths=lengths, ctc_eps=ctc_eps)
+        p_code, new_latent, idx, vq, commit = out[:5]
+        self._ctc_out.value = out[5] if ctc_eps is not None else None
         self.last_idx = idx
         return (p_code, new_latent) + self._losses(vq, commit)
 

@@ -114,7 +114,9 @@ def _lengths_arg(lengths, n_utts, dev):
 
 
 def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, hist, want_sqerr,
-                 score_w_bf16=None, search_stats=None, operand_cache=None, lengths=None, frames=0):
+                 score_w_bf16=None, search_stats=None, operand_cache=None, lengths=None, frames=0, ctc_eps=None):
+    """`ctc_eps` (with `frames`): also ask the parity-mode kernel for log(p_code + ctc_eps) in nn.CTCLoss's [S, B, K] layout
+    (returned as a sixth value; None when the route taken cannot emit it)"""
     lib = _lib.load()
     N, D = x2d.shape
     K = score_w.shape[0]
@@ -133,12 +135,18 @@ def _run_forward(flags, x2d, score_w, score_b, gather_table, temp, want_pcode, h
     a.hist, a.sq_err_sum, a.search_stats = ptr(hist), ptr(sq), ptr(search_stats)
     a.operand_cache = ptr(operand_cache)
     a.row_lengths, a.frames_per_utt = ptr(lengths), (frames if lengths is not None else 0)
+    logp = None
+    if ctc_eps is not None and N > 0 and frames > 0 and lib.vqb_forward_kernel_name(ctypes.byref(a)) == b"vqb_fwd_pcode_kernel":
+        logp = torch.empty(frames, N // frames, K, device=dev, dtype=torch.float32)
+        a.frames_per_utt, a.ctc_logp, a.ctc_eps = frames, ptr(logp), float(ctc_eps)
     with torch.cuda.device(dev):
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
         ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8) if nbytes.value else None
         a.workspace, a.workspace_bytes = ptr(ws), nbytes.value
         _lib.check(lib.vqb_forward(ctypes.byref(a), _stream(x2d)))
+    if ctc_eps is not None:
+        return p_code, idx, q, sq, logp
     return p_code, idx, q, sq
 
 
@@ -282,8 +290,10 @@ def _exchange_timeout_ms():
 
 
 def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp, p_code, idx, g_p, g_q,
-                  want_dx_buffer, separate_gather, operand_cache=None, tail=None, phn_attr=None, Da=0, lengths=None, frames=0):
-    """Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None, flat or None).
+                  want_dx_buffer, separate_gather, operand_cache=None, tail=None, phn_attr=None, Da=0, lengths=None, frames=0,
+                  g_logp=None, ctc_eps=0.0):
+    """`g_logp` [S, B, K] (instead of g_p): the upstream gradient of the forward's ctc_logp output, folded into the kernel.
+    Returns (dx or None, d_score_w, colsum, d_gather or None, d_temp or None, flat or None).
     `flat` is set when the fused tail ran: [d_learnable | d_proj_w | d_proj_b], already summed over the group."""
     lib = _lib.load()
     N, D = x2d.shape
@@ -298,6 +308,19 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
     a.p_code, a.idx, a.g_p, a.g_q = ptr(p_code), ptr(idx), ptr(g_p), ptr(g_q)
     a.operand_cache = ptr(operand_cache)
     a.row_lengths, a.frames_per_utt = ptr(lengths), (frames if lengths is not None else 0)
+    if g_logp is not None:
+        a.frames_per_utt, a.g_logp, a.ctc_eps = frames, ptr(g_logp), float(ctc_eps)
+        a.g_p = None
+        if g_p is not None or lib.vqb_backward_kernel_name(ctypes.byref(a)) != b"vqb_bwd_pcode_kernel":
+            # this call is not served by the kernel that folds the division in (or g_p is there as well): one extra pass
+            # turns g_logp into (an addition to) g_p
+            acc = g_p is not None
+            g_p = g_p.clone() if acc else torch.empty(N, K, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(lib.vqb_ctc_logp_backward(ptr(g_logp), ptr(p_code), N // frames, frames, K, float(ctc_eps), ptr(g_p),
+                                                     1 if acc else 0, _stream(x2d)))
+            a.g_logp, a.ctc_eps, a.frames_per_utt = None, 0.0, (frames if lengths is not None else 0)
+        a.g_p = ptr(g_p)
     use_tail = bool(tail is not None and tail.enabled and (flags & _lib.SCORE_L2) and not separate_gather
                     and (lib.vqb_backward_kernel_name(ctypes.byref(a)) == b"vqb_bwd_pcode_kernel"
                          or (N == 0 and tail.exchange is not None)))      # an empty shard still joins its peers' exchange
@@ -355,12 +378,13 @@ def _loss_backward(x2d, table, idx, g_vq, g_commit, dx, dx_accumulate, dtable):
 
 class _Cfg:
     """Per-call options (plain Python, not a tensor)."""
-    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores", "tail", "lengths")
+    __slots__ = ("stop_grad", "skip", "n_real_rows", "want_pcode", "hist", "want_losses", "tensor_cores", "tail", "lengths", "ctc_eps")
 
     def __init__(self, stop_grad=True, skip=False, n_real_rows=0, want_pcode=True, hist=None,
-                 want_losses=False, tensor_cores=True, tail=None, lengths=None):
+                 want_losses=False, tensor_cores=True, tail=None, lengths=None, ctc_eps=None):
         self.tail = tail
         self.lengths = lengths
+        self.ctc_eps = None if ctc_eps is None else float(ctc_eps)
         self.stop_grad, self.skip, self.n_real_rows = bool(stop_grad), bool(skip), int(n_real_rows)
         self.want_pcode, self.hist, self.want_losses = bool(want_pcode), hist, bool(want_losses)
         self.tensor_cores = bool(tensor_cores)
@@ -402,8 +426,21 @@ class _VQL2(torch.autograd.Function):
         lens = _lengths_arg(cfg.lengths, B, x2d.device)
         if lens is not None and (cfg.want_losses or not cfg.want_pcode):
             raise RuntimeError("semi-tts_b200: `lengths` is served by the parity-mode route only (p_code on, no loss extensions)")
-        p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
-                                          cfg.want_losses, tbf, None, cache, lens, S)
+        logp = None
+        if cfg.ctc_eps is not None:
+            if not cfg.want_pcode:
+                raise RuntimeError("semi-tts_b200: ctc_eps needs p_code (fused_search off)")
+            p_code, idx, q, sq, logp = _run_forward(flags, x2d, table, enorm, table, temp_c, True, cfg.hist,
+                                                    cfg.want_losses, tbf, None, cache, lens, S, cfg.ctc_eps)
+            if logp is None:
+                # a route without the fused emission (K > 64, SIMT, ...): the standalone pass over p_code
+                logp = torch.empty(S, B, K, device=x2d.device, dtype=torch.float32)
+                if B * S:
+                    with torch.cuda.device(x2d.device):
+                        _lib.check(_lib.load().vqb_ctc_logp(ptr(p_code), B, S, K, cfg.ctc_eps, ptr(logp), _stream(x2d)))
+        else:
+            p_code, idx, q, sq = _run_forward(flags, x2d, table, enorm, table, temp_c, cfg.want_pcode, cfg.hist,
+                                              cfg.want_losses, tbf, None, cache, lens, S)
         ctx.lens = lens
         ctx.op_cache = cache
         ctx.set_materialize_grads(False)                    # an unused output must arrive as None, not zeros
@@ -417,16 +454,16 @@ class _VQL2(torch.autograd.Function):
         if cfg.want_losses:
             vq = (sq / float(max(B * S * D, 1))).to(torch.float32).view(())
             commit = vq.clone()
-        return (p_code.view(B, S, K) if p_code is not None else None), q.view(B, S, D), idx3, vq, commit
+        return (p_code.view(B, S, K) if p_code is not None else None), q.view(B, S, D), idx3, vq, commit, logp
 
     @staticmethod
-    def backward(ctx, g_p, g_q, _g_idx, g_vq, g_commit):
+    def backward(ctx, g_p, g_q, _g_idx, g_vq, g_commit, g_logp=None):
         x2d, table, enorm, temp, p_code, idx, phn_attr = ctx.saved_tensors
         cfg = ctx.cfg
         B, S, D, K = ctx.shape
         N = B * S
         have_loss = g_vq is not None or g_commit is not None
-        if g_p is None and g_q is None and not have_loss:
+        if g_p is None and g_q is None and g_logp is None and not have_loss:
             return (None,) * 7
         dev = x2d.device
         exchange_on = cfg.tail is not None and cfg.tail.exchange is not None
@@ -434,6 +471,9 @@ class _VQL2(torch.autograd.Function):
             return (None,) * 7
         g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
+        g_l = _g32(g_logp) if (g_logp is not None and N > 0) else None      # [S, B, K]
+        if g_logp is not None and N == 0 and g_p2 is None:
+            g_p2 = torch.zeros(0, K, device=dev, dtype=torch.float32)
         flags = _fwd_flags(_lib.SCORE_L2, cfg) | (_lib.TEMP_GRAD if ctx.temp_grad else 0) | \
             (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         d_temp = colsum = flat = None
@@ -448,20 +488,21 @@ class _VQL2(torch.autograd.Function):
                     tail=cfg.tail, phn_attr=phn_attr, Da=ctx.Da)
             if flat is None:
                 d_w = torch.zeros(K, D, device=dev, dtype=torch.float32)
-        elif g_p2 is None and g_q2 is None:
+        elif g_p2 is None and g_q2 is None and g_l is None:
             dx, d_w = None, torch.zeros(K, D, device=dev, dtype=torch.float32)
-        elif g_p2 is None and cfg.stop_grad and ctx.lens is None:
+        elif g_p2 is None and g_l is None and cfg.stop_grad and ctx.lens is None:
             # scatter-only: dx = g_q, the straight-through identity, returned as the same tensor (zero bytes)
             _, d_w, _, _, _, _ = _run_backward(flags & ~_lib.TEMP_GRAD, cfg.n_real_rows, x2d, table, enorm, table, temp,
                                                None, idx, None, g_q2, False, False)
             dx = g_q2
         else:
-            if ctx.lens is not None and g_p2 is None:
+            if ctx.lens is not None and g_p2 is None and g_l is None:
                 # (the tensor-core backward is keyed on g_p; a step that only back-propagates through new_latent gets a zero g_p)
                 g_p2 = torch.zeros(N, K, device=dev, dtype=torch.float32)
             dx, d_w, colsum, _, d_temp, flat = _run_backward(
                 flags, cfg.n_real_rows, x2d, table, enorm, table, temp, p_code, idx, g_p2, g_q2, True, False,
-                ctx.op_cache, tail=None if have_loss else cfg.tail, phn_attr=phn_attr, Da=ctx.Da, lengths=ctx.lens, frames=S)
+                ctx.op_cache, tail=None if have_loss else cfg.tail, phn_attr=phn_attr, Da=ctx.Da, lengths=ctx.lens, frames=S,
+                g_logp=g_l, ctc_eps=cfg.ctc_eps or 0.0)
         if flat is not None:
             # fused tail: table backward (and the sum over GPUs) already done behind the main kernel
             Da, A = (ctx.Da, phn_attr.shape[1]) if phn_attr is not None else (0, 0)
@@ -487,11 +528,14 @@ class _VQL2(torch.autograd.Function):
 
 
 def vq_l2(x, learnable_table, phn_attr, proj_w, proj_b, temp, stop_grad=True, skip=False, n_real_rows=0,
-          want_pcode=True, hist=None, want_losses=False, tensor_cores=True, tail=None, lengths=None):
+          want_pcode=True, hist=None, want_losses=False, tensor_cores=True, tail=None, lengths=None, ctc_eps=None):
     """L2 quantizer (src/embed.py:105-147).
-    Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S] int64, vq_loss or None, commit_loss or None)."""
-    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores, tail, lengths)
-    return _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
+    Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S] int64, vq_loss or None, commit_loss or None) and, with
+    `ctc_eps`, a sixth value: log(p_code + ctc_eps) as contiguous [S,B,K] -- the nn.CTCLoss input of
+    bin/train_vqvae.py:430-432, written by the forward kernel's epilogue, its gradient folded into the backward kernel."""
+    cfg = _Cfg(stop_grad, skip, n_real_rows, want_pcode, hist, want_losses, tensor_cores, tail, lengths, ctc_eps)
+    out = _VQL2.apply(x, learnable_table, phn_attr, proj_w, proj_b, temp, cfg)
+    return out if ctc_eps is not None else out[:5]
 
 
 def vq_search(x, table, temp=None, hist=None, search_tensor=True, stats=None):

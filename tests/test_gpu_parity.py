@@ -682,3 +682,61 @@ def test_length_aware_rows_match_the_dense_call_on_valid_frames(B, S):
     with torch.no_grad():
         p2, q2, _, _ = m(x, 0, lengths=lens)
     assert torch.equal(p2, la["p"]) and torch.equal(q2, la["q"])
+
+
+@pytest.mark.parametrize("B,S,with_lengths", [(6, 400, False), (5, 77, False), (16, 800, False), (8, 200, False), (4, 130, True), (4, 96, True)])
+def test_ctc_log_probs_from_the_forward_epilogue_and_folded_gradient(B, S, with_lengths):
+    """SURVEY 8f rank 3 (bin/train_vqvae.py:18,430-432): with `ctc_eps` set the forward kernel also writes
+    log(p_code + EPS) in nn.CTCLoss's [S, B, K] layout and the backward kernel takes the gradient of THAT tensor
+    (G = g_logp^T / (p_code + EPS) formed in its prologue).  Checked against the fp64 oracle and against the unfused pair
+    (standalone ctc_log_probs pass + its backward) on the same inputs."""
+    import semi_tts_b200 as V
+    g = load_golden("l2_attr_stopgrad")
+    K, D = 43, 64
+    gen = torch.Generator().manual_seed(B * 977 + S)
+    x = (torch.randn(B, S, D, generator=gen) * 0.7).cuda()
+    gl = torch.randn(S, B, K, generator=gen).cuda()
+    gq = torch.randn(B, S, D, generator=gen).cuda()
+    gp_extra = torch.randn(B, S, K, generator=gen).cuda()
+    lens = torch.randint(1, S + 1, (B,), generator=gen) if with_lengths else None
+    mask = (torch.arange(S)[None, :] < lens[:, None]).cuda() if with_lengths else torch.ones(B, S, dtype=torch.bool).cuda()
+
+    def run(fused, also_gp=False):
+        m = build_module(g, "l2")
+        m.ctc_eps = 1e-10 if fused else None
+        xi = x.clone().requires_grad_(True)
+        p, q, _, _ = m(xi, 0, lengths=lens) if with_lengths else m(xi)
+        logp = m.ctc_logp if fused else V.ctc_log_probs(p)
+        assert logp.shape == (S, B, K) and logp.is_contiguous()
+        outs, grads = [logp, q], [gl, gq]
+        if also_gp:
+            outs.append(p); grads.append(gp_extra)
+        torch.autograd.backward(outs, grads)
+        return dict(p=p.detach(), logp=logp.detach(), dx=xi.grad.clone(), dl=m.learnable_table.grad.clone(),
+                    dw=m.proj_attr.weight.grad.clone(), db=m.proj_attr.bias.grad.clone())
+
+    f, u = run(True), run(False)
+    assert torch.equal(f["p"], u["p"])
+    mt = mask.t()
+    # forward: same formula on the same fp32 p_code; the oracle in fp64
+    E = _table64(g)
+    of = O.l2_forward(x.cpu().numpy(), E, 1.0)
+    ref_logp = O.ctc_input(f["p"].cpu().numpy().astype(np.float64))
+    assert rel_err(f["logp"][mt].cpu().numpy(), ref_logp[mt.cpu().numpy()]) < 1e-6
+    assert torch.allclose(f["logp"][mt], u["logp"][mt], rtol=1e-6, atol=1e-6)
+    if with_lengths:
+        assert torch.all(f["logp"][~mt] == float(np.log(np.float32(1e-10))))        # pad frames: p_code = 0
+    # backward: oracle chain  g_logp -> g_p -> (dx, dtable)
+    mk = mask.cpu().numpy()
+    g_p = O.ctc_input_backward(of["p_code"], gl.cpu().numpy().astype(np.float64)) * mk[..., None]
+    ob = O.l2_backward(x.cpu().numpy(), E, 1.0, of["p_code"], of["idx"], g_p, gq.cpu().numpy() * mk[..., None])
+    assert rel_err(f["dx"].cpu().numpy(), ob["dx"]) < TOL
+    tb = O.table_backward(ob["dtable"], g["sd.phn_attr.weight"], g["sd.proj_attr.weight"])
+    assert rel_err(f["dl"].cpu().numpy(), tb["d_learnable"]) < TOL
+    for k in ("dx", "dl", "dw", "db"):
+        assert torch.allclose(f[k], u[k], rtol=1e-5, atol=1e-5 * float(u[k].abs().max())), k
+    # a step that ALSO back-propagates through p_code itself takes the unfolded route (one extra pass) -- same numbers
+    f2, u2 = run(True, True), run(False, True)
+    for k in ("dx", "dl", "dw", "db"):
+        assert torch.allclose(f2[k], u2[k], rtol=1e-5, atol=1e-5 * float(u2[k].abs().max())), k
+    _record("ctc_fold", dict(B=B, S=S, lengths=with_lengths, dx_rel_err_vs_oracle=float(rel_err(f["dx"].cpu().numpy(), ob["dx"]))))
