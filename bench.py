@@ -331,6 +331,7 @@ def run_ours(args, rank, world, local_rank):
     deferred = dist_on and m.fused_tail.exchange is not None and not os.environ.get("VQB_NO_DEFER")
     m.fused_tail.defer = deferred
     side_x = torch.cuda.Stream() if deferred else None
+    join_early = bool(os.environ.get("VQB_DEFER_JOIN_EARLY"))      # developer A/B: join the exchange before the backward
 
     def step(s):
         if deferred:
@@ -338,9 +339,11 @@ def run_ours(args, rank, world, local_rank):
             side_x.wait_stream(cur)
             V.dist.finish_codebook_grads(m, stream=side_x)      # the previous step's exchange, concurrent with this forward
         p, q, _, _ = m(s[0])
-        if deferred:
+        if deferred and join_early:
             cur.wait_stream(side_x)
         torch.autograd.backward([p, q], [s[1], s[2]])
+        if deferred and not join_early:
+            cur.wait_stream(side_x)
         if dist_on and not deferred and not no_exchange:
             V.dist.allreduce_codebook_grads(m)
 

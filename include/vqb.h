@@ -172,18 +172,20 @@ typedef struct vqb_bwd_tail {
     void* const* peer_bufs;      /* DEVICE array [world] of each rank's exchange-buffer address as mapped here */
     uint32_t timeout_ms;         /* how long a block polls for a peer's words before it raises counter[2] and returns
                                     with an incomplete sum (no trap: the context survives); 0 = 120 000 ms */
-    uint32_t reserved;           /* bit 0 (VQB_TAIL_DEFER), world > 1: this call only PUSHES its gradient to the peers and does
-                                    not write d_flat; vqb_exchange_finish() completes the exchange later */
+    uint32_t reserved;           /* bit 0 (VQB_TAIL_DEFER), world > 1: this call leaves THIS rank's sums in d_flat and touches no
+                                    peer memory; vqb_exchange_finish() runs the exchange later, on a stream of the caller's
+                                    choice */
 } vqb_bwd_tail;
 #define VQB_TAIL_DEFER 1u
 
 #define VQB_MAX_WORLD 16
 VQB_API size_t vqb_exchange_bytes(int64_t n_flat, int32_t world);
-/* Second half of a deferred exchange (tail.reserved & VQB_TAIL_DEFER): poll this rank's buffer for every rank's words of the
- * last exchange, add them in rank order and write d_flat[0 .. n_flat).  Enqueue it on any stream ordered after the
- * vqb_backward call that pushed, and before the NEXT vqb_backward of the module (the exchange slots alternate: a rank may
- * run one exchange ahead of its peers, not two).  Between the two calls the skew of the ranks and the NVLink round trip
- * are hidden behind whatever the caller runs there (the rest of the model's backward, the next forward). */
+/* The deferred exchange (tail.reserved & VQB_TAIL_DEFER): push d_flat[0 .. n_flat) to every rank's buffer, poll this rank's
+ * buffer for every rank's words of the same exchange, add them in rank order and write the sums back to d_flat.  Enqueue it
+ * on any stream ordered after the vqb_backward call that produced d_flat; the module's exchanges must be enqueued in the
+ * same order on every rank, one after the other (the exchange slots alternate: a rank may run one exchange ahead of its
+ * peers, not two).  On a side stream, the remote stores, the NVLink round trip and the skew of the ranks are hidden behind
+ * whatever the caller runs meanwhile (the rest of the model's backward, the next forward). */
 VQB_API int vqb_exchange_finish(const vqb_bwd_tail* tail, int64_t n_flat, void* stream);
 
 typedef struct vqb_bwd_args {

@@ -78,7 +78,7 @@ struct TailP {
     unsigned long long* dbg;  // optional timeline buffer (developer hook), slots 100..
     unsigned long long timeout_ns;
     int A, Da, world, rank, n_learn_blocks;
-    int defer;                // world > 1: push only; the poll + rank-ordered sum runs later (exchange_finish_kernel)
+    int defer;                // world > 1: this kernel leaves the LOCAL sums in d_flat; the exchange runs later (exchange_kernel)
 };
 #define VQB_TTL(slot) do { if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100 + (slot)] = globaltimer_ns(); } while (0)
 
@@ -105,7 +105,7 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
     const int tid = ty * 32 + tx;
     const int Dl = 64 - t.Da;
     const int n_l = K * Dl, n_w = t.Da * t.A, n_flat = n_l + n_w + t.Da;
-    const bool exchange = t.world > 1;
+    const bool exchange = t.world > 1 && !t.defer;               // deferred: local sums only, exchange_kernel does the rest
     if (t.dbg && tid == 0 && blockIdx.x == gridDim.x - 1) t.dbg[100] = globaltimer_ns();
     if ((int)blockIdx.x >= t.n_learn_blocks) {
         // constants of a projection block (frozen attribute table, this step's codebook column): fetched while the main
@@ -202,7 +202,7 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
         }
     }
     VQB_TTL(3);
-    if (!t.defer && tid < n_mine && s_idx[tid] >= 0) {
+    if (tid < n_mine && s_idx[tid] >= 0) {
         const int i = s_idx[tid];
         const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(t.peer_bufs[t.rank]) + slot_off + i;
         float sum = 0.f;
@@ -231,31 +231,42 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
     }
 }
 
-// Deferred second half of the exchange (vqb_bwd_tail.reserved bit 0 / vqb_exchange_finish): every output polls this rank's
-// buffer for all ranks' words of the LAST published epoch and adds them in rank order.  It runs wherever the caller puts
-// it -- behind the rest of the model's backward in a trainer, behind the next step's forward in the bench -- so the
-// round trip over NVLink and the skew between ranks are off the quantizer's critical path.
+// Deferred exchange (vqb_bwd_tail.reserved bit 0 / vqb_exchange_finish): the whole cross-GPU part as a kernel of its own.
+// The tail kernel has left this rank's sums in d_flat; every output is pushed to all ranks' buffers (own included), then
+// polls this rank's buffer for all ranks' words of the same epoch and adds them in rank order (identical bits everywhere).
+// It runs wherever the caller puts it -- behind the rest of the model's backward in a trainer, on a side stream beside the
+// next step's forward in the bench -- so neither the remote stores (a kernel does not retire before they are acknowledged
+// over NVLink) nor the skew between ranks sit on the quantizer's critical path (profiles/r2_n2_exchange_ab.txt).  Pushes precede polls and no block waits for a block of its own GPU: no deadlock.
 __global__ void __launch_bounds__(256)
-exchange_finish_kernel(float* __restrict__ d_flat, void* const* __restrict__ peer_bufs, int rank, unsigned int* counter,
-                       int n_flat, int world, unsigned long long timeout_ns) {
+exchange_kernel(float* __restrict__ d_flat, void* const* __restrict__ peer_bufs, int rank, unsigned int* counter,
+                int n_flat, int world, unsigned long long timeout_ns) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_flat) return;
-    const unsigned long long* own = reinterpret_cast<const unsigned long long*>(peer_bufs[rank]);
-    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(counter + 1);
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(counter + 1) + 1u;
     const int n_pad = (n_flat + 3) & ~3;
-    const unsigned long long* mine = own + (size_t)(epoch & 1u) * world * n_pad + i;
-    float sum = 0.f;
-    const unsigned long long t0 = globaltimer_ns();
-    for (int r = 0; r < world; ++r) {                               // rank order: identical bits on every GPU
-        unsigned long long w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
-        bool gave_up = false;
-        while ((unsigned int)(w >> 32) != epoch) {
-            if (globaltimer_ns() - t0 > timeout_ns) { atomicMax(counter + 2, (unsigned int)(r + 1)); gave_up = true; break; }
-            w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+    const size_t slot_off = (size_t)(epoch & 1u) * world * n_pad;
+    if (i < n_flat) {
+        const unsigned long long word = ((unsigned long long)epoch << 32) | __float_as_uint(d_flat[i]);
+        for (int r = 0; r < world; ++r)
+            st_relaxed_sys_b64(reinterpret_cast<unsigned long long*>(peer_bufs[r]) + slot_off + (size_t)rank * n_pad + i, word);
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peer_bufs[rank]) + slot_off + i;
+        float sum = 0.f;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int r = 0; r < world; ++r) {                           // rank order: identical bits on every GPU
+            unsigned long long w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+            bool gave_up = false;
+            while ((unsigned int)(w >> 32) != epoch) {
+                if (globaltimer_ns() - t0 > timeout_ns) { atomicMax(counter + 2, (unsigned int)(r + 1)); gave_up = true; break; }
+                w = ld_relaxed_sys_b64(mine + (size_t)r * n_pad);
+            }
+            if (!gave_up) sum += __uint_as_float((unsigned int)w);
         }
-        if (!gave_up) sum += __uint_as_float((unsigned int)w);
+        d_flat[i] = sum;
     }
-    d_flat[i] = sum;
+    // the last block hands the ticket back and publishes the epoch (every block has read it by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) { counter[0] = 0u; counter[1] = epoch; }
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -264,9 +275,9 @@ exchange_finish_kernel(float* __restrict__ d_flat, void* const* __restrict__ pee
 int launch_exchange_finish(const vqb_bwd_tail* tl, int64_t n_flat, cudaStream_t s) {
     if (tl->world <= 1) return VQB_OK;
     const unsigned long long timeout_ns = (unsigned long long)(tl->timeout_ms ? tl->timeout_ms : 120000u) * 1000000ull;
-    exchange_finish_kernel<<<(unsigned)ceil_div(n_flat, 256), 256, 0, s>>>(tl->d_flat, tl->peer_bufs, tl->rank, tl->counter, (int)n_flat,
-                                                                        tl->world, timeout_ns);
-    VQB_CHECK_LAUNCH("exchange_finish_kernel");
+    exchange_kernel<<<(unsigned)ceil_div(n_flat, 256), 256, 0, s>>>(tl->d_flat, tl->peer_bufs, tl->rank, tl->counter, (int)n_flat,
+                                                                 tl->world, timeout_ns);
+    VQB_CHECK_LAUNCH("exchange_kernel");
     return VQB_OK;
 }
 

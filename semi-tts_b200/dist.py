@@ -120,8 +120,9 @@ def enable_fused_allreduce(module, group=None):
 
 
 def finish_codebook_grads(module, stream=None):
-    """Deferred exchange (module.fused_tail.defer = True): complete the gradient exchange that the last backward started --
-    poll for every rank's contribution and add them in rank order -- on `stream` (default: the current stream).  In a trainer
+    """Deferred exchange (module.fused_tail.defer = True): run the gradient exchange of the last backward -- push this rank's
+    sums to the peers, poll for every rank's contribution and add them in rank order -- on `stream` (default: the current
+    stream; a side stream keeps the remote stores off the stream the next kernels are queued on).  In a trainer
     call it (or allreduce_codebook_grads, which does it) after loss.backward(): the rest of the model's backward has run in
     between, so no rank waits for another.  It must be enqueued before the module's next backward (the module does so
     itself if the caller forgot)."""

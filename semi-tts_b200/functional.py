@@ -256,8 +256,8 @@ class FusedTail:
         self.exchange = None         # dist.PeerExchange or None
         self.fused = False
         self.enabled = not os.environ.get("VQB_NO_TAIL_TEST")     # developer switch
-        # deferred exchange (data-parallel runs): the backward's tail only PUSHES this rank's gradient to its peers; the
-        # poll + rank-ordered sum runs in finish() -- called by dist.allreduce_codebook_grads / dist.finish_codebook_grads,
+        # deferred exchange (data-parallel runs): the backward's tail leaves this rank's sums in the flat gradient; the
+        # exchange kernel (push to the peers, poll, rank-ordered sum) runs in finish() -- called by dist.allreduce_codebook_grads / dist.finish_codebook_grads,
         # i.e. behind the rest of the model's backward -- or at the latest before the module's next backward
         self.defer = False
         self.pending = None          # (BwdTail struct, flat tensor, n_flat) of the exchange that still has to be finished
@@ -340,7 +340,7 @@ def _run_backward(flags, n_real_rows, x2d, score_w, score_b, gather_table, temp,
         tl.timeout_ms = _exchange_timeout_ms()
         if ex is not None and tail.defer:
             tail.finish()                                  # (an unfinished exchange of the previous step: finish it first)
-            tl.reserved = 1                                # VQB_TAIL_DEFER: push only
+            tl.reserved = 1                                # VQB_TAIL_DEFER: local sums now, the exchange in finish()
         a.tail = ctypes.pointer(tl)
     else:
         # one zero-filled buffer (one fill kernel) carved into the accumulation targets
