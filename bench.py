@@ -583,8 +583,11 @@ def run_encode(args, rank, world, local_rank):
         with torch.no_grad():
             for b in range(n_batches):
                 nb = min(batch, hi - lo - done)
-                m(ring[b % ring_n][:nb])
-                m.inference(txt[:nb])
+                x, t = ring[b % ring_n], txt
+                if nb < batch:                                   # the shard's last, ragged batch
+                    x, t = x[:nb], t[:nb]
+                m(x)
+                m.inference(t)
                 done += nb
         return done
 

@@ -95,6 +95,20 @@ class _QuantizerBase(nn.Module):
     def _hist(self, ref):
         return self.usage.buffer_for(ref) if self.track_usage else None
 
+    def _nograd_params(self):
+        """(learnable_table, phn_attr.weight, proj_attr.weight, proj_attr.bias, temp) for the no-grad fast path, looked up
+        once: nn.Module.__getattr__ costs more than the rest of the call's bookkeeping.  Rebuilt when the table Parameter
+        or temp object is replaced."""
+        c = self.__dict__.get("_np")
+        lt = self._parameters.get("learnable_table")
+        tp = self._parameters.get("temp")
+        if tp is None:
+            tp = self._buffers.get("temp")
+        if c is None or c[0] is not lt or c[4] is not tp:
+            c = (lt,) + tuple(self._attr_params()) + (tp,)
+            self.__dict__["_np"] = c
+        return c
+
     def create_msg(self):
         return "           | EMA update = {}\t | Temp. = {}\t| Phn. attributs = {} ( projected = {})".format(
             self.ema, "learnable" if type(self.temp) is nn.Parameter else self.temp.data.item(),
@@ -165,7 +179,8 @@ class L2Embedding(_QuantizerBase):
 
     def inference(self, txt):
         if not torch.is_grad_enabled():
-            return VF.lookup_nograd(self._nograd, txt, self.learnable_table, *self._attr_params())
+            lt, attr, pw, pb, _ = self._nograd_params()
+            return VF.lookup_nograd(self._nograd, txt, lt, attr, pw, pb)
         return VF.codebook_lookup(txt, self.learnable_table, *self._attr_params(), tail=self.fused_tail)
 
     def forward(self, enc_embs, first_n_real_mel=0, lengths=None):
@@ -174,18 +189,18 @@ class L2Embedding(_QuantizerBase):
         p_code / new_latent rows are zero, they take no part in the histogram or in any gradient, and tiles that hold
         nothing else are skipped; valid rows are bit-identical to the dense call.  (With `--actual_len` the reference's CTC
         already ignores those frames, bin/train_vqvae.py:436-439; the unpaired branch keeps using every frame.)"""
-        B, S, _ = enc_embs.shape
         # numpy's global RNG is consumed exactly when the reference consumes it (src/embed.py:140)
         skip = bool(self.training and self.skip_prob > 0 and np.random.rand() < self.skip_prob)
         want_losses = self.vq_weight > 0 or self.commit_weight > 0
-        attr, pw, pb = self._attr_params()
         if not torch.is_grad_enabled() and not want_losses:
             # bin/train_vqvae.py:343 (validate) and the encode path: nothing to differentiate, nothing to save
-            p_code, new_latent, idx = VF.forward_nograd(self._nograd, enc_embs, self.learnable_table, attr, pw, pb, self.temp,
-                                                        skip, not self.fused_search, self._hist(enc_embs), self.tensor_cores,
-                                                        lengths)
-            self.last_idx = idx
+            lt, attr, pw, pb, temp = self._nograd_params()
+            p_code, new_latent, idx = VF.forward_nograd(self._nograd, enc_embs, lt, attr, pw, pb, temp, skip,
+                                                        not self.fused_search, self._hist(enc_embs), self.tensor_cores, lengths)
+            self.__dict__["last_idx"] = idx              # (plain attribute: skips nn.Module.__setattr__)
             return p_code, new_latent, 0, 0
+        B, S, _ = enc_embs.shape
+        attr, pw, pb = self._attr_params()
         ctc_eps = self.ctc_eps if not self.fused_search else None
         out = VF.vq_l2(
             enc_embs, self.learnable_table, attr, pw, pb, self.temp, stop_grad=self.stop_grad, skip=skip,

@@ -24,8 +24,14 @@ def _require(t, name, dtype=torch.float32):
         raise RuntimeError("semi-tts_b200: `%s` must be %s (got %s)" % (name, dtype, t.dtype))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(t):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    """the current CUDA stream of the tensor's device as a raw handle (the C ABI takes a void*)"""
+    if _raw_stream is not None:
+        return _raw_stream(t.device.index)           # no Stream object: a fraction of a microsecond
+    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 def _c(t):
@@ -161,6 +167,7 @@ class NoGradCache:
         self.table = self.enorm = self.image = None
         self.args = None
         self.ws = None
+        self.fn = self.ref = self.last = None
 
     def __deepcopy__(self, memo):
         return NoGradCache()                      # a copied module rebuilds its cache (the struct holds raw device pointers)
@@ -172,11 +179,15 @@ class NoGradCache:
         self.__init__()
 
     @staticmethod
-    def _key(tensors):
-        return tuple((t.data_ptr(), t._version, t.device.index) for t in tensors if t is not None)
+    def _key(learnable, phn_attr, proj_w, proj_b, want_image):
+        # optimizer steps and load_state_dict write in place (version counters), .to() / .data = ... move the storage
+        if proj_w is None:
+            return (learnable.data_ptr(), learnable._version, want_image)
+        return (learnable.data_ptr(), learnable._version, proj_w.data_ptr(), proj_w._version, proj_b._version,
+                phn_attr.data_ptr(), phn_attr._version, want_image)
 
     def tables(self, learnable, phn_attr, proj_w, proj_b, want_image):
-        key = self._key((learnable, phn_attr, proj_w, proj_b)) + (bool(want_image),)
+        key = self._key(learnable, phn_attr, proj_w, proj_b, bool(want_image))
         if key != self.key:
             res = assemble_table(learnable, phn_attr, proj_w, proj_b, want_cache=want_image)
             self.table, self.enorm = res[0], res[1]
@@ -188,23 +199,24 @@ class NoGradCache:
 
 def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, want_pcode, hist, tensor_cores, lengths=None):
     """L2 quantizer forward without autograd (src/embed.py:105-147 under torch.no_grad()).
-    Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S])."""
-    _require(x, "enc_embs")
+    Returns (p_code[B,S,K] or None, new_latent[B,S,D], idx[B,S]).
+    The per-call host work is kept to: three output allocations in their final shape, six struct fields, one C call."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        _require(x, "enc_embs")
     if x.dim() != 3:
         raise RuntimeError("semi-tts_b200: enc_embs must be [B, S, D]")
-    lib = _lib.load()
     B, S, D = x.shape
-    x2d = _c(x).view(B * S, D)
+    if not x.is_contiguous():
+        x = x.contiguous()
     use_image = bool(tensor_cores and want_pcode)
     table, enorm, image = cache.tables(learnable, phn_attr, proj_w, proj_b, use_image)
     K = table.shape[0]
     if table.shape[1] != D:
         raise RuntimeError("semi-tts_b200: enc_embs has D=%d but the codebook has D=%d" % (D, table.shape[1]))
     dev = x.device
-    N = B * S
-    p_code = torch.empty(N, K, device=dev, dtype=torch.float32) if want_pcode else None
-    idx = torch.empty(N, device=dev, dtype=torch.int64)
-    q = torch.empty(N, D, device=dev, dtype=torch.float32)
+    p_code = torch.empty((B, S, K), device=dev, dtype=torch.float32) if want_pcode else None
+    idx = torch.empty((B, S), device=dev, dtype=torch.int64)
+    q = torch.empty((B, S, D), device=dev, dtype=torch.float32)
     a = cache.args
     if a is None:
         a = _lib.FwdArgs()
@@ -214,34 +226,49 @@ def forward_nograd(cache, x, learnable, phn_attr, proj_w, proj_b, temp, skip, wa
         a.operand_cache = ptr(image)
         cache.args = a
         cache.ws = None
-    a.flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SKIP if skip else 0) | (_lib.TENSOR_CORES if tensor_cores else 0)
-    a.n_rows = N
-    a.x, a.temp, a.p_code, a.idx, a.new_latent, a.hist = ptr(x2d), ptr(temp), ptr(p_code), ptr(idx), ptr(q), ptr(hist)
-    lens = _lengths_arg(lengths, B, dev)
-    a.row_lengths, a.frames_per_utt = ptr(lens), (S if lens is not None else 0)
+        cache.fn = _lib.load().vqb_forward
+        cache.ref = ctypes.byref(a)
+        cache.last = None
+    # fields that rarely change between calls are written only when they do
+    var = (B * S, skip, tensor_cores, temp.data_ptr(), None if hist is None else hist.data_ptr(), lengths is None)
+    if var != cache.last:
+        a.flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.SKIP if skip else 0) | (_lib.TENSOR_CORES if tensor_cores else 0)
+        a.n_rows = B * S
+        a.temp, a.hist = ptr(temp), ptr(hist)
+        a.row_lengths, a.frames_per_utt = None, 0
+        cache.last = var
+    a.x, a.idx, a.new_latent = x.data_ptr(), idx.data_ptr(), q.data_ptr()
+    a.p_code = p_code.data_ptr() if want_pcode else None
+    if lengths is not None:
+        lens = _lengths_arg(lengths, B, dev)
+        a.row_lengths, a.frames_per_utt = ptr(lens), S
     with _on(dev):
         if not (use_image and image is not None):
             # shapes outside the cached-image route (fused search, CUDA-core kernels) may need scratch: sized once per module
             if cache.ws is None:
                 nbytes = ctypes.c_size_t(0)
-                _lib.check(lib.vqb_forward_workspace(ctypes.byref(a), ctypes.byref(nbytes)))
+                _lib.check(_lib.load().vqb_forward_workspace(cache.ref, ctypes.byref(nbytes)))
                 cache.ws = torch.empty(max(nbytes.value, 1), device=dev, dtype=torch.uint8)
             a.workspace, a.workspace_bytes = ptr(cache.ws), cache.ws.numel()
-        _lib.check(lib.vqb_forward(ctypes.byref(a), _stream(x2d)))
-    return (p_code.view(B, S, K) if want_pcode else None), q.view(B, S, D), idx.view(B, S)
+        rc = cache.fn(cache.ref, _stream(x))
+        if rc:
+            _lib.check(rc)
+    return p_code, q, idx
 
 
 def lookup_nograd(cache, txt, learnable, phn_attr, proj_w, proj_b):
     """inference(txt) without autograd (src/embed.py:96-103 under torch.no_grad()): a gather from the cached table."""
-    _require(txt, "txt", torch.int64)
-    lib = _lib.load()
+    if not txt.is_cuda or txt.dtype != torch.int64:
+        _require(txt, "txt", torch.int64)
     want_image = cache.key[-1] if cache.key is not None else False
     table, _, _ = cache.tables(learnable, phn_attr, proj_w, proj_b, want_image)
     K, D = table.shape
-    t = _c(txt)
-    out = torch.empty(*t.shape, D, device=t.device, dtype=torch.float32)
+    t = txt if txt.is_contiguous() else txt.contiguous()
+    out = torch.empty(t.shape + (D,), device=t.device, dtype=torch.float32)
     with _on(t.device):
-        _lib.check(lib.vqb_inference_gather(ptr(t), t.numel(), ptr(table), K, D, ptr(out), _stream(t)))
+        rc = _lib.load().vqb_inference_gather(t.data_ptr(), t.numel(), table.data_ptr(), K, D, out.data_ptr(), _stream(t))
+        if rc:
+            _lib.check(rc)
     return out
 
 
@@ -271,6 +298,8 @@ class FusedTail:
         self.pending = None
         lib = _lib.load()
         st = stream if stream is not None else torch.cuda.current_stream(flat.device)
+        if stream is not None:
+            flat.record_stream(stream)         # the allocator must not hand the block out again while the side stream uses it
         with _on(flat.device):
             _lib.check(lib.vqb_exchange_finish(ctypes.byref(tl), n_flat, ctypes.c_void_p(st.cuda_stream)))
 
