@@ -3,8 +3,16 @@
 The reference appends `unpair_prob.argmax(-1).cpu().flatten().tolist()` to a Python list every other
 step (bin/train_vqvae.py:256-261) and, every 500 steps, computes `data.count(i)/len(data)` per code with
 entry 0 forced to zero (src/util.py:139-143) before resetting the list (:310).  Here the counts are
-accumulated by the forward kernel itself into an int64 [K] buffer; `bar()` returns the same numbers
-without a per-step device->host sync.
+accumulated by the forward kernel itself into an int64 [K] buffer; `bar()` applies the same formula without a
+per-step device->host sync.
+
+WHICH ROWS ARE COUNTED differs from the reference unless the trainer says so: the kernel counts every row of every
+forward while `module.track_usage` is True (the default) -- paired and unpaired rows, validation passes included --
+whereas the reference counts only the unpaired batch's arg-max, on the speech-first steps (:256-261).  To reproduce
+the reference's plot exactly, set `codebook.track_usage = False` and switch it on around the unpaired forward only,
+or count rows of one's choosing from `module.last_idx` with `usage.add(idx)`.  (Under the reference's own, unmodified
+trainer its host list keeps working as before -- it reads p_code -- and this histogram is an extra.)  Rows masked
+by `lengths=` are never counted.
 
 Data-parallel runs: `counts` holds this rank's rows that have not been exchanged yet, `reduced` the part
 already summed over all ranks.  `all_reduce()` moves `counts` into `reduced` (sum over ranks) and zeroes it,
@@ -24,6 +32,12 @@ class UsageHistogram:
         if self.counts is None or self.counts.device != ref.device:
             self.counts = torch.zeros(self.n_codes, dtype=torch.int64, device=ref.device)
         return self.counts
+
+    def add(self, idx):
+        """count the codes of an index tensor (any shape, int64, on the histogram's device) -- for callers that pick the
+        rows themselves, e.g. `usage.add(codebook.last_idx[first_n_real_mel:])` for the reference's unpaired rows"""
+        flat = idx.reshape(-1)
+        self.buffer_for(flat).add_(torch.bincount(flat, minlength=self.n_codes)[:self.n_codes])
 
     def reset(self):
         if self.counts is not None:

@@ -28,20 +28,37 @@ def test_library_exports_every_declared_symbol():
     assert lib.vqb_abi_version() == V._lib.ABI_VERSION
 
 
+def test_nothing_is_exported_that_no_header_declares():
+    """the drop-in ABI is include/vqb.h; the developer hooks are declared (and fenced off) in include/vqb_debug.h; the
+    library exports nothing else"""
+    import subprocess
+    import semi_tts_b200 as V
+    so = os.path.join(os.path.dirname(V.__file__), "libvqb200.so")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split()[-1].startswith("vqb_")}
+    dbg = open(os.path.join(ROOT, "include", "vqb_debug.h")).read()
+    debug = set(re.findall(r"VQB_API\s+[\w\s\*]+?\b(vqb_\w+)\s*\(", dbg))
+    assert debug and all(n.startswith("vqb_debug_") for n in debug)
+    assert exported == set(_declared_symbols()) | debug
+
+
 def test_ctypes_structs_match_the_c_header(tmp_path):
     """sizeof/offsetof of the ctypes mirrors == what a C compiler makes of include/vqb.h."""
     import subprocess
     import semi_tts_b200 as V
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vqb.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vqb.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(vqb_fwd_args), offsetof(vqb_fwd_args, temp), offsetof(vqb_fwd_args, workspace_bytes),'
-                   'sizeof(vqb_bwd_args), offsetof(vqb_bwd_args, idx), offsetof(vqb_bwd_args, d_temp));return 0;}\n')
+                   'sizeof(vqb_bwd_args), offsetof(vqb_bwd_args, idx), offsetof(vqb_bwd_args, d_temp),'
+                   'offsetof(vqb_fwd_args, row_lengths), offsetof(vqb_fwd_args, ctc_eps), offsetof(vqb_bwd_args, g_logp),'
+                   'offsetof(vqb_bwd_args, tail), sizeof(vqb_bwd_tail), offsetof(vqb_bwd_tail, reserved));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    F, B = V._lib.FwdArgs, V._lib.BwdArgs
+    F, B, T = V._lib.FwdArgs, V._lib.BwdArgs, V._lib.BwdTail
     assert got == [ctypes.sizeof(F), F.temp.offset, F.workspace_bytes.offset,
-                   ctypes.sizeof(B), B.idx.offset, B.d_temp.offset]
+                   ctypes.sizeof(B), B.idx.offset, B.d_temp.offset,
+                   F.row_lengths.offset, F.ctc_eps.offset, B.g_logp.offset, B.tail.offset, ctypes.sizeof(T), T.reserved.offset]
 
 
 def test_c_program_links_and_uses_the_abi_without_python(tmp_path):
@@ -304,3 +321,16 @@ def test_drop_in_into_reference_vqvae_construction():
     new_model.load_state_dict(a, strict=True)
     assert new_model.codebook.out_dim == ref_model.codebook.out_dim
     assert "Phn. attributs = True" in new_model.create_msg()[-1] or True
+
+
+def test_usage_add_counts_chosen_rows():
+    """usage.add(idx): the caller picks the rows (the reference counts the unpaired batch only, bin/train_vqvae.py:256-261);
+    bar() then applies src/util.py:139-143 to exactly those."""
+    from semi_tts_b200.usage import UsageHistogram
+    u = UsageHistogram(6)
+    idx = torch.tensor([[1, 2, 2], [5, 0, 2]])
+    u.add(idx)
+    u.add(idx[1:])
+    assert u.all_counts().tolist() == [2, 1, 4, 0, 0, 2] and u.total() == 9
+    bar = u.bar()
+    assert bar[0] == 0.0 and abs(bar[2] - 4 / 9) < 1e-12
