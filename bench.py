@@ -218,7 +218,6 @@ def _time_kernels(V, m, sets, iters=24):
     flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.TENSOR_CORES if m.tensor_cores else 0)     # no AFTER_ASSEMBLE: launched alone
     outs = [VF._run_forward(flags, s[0].view(N_ROWS, D), table, enorm, table, m.temp, True, None, False) for s in sets]
     stream = torch.cuda.current_stream()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     fwd_ms, bwd_ms = [], []
     lib = _lib.load()
     # pre-build argument structs so only the launch is inside the events
@@ -252,21 +251,27 @@ def _time_kernels(V, m, sets, iters=24):
     sp = ctypes.c_void_p(stream.cuda_stream)
     # the library records these events on the launch stream right before / after the dominant kernel of each call
     # (vqb_debug_set_kernel_events), so helper kernels of the same call are outside the measured interval
-    for e in ev:
-        e.record(stream)
-    torch.cuda.synchronize()
     lib.vqb_debug_set_kernel_events.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.vqb_debug_set_kernel_events.restype = None
-    for i in range(iters + 4):
+    # launches go out back to back, as in the timed region (no host synchronisation between them: an isolated launch on an
+    # idle GPU adds its own start-up latency to the interval); every launch has its own event pair
+    n = iters + 4
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n)]
+    for e4 in evs:
+        for e in e4:
+            e.record(stream)              # (torch creates the CUDA event on first use; the library records it again)
+    torch.cuda.synchronize()
+    for i in range(n):
         j = i % len(sets)
-        lib.vqb_debug_set_kernel_events(ctypes.c_void_p(ev[0].cuda_event), ctypes.c_void_p(ev[1].cuda_event))
+        e = evs[i]
+        lib.vqb_debug_set_kernel_events(ctypes.c_void_p(e[0].cuda_event), ctypes.c_void_p(e[1].cuda_event))
         _lib.check(lib.vqb_forward(ctypes.byref(fa[j]), sp))
-        lib.vqb_debug_set_kernel_events(ctypes.c_void_p(ev[2].cuda_event), ctypes.c_void_p(ev[3].cuda_event))
+        lib.vqb_debug_set_kernel_events(ctypes.c_void_p(e[2].cuda_event), ctypes.c_void_p(e[3].cuda_event))
         _lib.check(lib.vqb_backward(ctypes.byref(ba[j]), sp))
-        lib.vqb_debug_set_kernel_events(None, None)
-        torch.cuda.synchronize()
-        if i >= 4:
-            fwd_ms.append(ev[0].elapsed_time(ev[1])); bwd_ms.append(ev[2].elapsed_time(ev[3]))
+    lib.vqb_debug_set_kernel_events(None, None)
+    torch.cuda.synchronize()
+    for e in evs[4:]:
+        fwd_ms.append(e[0].elapsed_time(e[1])); bwd_ms.append(e[2].elapsed_time(e[3]))
     kf = lib.vqb_forward_kernel_name(ctypes.byref(fa[0])).decode()
     kb = lib.vqb_backward_kernel_name(ctypes.byref(ba[0])).decode()
     return statistics.mean(fwd_ms), statistics.mean(bwd_ms), kf, kb
@@ -560,8 +565,9 @@ def run_ours(args, rank, world, local_rank):
                              "frac_per_kernel": {kf: fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peak, kb_: bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak},
                              "step_frac": (fwd_bytes + bwd_bytes) / (ms_total / args.steps * 1e-3) / 1e9 / peak if world == 1 else None,
                              "note": "kernel_ms = CUDA-event time of the named kernel alone: the library records the two events on "
-                                     "the launch stream immediately around that launch (vqb_debug_set_kernel_events); "
-                                     "averaged over ring-rotated inputs (> L2)",
+                                     "the launch stream immediately around that launch (vqb_debug_set_kernel_events), every launch its "
+                                     "own pair; forward and backward launches alternate back to back without host "
+                                     "synchronisation, as in the timed region; averaged over ring-rotated inputs (> L2)",
                              "algorithmic_bytes": {"fwd": fwd_bytes, "bwd": bwd_bytes}},
                 "clocks": clocks}
         if world == 1:
