@@ -43,9 +43,9 @@ def _config(world):
             "l2_policy": "ring of %d distinct input/output sets (%.0f MB touched per ring pass) > 126 MB L2" % (
                 RING, RING * (fwd_bytes + bwd_bytes) / 1e6),
             "parallelism": "dp%d (frames sharded by batch, codebook replicated; codebook-gradient sum over GPUs by this library's "
-                           "own kernels over NVLink peer memory: the backward's tail pushes, the rank-ordered sum of step i runs "
-                           "behind step i+1's forward and is joined before its backward; the usage histogram is exchanged once "
-                           "per timed window, where the trainer reads it)" % world}
+                           "own exchange kernel over NVLink peer memory (push, poll, rank-ordered sum): step i's exchange runs on "
+                           "a side stream beside step i+1 and is joined at that step's end, the last one inside the timed "
+                           "region; the usage histogram is exchanged once per timed window, where the trainer reads it)" % world}
 
 
 def _peaks():
@@ -216,6 +216,7 @@ def _time_kernels(V, m, sets, iters=24):
     attr, pw, pb = m.phn_attr.weight, m.proj_attr.weight, m.proj_attr.bias
     table, enorm, _, cache = VF.assemble_table(m.learnable_table, attr, pw, pb, want_cache=True)
     flags = _lib.SCORE_L2 | _lib.STOP_GRAD | (_lib.TENSOR_CORES if m.tensor_cores else 0)     # no AFTER_ASSEMBLE: launched alone
+    N_ROWS = sets[0][0].numel() // D            # (config 2: 51 200; the steady-state record passes 2^20-row sets)
     outs = [VF._run_forward(flags, s[0].view(N_ROWS, D), table, enorm, table, m.temp, True, None, False) for s in sets]
     stream = torch.cuda.current_stream()
     fwd_ms, bwd_ms = [], []
@@ -570,6 +571,18 @@ def run_ours(args, rank, world, local_rank):
                                      "synchronisation, as in the timed region; averaged over ring-rotated inputs (> L2)",
                              "algorithmic_bytes": {"fwd": fwd_bytes, "bwd": bwd_bytes}},
                 "clocks": clocks}
+        if world == 1 and not args.no_sweep:
+            # the same two kernels where launch latency and the single wave no longer dominate: 2^20 rows (20 x config 2)
+            big = [[torch.randn(1024, 1024, D, device=dev), torch.randn(1024, 1024, K, device=dev),
+                    torch.randn(1024, 1024, D, device=dev)] for _ in range(2)]
+            f1, b1, _, _ = _time_kernels(V, m, big, iters=8)
+            del big
+            n1 = 1 << 20
+            line["roofline"]["at_2^20_rows"] = {
+                "kernel_ms": {kf: f1, kb_: b1},
+                "frac_per_kernel": {kf: n1 * (8 * D + 8 + 4 * K) / (f1 * 1e-3) / 1e9 / peak,
+                                    kb_: n1 * (12 * D + 8 * K + 8) / (b1 * 1e-3) / 1e9 / peak},
+                "note": "same kernels, same algorithmic bytes per row, 2^20 rows per launch (inputs and outputs far beyond L2)"}
         if world == 1:
             # the CPU arm beside it: measured once, at N = 1 only (at N > 1 the other ranks would spin in a barrier meanwhile)
             cpu_rate, cpu_ms, cpu_done, cores, kind, what = cpu_fwd_bwd_rate(400, 3, budget_s=12.0)
