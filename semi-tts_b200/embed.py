@@ -76,6 +76,16 @@ class _QuantizerBase(nn.Module):
         self.fused_tail = VF.FusedTail()
         # no-grad fast path (validation / encode loops): cached table + operand image, direct C-ABI call
         self._nograd = VF.NoGradCache()
+        # extension (SURVEY 8f rank 3): set to EPS of bin/train_vqvae.py:18 and every grad-mode forward also leaves
+        # `self.ctc_logp` = log(p_code + EPS) as contiguous [S, B, K], the tensor compute_ctc_loss builds at :430-432 with a
+        # transpose + add + log -- written by the forward kernel's epilogue, its gradient folded into the backward kernel
+        self.ctc_eps = None
+        self._ctc_out = _Transient()
+
+    @property
+    def ctc_logp(self):
+        """log(p_code + ctc_eps) [S, B, K] of the last grad-mode forward (None unless `ctc_eps` is set)"""
+        return self._ctc_out.value
 
     def _init_attr(self, latent_dim, phn_attr_pth, proj_attr):
         self.use_phn_attr = phn_attr_pth is not None and phn_attr_pth != ""
@@ -161,16 +171,6 @@ class L2Embedding(_QuantizerBase):
         self.learnable_table = nn.Parameter(torch.randn((vocab_size, latent_dim - d_attr)))
         # large-codebook option: do not materialise p_code (slot 1 of the return tuple is None)
         self.fused_search = False
-        # extension (SURVEY 8f rank 3): set to EPS of bin/train_vqvae.py:18 and every grad-mode forward also leaves
-        # `self.ctc_logp` = log(p_code + EPS) as contiguous [S, B, K], the tensor compute_ctc_loss builds at :430-432 with a
-        # transpose + add + log -- written by the forward kernel's epilogue, its gradient folded into the backward kernel
-        self.ctc_eps = None
-        self._ctc_out = _Transient()
-
-    @property
-    def ctc_logp(self):
-        """log(p_code + ctc_eps) [S, B, K] of the last grad-mode forward (None unless `ctc_eps` is set)"""
-        return self._ctc_out.value
 
     @property
     def embedding(self):
@@ -198,6 +198,7 @@ class L2Embedding(_QuantizerBase):
             p_code, new_latent, idx = VF.forward_nograd(self._nograd, enc_embs, lt, attr, pw, pb, temp, skip,
                                                         not self.fused_search, self._hist(enc_embs), self.tensor_cores, lengths)
             self.__dict__["last_idx"] = idx              # (plain attribute: skips nn.Module.__setattr__)
+            self._ctc_out.value = None
             return p_code, new_latent, 0, 0
         B, S, _ = enc_embs.shape
         attr, pw, pb = self._attr_params()
@@ -235,9 +236,12 @@ class SeperateEmbedding(_QuantizerBase):
     def forward(self, enc_embs, first_n_real_mel=0):
         # first_n_real_mel is unused here, as in the reference (src/embed.py:188)
         attr, pw, pb = self._attr_params()
-        p_code, new_latent, idx = VF.vq_linear(
+        ctc_eps = self.ctc_eps if torch.is_grad_enabled() else None
+        out = VF.vq_linear(
             enc_embs, self.asr_final_layer.weight, self.asr_final_layer.bias, self.embedding.weight,
             attr, pw, pb, stop_grad=self.stop_grad, hist=self._hist(enc_embs), tensor_cores=self.tensor_cores,
-            tail=self.fused_tail)
+            tail=self.fused_tail, ctc_eps=ctc_eps)
+        p_code, new_latent, idx = out[:3]
+        self._ctc_out.value = out[3] if ctc_eps is not None else None
         self.last_idx = idx
         return p_code, new_latent, 0, 0

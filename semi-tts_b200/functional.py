@@ -601,28 +601,39 @@ class _VQLinear(torch.autograd.Function):
             raise RuntimeError("semi-tts_b200: shape mismatch between enc_embs, asr_final_layer and the embedding table")
         w, b = _c(asr_w.detach()), _c(asr_b.detach())
         flags = _fwd_flags(_lib.SCORE_LINEAR, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
-        p_code, idx, q, _ = _run_forward(flags, x2d, w, b, table, None, True, cfg.hist, False)
+        logp = None
+        if cfg.ctc_eps is not None:
+            p_code, idx, q, _, logp = _run_forward(flags, x2d, w, b, table, None, True, cfg.hist, False, frames=S,
+                                                   ctc_eps=cfg.ctc_eps)
+            if logp is None:                            # a route without the fused emission: the standalone pass
+                logp = torch.empty(S, B, K, device=x2d.device, dtype=torch.float32)
+                if B * S:
+                    with torch.cuda.device(x2d.device):
+                        _lib.check(_lib.load().vqb_ctc_logp(ptr(p_code), B, S, K, cfg.ctc_eps, ptr(logp), _stream(x2d)))
+        else:
+            p_code, idx, q, _ = _run_forward(flags, x2d, w, b, table, None, True, cfg.hist, False)
         ctx.set_materialize_grads(False)
         ctx.cfg, ctx.shape = cfg, (B, S, D, K)
         ctx.Da = proj_w.shape[0] if phn_attr is not None else 0
         ctx.save_for_backward(x2d, w, table, p_code, idx, phn_attr)
         idx3 = idx.view(B, S)
         ctx.mark_non_differentiable(idx3)
-        return p_code.view(B, S, K), q.view(B, S, D), idx3
+        return p_code.view(B, S, K), q.view(B, S, D), idx3, logp
 
     @staticmethod
-    def backward(ctx, g_p, g_q, _g_idx):
+    def backward(ctx, g_p, g_q, _g_idx, g_logp=None):
         x2d, w, table, p_code, idx, phn_attr = ctx.saved_tensors
         cfg = ctx.cfg
         B, S, D, K = ctx.shape
         N = B * S
-        if (g_p is None and g_q is None) or N == 0:
+        if (g_p is None and g_q is None and g_logp is None) or N == 0:
             return (None,) * 8
         g_p2 = _g32(g_p).view(N, K) if g_p is not None else None
         g_q2 = _g32(g_q).view(N, D) if g_q is not None else None
+        g_l = _g32(g_logp) if g_logp is not None else None
         flags = _fwd_flags(_lib.SCORE_LINEAR, cfg) | (_lib.TENSOR_CORES if cfg.tensor_cores else 0)
         dx, d_w, colsum, d_tab, _, _ = _run_backward(flags, 0, x2d, w, None, table, None, p_code, idx, g_p2, g_q2,
-                                                     True, True)
+                                                     True, True, frames=S, g_logp=g_l, ctc_eps=cfg.ctc_eps or 0.0)
         d_emb, d_pw, d_pb = _table_backward(d_tab, None, None, phn_attr, ctx.Da, cfg.tail)
         if cfg.tail is not None and cfg.tail.exchange is not None:
             from .dist import reduce_route_output
@@ -631,10 +642,13 @@ class _VQLinear(torch.autograd.Function):
         return dx.view(B, S, D), d_w, colsum, d_emb, None, d_pw, d_pb, None
 
 
-def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None, tensor_cores=True, tail=None):
-    """Separate quantizer (src/embed.py:187-205). Returns (p_code, new_latent, idx)."""
-    cfg = _Cfg(stop_grad=stop_grad, hist=hist, tensor_cores=tensor_cores, tail=tail)
-    return _VQLinear.apply(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, cfg)
+def vq_linear(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, stop_grad=True, hist=None, tensor_cores=True, tail=None,
+              ctc_eps=None):
+    """Separate quantizer (src/embed.py:187-205). Returns (p_code, new_latent, idx) and, with `ctc_eps`, a fourth value:
+    log(p_code + ctc_eps) as contiguous [S,B,K] (see vq_l2)."""
+    cfg = _Cfg(stop_grad=stop_grad, hist=hist, tensor_cores=tensor_cores, tail=tail, ctc_eps=ctc_eps)
+    out = _VQLinear.apply(x, asr_w, asr_b, emb_w, phn_attr, proj_w, proj_b, cfg)
+    return out if ctc_eps is not None else out[:3]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -740,3 +740,38 @@ def test_ctc_log_probs_from_the_forward_epilogue_and_folded_gradient(B, S, with_
     for k in ("dx", "dl", "dw", "db"):
         assert torch.allclose(f2[k], u2[k], rtol=1e-5, atol=1e-5 * float(u2[k].abs().max())), k
     _record("ctc_fold", dict(B=B, S=S, lengths=with_lengths, dx_rel_err_vs_oracle=float(rel_err(f["dx"].cpu().numpy(), ob["dx"]))))
+
+
+@pytest.mark.parametrize("B,S", [(16, 200), (8, 96), (5, 77)])
+def test_ctc_log_probs_fused_for_the_separate_quantizer(B, S):
+    """the same fusion behind SeperateEmbedding (src/embed.py:187-205; the quantizer config/supervised.yaml selects, whose
+    CTC loss reads p_code the same way): fused emission + folded gradient == standalone pass + its backward, and the
+    forward values == the oracle's log(p + EPS)."""
+    import semi_tts_b200 as V
+    g = load_golden("sep_attr_stopgrad")
+    K, D = g["sd.asr_final_layer.weight"].shape
+    gen = torch.Generator().manual_seed(B * 31 + S)
+    x = (torch.randn(B, S, D, generator=gen) * 0.7).cuda()
+    gl = torch.randn(S, B, K, generator=gen).cuda()
+    gq = torch.randn(B, S, D, generator=gen).cuda()
+
+    def run(fused):
+        m = build_module(g, "sep")
+        m.ctc_eps = 1e-10 if fused else None
+        xi = x.clone().requires_grad_(True)
+        p, q, _, _ = m(xi)
+        logp = m.ctc_logp if fused else V.ctc_log_probs(p)
+        assert logp.shape == (S, B, K) and logp.is_contiguous()
+        torch.autograd.backward([logp, q], [gl, gq])
+        grads = {n: t.grad.clone() for n, t in m.named_parameters() if t.grad is not None}
+        return p.detach(), logp.detach(), xi.grad.clone(), grads
+
+    pf, lf, dxf, gf = run(True)
+    pu, lu, dxu, gu = run(False)
+    assert torch.equal(pf, pu)
+    assert rel_err(lf.cpu().numpy(), O.ctc_input(pf.cpu().numpy().astype(np.float64))) < 1e-6
+    assert torch.allclose(lf, lu, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(dxf, dxu, rtol=1e-5, atol=1e-5 * float(dxu.abs().max()))
+    assert set(gf) == set(gu)
+    for n in gu:
+        assert torch.allclose(gf[n], gu[n], rtol=1e-5, atol=1e-5 * float(gu[n].abs().max())), n
