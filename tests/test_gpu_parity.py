@@ -775,3 +775,40 @@ def test_ctc_log_probs_fused_for_the_separate_quantizer(B, S):
     assert set(gf) == set(gu)
     for n in gu:
         assert torch.allclose(gf[n], gu[n], rtol=1e-5, atol=1e-5 * float(gu[n].abs().max())), n
+
+
+@pytest.mark.parametrize("K,D,B,S,with_lengths", [(44, 64, 8, 200, False), (64, 64, 4, 160, False), (16, 64, 8, 96, True),
+                                                  (5, 64, 4, 64, False), (37, 32, 6, 90, False), (50, 64, 3, 1000, False)])
+def test_ctc_fusion_across_codebook_sizes(K, D, B, S, with_lengths):
+    """the fused CTC input for even / small / full codebooks (staging strides, box widths and TMEM column counts all depend
+    on K) and for D = 32 (forward emission from the tensor-core kernel, gradient through the unfolded route): fused ==
+    standalone pass, forward values == the oracle's log(p + EPS)."""
+    import semi_tts_b200 as V
+    torch.manual_seed(K * 100 + D)
+    kw = dict(softmax="normal", latent_dim=D, commit_weight=0, vq_weight=0, temp=1.0, skip_prob=0, stop_grad=True)
+    gen = torch.Generator().manual_seed(K + S)
+    x = (torch.randn(B, S, D, generator=gen) * 0.8).cuda()
+    gl = torch.randn(S, B, K, generator=gen).cuda()
+    gq = torch.randn(B, S, D, generator=gen).cuda()
+    lens = torch.randint(1, S + 1, (B,), generator=gen) if with_lengths else None
+    mask = ((torch.arange(S)[None, :] < lens[:, None]) if with_lengths else torch.ones(B, S, dtype=torch.bool)).cuda()
+    base = V.L2Embedding(K, False, **kw).cuda()
+
+    def run(fused):
+        m = V.L2Embedding(K, False, **kw).cuda()
+        m.load_state_dict(base.state_dict())
+        m.ctc_eps = 1e-10 if fused else None
+        xi = x.clone().requires_grad_(True)
+        p, q, _, _ = m(xi, 0, lengths=lens) if with_lengths else m(xi)
+        logp = m.ctc_logp if fused else V.ctc_log_probs(p)
+        torch.autograd.backward([logp, q], [gl, gq])
+        return p.detach(), logp.detach(), xi.grad.clone(), m.learnable_table.grad.clone()
+
+    pf, lf, dxf, dlf = run(True)
+    pu, lu, dxu, dlu = run(False)
+    mt = mask.t()
+    assert torch.equal(pf, pu)
+    assert rel_err(lf[mt].cpu().numpy(), O.ctc_input(pf.cpu().numpy().astype(np.float64))[mt.cpu().numpy()]) < 1e-6
+    assert torch.allclose(lf[mt], lu[mt], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(dxf[mask], dxu[mask], rtol=1e-5, atol=1e-5 * float(dxu.abs().max()))
+    assert torch.allclose(dlf, dlu, rtol=1e-5, atol=1e-5 * float(dlu.abs().max()))
