@@ -550,9 +550,17 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 }
                             }
                         }
-                        float bm = v[0];
+                        float bm;                                   // batch minimum: a 5-level tree, not a 31-long dependent chain
+                        {
+                            float t16[16];
 #pragma unroll
-                        for (int j = 1; j < 32; ++j) bm = fminf(bm, v[j]);
+                            for (int j = 0; j < 16; ++j) t16[j] = fminf(v[j], v[j + 16]);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) t16[j] = fminf(t16[j], t16[j + 8]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) t16[j] = fminf(t16[j], t16[j + 4]);
+                            bm = fminf(fminf(t16[0], t16[2]), fminf(t16[1], t16[3]));
+                        }
                         if (bm <= thr) {
                             mn = fminf(mn, bm);
                             thr = mn + W;
