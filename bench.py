@@ -45,7 +45,8 @@ def _config(world):
             "parallelism": "dp%d (frames sharded by batch, codebook replicated; codebook-gradient sum over GPUs by this library's "
                            "own exchange kernel over NVLink peer memory (push, poll, rank-ordered sum): step i's exchange runs on "
                            "a side stream beside step i+1 and is joined at that step's end, the last one inside the timed "
-                           "region; the usage histogram is exchanged once per timed window, where the trainer reads it)" % world}
+                           "region; the usage histogram is exchanged every 500 steps, the cadence at which the trainer reads it "
+                           "(bin/train_vqvae.py:305), so a timed window shorter than that holds no histogram exchange)" % world}
 
 
 def _peaks():
@@ -303,6 +304,31 @@ def _log(rank, msg):
 _T0 = time.perf_counter()
 
 
+def _bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: pin this process (and with it the pinned host buffers it allocates from here on: Linux allocates on
+    the node of the running CPU) to the NUMA node the GPU's PCIe root hangs off, so that the per-step upload does not cross
+    the socket interconnect.  Returns what was done, for the JSON line; None if the topology is not visible."""
+    if os.environ.get("VQB_NO_NUMA_BIND"):
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        addr = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % addr).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": addr, "node": node, "cpus": len(cpus)}
+    except Exception:                 # noqa: BLE001 -- no topology in this container: leave the process where it is
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import faulthandler
     faulthandler.dump_traceback_later(240, exit=True)      # a wedged collective must not eat the GPU budget
@@ -312,11 +338,13 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
+    numa = None
     if dist_on:
         import datetime
         import torch.distributed as dist
+        numa = _bind_to_gpu_numa_node(local_rank)       # (N = 1 keeps every core: the CPU baseline runs in this process)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
-        _log(rank, "process group up (world %d)" % world)
+        _log(rank, "process group up (world %d), numa binding %s" % (world, numa))
     torch.manual_seed(0)
     m = V.L2Embedding(K, False, **_codebook_kwargs()).to(dev)
     m.train()
@@ -404,12 +432,16 @@ def run_ours(args, rank, world, local_rank):
         launches_per_step = int(lib_.vqb_launch_count() - l0)
     _log(rank, "launch mode: %s, %d libvqb200 kernels per step" % ("cuda_graph" if use_graph else "eager", launches_per_step))
 
+    USAGE_EVERY = 500                       # the trainer reads (and resets) the usage histogram every 500 steps (:305, :310)
+
     def run_steps(n, first=0):
         for i in range(n):
             if use_graph:
                 graphs[(first + i) % RING].replay()
             else:
                 step(sets[(first + i) % RING])
+            if dist_on and (i + 1) % USAGE_EVERY == 0:
+                V.dist.allreduce_usage(m)   # at the reference's own cadence, inside the timed region when it falls there
 
     def barrier():
         if dist_on:
@@ -428,8 +460,9 @@ def run_ours(args, rank, world, local_rank):
     run_steps(args.steps, first=args.warmup)
     if dist_on:
         V.dist.finish_codebook_grads(m)    # the last step's exchange (deferred mode) completes inside the timed region
-        V.dist.allreduce_usage(m)          # bin/train_vqvae.py:305 reads the histogram once per 500-step window
     e1.record()
+    if dist_on:
+        V.dist.allreduce_usage(m)          # what is pending of the current 500-step window (outside the timed region)
     barrier()
     ms_total = e0.elapsed_time(e1)
     if dist_on:
@@ -556,6 +589,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                         "launch_mode": "cuda_graph per upload buffer" if e2e_graphs else "eager",
+                        "numa_binding_rank0": numa,
                         "note": "enc_embs uploaded from pinned host memory every step; the upstream gradients are device-resident "
                                 "(the downstream losses produce them on the device); indices, parameter gradients and the usage "
                                 "histogram read back every step"},
