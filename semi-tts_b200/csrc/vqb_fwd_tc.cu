@@ -550,16 +550,17 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 }
                             }
                         }
-                        float bm;                                   // batch minimum: a 5-level tree, not a 31-long dependent chain
+                        // batch minimum as a tree, not a 31-long dependent chain; its second level -- eight minima over the
+                        // column groups {g, g + 8, g + 16, g + 24} -- is kept: the candidate scan below only opens the groups
+                        // that hold something inside the window
+                        float bm, t8[8];
                         {
                             float t16[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) t16[j] = fminf(v[j], v[j + 16]);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) t16[j] = fminf(t16[j], t16[j + 8]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) t16[j] = fminf(t16[j], t16[j + 4]);
-                            bm = fminf(fminf(t16[0], t16[2]), fminf(t16[1], t16[3]));
+                            for (int j = 0; j < 8; ++j) t8[j] = fminf(t16[j], t16[j + 8]);
+                            bm = fminf(fminf(fminf(t8[0], t8[4]), fminf(t8[2], t8[6])), fminf(fminf(t8[1], t8[5]), fminf(t8[3], t8[7])));
                         }
                         if (bm <= thr) {
                             mn = fminf(mn, bm);
@@ -573,11 +574,18 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 }
                                 cnt = kept;
                             }
+                            // (the order of the list does not matter: the re-rank breaks ties by code index)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (v[j] <= thr) {
-                                    if (cnt < CAP) sCandG[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
-                                    else overflow = true;
+                            for (int g = 0; g < 8; ++g) {
+                                if (t8[g] <= thr) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int j = g + 8 * q;
+                                        if (v[j] <= thr) {
+                                            if (cnt < CAP) sCandG[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
+                                            else overflow = true;
+                                        }
+                                    }
                                 }
                             }
                         }
