@@ -199,8 +199,8 @@ __device__ __forceinline__ float prep_tile(const uint8_t* sX, uint8_t* sXlo, uin
 // (build_f16_operands_kernel).  Exactness is untouched: the re-rank, the gather and the straight-through need the raw fp32
 // tile again, so it is simply fetched a second time (from L2) once the tile's last MMA has retired -- 128 KB against the
 // 8 MB of codebook that streamed through meanwhile.
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG, bool F16>
-__global__ void __launch_bounds__(192, 1)
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG, bool F16, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
 vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                   const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_q, TcP p) {
     constexpr int PIECE = BN * 128;                               // one codebook K-block in bytes
@@ -208,10 +208,16 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     constexpr int PIECES = F16 ? KH : (PASSES == 3 ? 2 * KB : KB) + (NOAUG ? 0 : 1);   // per chunk: hi/lo per K-block + the bias block
     static_assert(!NOAUG || (PASSES == 1 && !RESIDENT), "NOAUG: streamed one-pass search");
     static_assert(!F16 || (NOAUG && KB % 2 == 0), "F16: one-pass streamed search, D a multiple of 64, bias added by the epilogue");
+    // EW = 2 (streamed 1xTF32 search, D <= 128): a SECOND epilogue warpgroup.  Both read the same TMEM lanes (thread = row)
+    // but different column halves of every chunk, each with its own running minimum and candidate list; the lists are
+    // merged under the window of the smaller minimum before the exact re-rank (each list is a superset of what that
+    // window needs from its half, because a half's own threshold is never tighter).  At D <= 128 the chunk time is the
+    // epilogue's, not the MMA's (profiles/r2_ncu_lines_search_d64.txt), and one warp per scheduler hides nothing.
+    static_assert(EW == 1 || (EW == 2 && PASSES == 1 && !RESIDENT && !NOAUG && !F16), "second epilogue warpgroup: streamed 1xTF32 search");
     constexpr int TMEM_COLS = 2 * BN;
     constexpr int CAP = NOAUG ? 15 : 16;                          // per-row candidate list capacity (SEARCH); 15: fits 227 KB
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
-    constexpr int NTHREADS = 192;
+    constexpr int NTHREADS = 64 + 128 * EW;
     constexpr int XLS = XS;                                       // x_lo slots
 
     extern __shared__ uint8_t smem_raw[];
@@ -221,7 +227,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint8_t* sAug = sXlo + (PASSES == 3 ? (size_t)XLS * KB * XBLK : 0);        // [16 KB] A block [1,1,1,0,...]
     uint8_t* sB = sAug + (NOAUG ? 0 : XBLK);                                   // [BS][PIECE]
     uint2* sCand = reinterpret_cast<uint2*>(sB + (size_t)BS * PIECE);          // [CAP][128] (value, code)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sCand) + CAP * BM * 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sCand) + EW * CAP * BM * 8);   // [EW] lists
     uint64_t* x_full = bars;
     uint64_t* x_empty = x_full + XS;
     uint64_t* xlo_full = x_empty + XS;
@@ -246,7 +252,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_prefetch_desc(&tm_q);
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * EW); }
         mbar_init(xlo_free, 1);
         for (int i = 0; i < XS; ++i) mbar_init(&xr_full[i], 1);
         fence_barrier_init();
@@ -392,8 +398,11 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // =============================== epilogue (thread = row) ==========================================
         const int q4 = warp & 3;                                    // TMEM lane quadrant this warp may read
         const int r = q4 * 32 + lane;                               // row within the tile == TMEM lane
-        constexpr int wg = 0, cg = 0;                               // (one epilogue warpgroup; names kept for the timeline macro)
+        const int wg = (warp - 2) >> 2, cg = wg;                    // epilogue warpgroup (0: primary; 1: second column half, EW == 2)
         const int et = ((warp - 2) & 3) * 32 + lane;                // 0..127 within the warpgroup
+        // (EW == 2) minimum / count / overflow of the second half: the last entry row of the second list (which holds CAP - 1)
+        int2* sMerge = reinterpret_cast<int2*>(sCand + (size_t)(2 * CAP - 1) * BM);
+        const int cap = CAP - ((EW == 2 && wg == 1) ? 1 : 0);
         const uint32_t bar_id = 1 + wg;                             // named barrier of this warpgroup
         const bool linear = (p.flags & VQB_SCORE_LINEAR) != 0;
         const float tau = linear ? 1.f : fmaxf(__ldg(p.temp), 0.f);
@@ -516,24 +525,16 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 float mn = INFINITY, thr = INFINITY;
                 int cnt = 0;
                 bool overflow = false;
-                uint2* sCandG = sCand;
+                uint2* sCandG = sCand + (size_t)wg * CAP * BM;           // this warpgroup's list
+                if (EW == 2 && wg == 1 && x_it > 0)
+                    asm volatile("bar.sync 4, 256;" ::: "memory");        // the primary has read the previous tile's list
                 // NOAUG: |e|^2 of the chunk's codes, staged by the row threads themselves (thread et <-> code), double-buffered;
                 // the value of the next chunk is fetched one iteration ahead.  Codes beyond K get +1e30 (never the minimum).
                 float* sEn = reinterpret_cast<float*>(sAfterBars + 2 * BM);     // [2][BN]
                 float en_next = 0.f;
                 if (NOAUG) en_next = et < p.K ? __ldg(p.bias + et) : 1e30f;
-                for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
-                    const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
-                    if (NOAUG) {
-                        sEn[(chunk & 1) * BN + et] = en_next;
-                        const int nk = (chunk + 1) * BN + et;
-                        en_next = (chunk + 1 < p.num_chunks && nk < p.K) ? __ldg(p.bias + nk) : 1e30f;
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // chunk's enorm visible; the buffer written
-                    }                                                                  // now was last read two chunks ago
-                    mbar_wait(&t_full[buf], tph);
-                    tcgen05_fence_after();
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
+                // one 32-column batch of a chunk's accumulator: minimum, window test, candidate list (both warpgroups)
+                auto scan_batch = [&](const int c, const uint32_t buf, const int chunk) {
                         float v[32];
                         tmem_ld_32x32(tmem_base + lane_addr + buf * BN + c * 32, v);
                         const int col0 = chunk * BN + c * 32;
@@ -565,7 +566,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         if (bm <= thr) {
                             mn = fminf(mn, bm);
                             thr = mn + W;
-                            if (cnt > 0 && cnt >= CAP - 4) {
+                            if (cnt > 0 && cnt >= cap - 4) {
                                 // make room: drop entries that fell out of the (tighter) window
                                 int kept = 0;
                                 for (int c2 = 0; c2 < cnt; ++c2) {
@@ -582,14 +583,26 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                     for (int q = 0; q < 4; ++q) {
                                         const int j = g + 8 * q;
                                         if (v[j] <= thr) {
-                                            if (cnt < CAP) sCandG[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
+                                            if (cnt < cap) sCandG[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
                                             else overflow = true;
                                         }
                                     }
                                 }
                             }
                         }
-                    }
+                                    };
+                for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
+                    const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                    if (NOAUG) {
+                        sEn[(chunk & 1) * BN + et] = en_next;
+                        const int nk = (chunk + 1) * BN + et;
+                        en_next = (chunk + 1 < p.num_chunks && nk < p.K) ? __ldg(p.bias + nk) : 1e30f;
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // chunk's enorm visible; the buffer written
+                    }                                                                  // now was last read two chunks ago
+                    mbar_wait(&t_full[buf], tph);
+                    tcgen05_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32 / EW; ++c) scan_batch(c + wg * (BN / 32 / EW), buf, chunk);
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
@@ -604,13 +617,29 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     }
                     mbar_wait(&xr_full[xs], xph);
                 }
+                int ctot1 = 0;                                              // entries in the second warpgroup's list
+                if constexpr (EW == 2) {
+                    if (wg == 1) {
+                        // second column half: publish minimum, count and overflow; the primary merges, re-ranks and stores
+                        sMerge[r] = make_int2(__float_as_int(mn), cnt | (overflow ? 0x10000 : 0));
+                        asm volatile("bar.arrive 3, 256;" ::: "memory");
+                        ++x_it;
+                        continue;
+                    }
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    const int2 o = sMerge[r];
+                    mn = fminf(mn, __int_as_float(o.x));
+                    thr = mn + W;                                           // the window of the row's overall approximate minimum
+                    ctot1 = o.y & 0xffff;
+                    overflow = overflow || (o.y & 0x10000) != 0;
+                }
                 const int ctot = cnt;
                 // survivors of the final window -> exact fp32 re-rank (same expression / fmaf order as the SIMT kernel)
                 int ncand = 0;
                 float bs_ = -INFINITY;
                 int first = 0;
-                for (int c2 = 0; c2 < ctot; ++c2) {
-                    const uint2 e = sCand[c2 * BM + r];
+                for (int c2 = 0; c2 < ctot + ctot1; ++c2) {
+                    const uint2 e = sCand[(c2 < ctot ? c2 : CAP + c2 - ctot) * BM + r];
                     if (__uint_as_float(e.x) <= thr) { if (ncand == 0) first = (int)e.y; ++ncand; }
                 }
                 const bool full_scan = valid && overflow;
@@ -622,8 +651,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         if (sc > bs_) { bs_ = sc; best = k; }
                     }
                 } else if (rerank) {
-                    for (int c2 = 0; c2 < ctot; ++c2) {
-                        const uint2 e = sCand[c2 * BM + r];
+                    for (int c2 = 0; c2 < ctot + ctot1; ++c2) {
+                        const uint2 e = sCand[(c2 < ctot ? c2 : CAP + c2 - ctot) * BM + r];
                         if (__uint_as_float(e.x) <= thr) {
                             const int k = (int)e.y;
                             const float sc = exact_score<KB>(sXt, r, xx, p.table, p.bias, k, tau);
@@ -631,6 +660,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         }
                     }
                 }
+                if (EW == 2) asm volatile("bar.arrive 4, 256;" ::: "memory");   // the second list may be overwritten
                 if (p.stats) {
                     const unsigned m1 = __ballot_sync(0xffffffffu, rerank), m2 = __ballot_sync(0xffffffffu, full_scan);
                     if (lane == 0) {
@@ -871,18 +901,18 @@ int forward_tensor_workspace(const vqb_fwd_args* a, size_t* bytes) {
     return VQB_OK;
 }
 
-template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG = false, bool F16 = false>
+template <int KB, int BN, int XS, int BS, int PASSES, bool RESIDENT, bool NOAUG = false, bool F16 = false, int EW = 1>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tl, const CUtensorMap& tq, const TcP& p,
                      cudaStream_t s) {
     const size_t smem = (size_t)XS * KB * XBLK + (PASSES == 3 ? (size_t)XS * KB * XBLK : 0) + (NOAUG ? 0 : XBLK) +
-                        (size_t)BS * BN * 128 + (NOAUG ? 15 : 16) * BM * 8 + 1024 + 320 + 2 * BM * 4 + (NOAUG ? 2 * BN * 4 : 0);
+                        (size_t)BS * BN * 128 + (size_t)EW * (NOAUG ? 15 : 16) * BM * 8 + 1024 + 320 + 2 * BM * 4 + (NOAUG ? 2 * BN * 4 : 0);
     if ((int)smem > max_optin_smem()) return invalid("vqb_forward: tensor-core configuration needs %zu B of shared memory", smem);
-    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, NOAUG, F16>;
+    auto kern = vqb_fwd_tc_kernel<KB, BN, XS, BS, PASSES, RESIDENT, NOAUG, F16, EW>;
     VQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     // PDL: this call has just launched build_operands_kernel; the prologue and the first x tile overlap it
     kernel_event_begin(s);
-    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, s, tx, th, tl, tq, p));
+    VQB_CUDA(launch_pdl(kern, dim3(grid), dim3(64 + 128 * EW), smem, s, tx, th, tl, tq, p));
     kernel_event_end(s);
     VQB_CHECK_LAUNCH("vqb_fwd_tc_kernel");
     return VQB_OK;
@@ -957,6 +987,15 @@ int launch_forward_tensor(const vqb_fwd_args* a, cudaStream_t s) {
         if (D == 64)  return launch_tc<2, 128, 2, 8, 1, false, true, true>(tx, th, tl, tq, p, s);
         if (D == 128) return launch_tc<4, 128, 1, 8, 1, false, true, true>(tx, th, tl, tq, p, s);
         return launch_tc<8, 128, 1, 5, 1, false, true, true>(tx, th, tl, tq, p, s);
+    }
+    // D <= 128: two epilogue warpgroups (EW = 2); the second candidate list costs one ring slot where shared memory is full.
+    // VQB_SEARCH_EW1=1 (developer A/B): the single-warpgroup kernels
+    static const bool ew1 = getenv("VQB_SEARCH_EW1") != nullptr;
+    if (!ew1) {
+        //                                KB  BN  XS BS PASSES RESIDENT NOAUG  F16   EW
+        if (D == 32)  return launch_tc<1, 128, 2, 8, 1, false, false, false, 2>(tx, th, tl, tq, p, s);
+        if (D == 64)  return launch_tc<2, 128, 2, 7, 1, false, false, false, 2>(tx, th, tl, tq, p, s);
+        if (D == 128) return launch_tc<4, 128, 1, 7, 1, false, false, false, 2>(tx, th, tl, tq, p, s);
     }
     switch (D) {
         case 32:  return launch_tc<1, 128, 2, 8, 1, false>(tx, th, tl, tq, p, s);
