@@ -39,8 +39,13 @@ reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int K, floa
     }
     float a = 0.f;
     if (src) {
-#pragma unroll 5
-        for (int cta = ty; cta < n_cta; cta += 32) a += __ldg(src + (size_t)cta * H_PARTIAL_FLOATS);
+        for (int c0 = ty; c0 < n_cta; c0 += 320) {                  // ten records per round, all loads before the first add
+            float va[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u) va[u] = c0 + 32 * u < n_cta ? __ldg(src + (size_t)(c0 + 32 * u) * H_PARTIAL_FLOATS) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 10; ++u) a += va[u];
+        }
     }
     red[ty][tx] = a;
     __syncthreads();
@@ -129,11 +134,19 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
         const int i = li, k = lk, d = ld;
         float a = 0.f, c = 0.f;
         if (live) {
-#pragma unroll 5
-            for (int cta = ty; cta < n_cta; cta += 32) {
-                const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
-                a += __ldg(rec + k * 64 + d);
-                c += __ldg(rec + 2 * H_KD + k);
+            // ten records per round, every load issued before the first add (the sum keeps its fixed order: missing records
+            // add 0): one round trip to L2 instead of one per unrolled group -- <= 320 records, i.e. one round on a B200
+            for (int c0 = ty; c0 < n_cta; c0 += 320) {
+                float va[10], vc[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) {
+                    const int cta = c0 + 32 * u;
+                    const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
+                    va[u] = cta < n_cta ? __ldg(rec + k * 64 + d) : 0.f;
+                    vc[u] = cta < n_cta ? __ldg(rec + 2 * H_KD + k) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 10; ++u) { a += va[u]; c += vc[u]; }
             }
         }
         red[ty][tx] = a; red2[ty][tx] = c;
@@ -154,11 +167,17 @@ bwd_tail_kernel(const float* __restrict__ partial, int n_cta, int K, TailP t) {
         for (int h = 0; h < 2; ++h) {
             const int k = tx + 32 * h;
             if (k < K) {
-#pragma unroll 5
-                for (int cta = ty; cta < n_cta; cta += 32) {
-                    const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
-                    a[h] += __ldg(rec + H_KD + (Dl + j) * 64 + k);   // column-major copy: lanes read consecutive codes
-                    c[h] += __ldg(rec + 2 * H_KD + k);
+                for (int c0 = ty; c0 < n_cta; c0 += 320) {           // (as above: all loads of a round first)
+                    float va[10], vc[10];
+#pragma unroll
+                    for (int u = 0; u < 10; ++u) {
+                        const int cta = c0 + 32 * u;
+                        const float* rec = partial + (size_t)cta * H_PARTIAL_FLOATS;
+                        va[u] = cta < n_cta ? __ldg(rec + H_KD + (Dl + j) * 64 + k) : 0.f;   // column-major copy: lanes read consecutive codes
+                        vc[u] = cta < n_cta ? __ldg(rec + 2 * H_KD + k) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 10; ++u) { a[h] += va[u]; c[h] += vc[u]; }
                 }
             }
         }
