@@ -334,3 +334,28 @@ def test_usage_add_counts_chosen_rows():
     assert u.all_counts().tolist() == [2, 1, 4, 0, 0, 2] and u.total() == 9
     bar = u.bar()
     assert bar[0] == 0.0 and abs(bar[2] - 4 / 9) < 1e-12
+
+
+def test_bench_reference_arm_runs_on_the_cpu_and_keeps_the_contract():
+    """bench.py --impl reference: ONE JSON line on stdout with the GPU arm's metric / unit / config, impl = reference, a
+    cpu_baseline that says what was timed, and the e2e object; the GPU arm refuses to run without a GPU (no CPU fallback)."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "vq_fwd_bwd_frames_per_sec" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench._config(1)                 # the dict the GPU arm prints (same function, same arguments)
+    if not torch.cuda.is_available():
+        gpu = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-sweep"],
+                             capture_output=True, text=True, timeout=600, env=env)
+        assert gpu.returncode != 0 and "no CPU fallback" in gpu.stderr
