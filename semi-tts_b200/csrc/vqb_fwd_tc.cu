@@ -576,18 +576,33 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 cnt = kept;
                             }
                             // (the order of the list does not matter: the re-rank breaks ties by code index)
+                            // Which groups hold something: a bit mask first, then one loop turn per set bit -- a jump table
+                            // picks the group's four registers and the pushes are predicated, so a batch costs a handful of
+                            // branches instead of eight group tests plus four value tests per group.
+                            unsigned gm = 0;
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                if (t8[g] <= thr) {
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const int j = g + 8 * q;
-                                        if (v[j] <= thr) {
-                                            if (cnt < cap) sCandG[(cnt++) * BM + r] = make_uint2(__float_as_uint(v[j]), (unsigned)(col0 + j));
-                                            else overflow = true;
-                                        }
-                                    }
+                            for (int g = 0; g < 8; ++g) gm |= t8[g] <= thr ? (1u << g) : 0u;
+                            while (gm) {
+                                const int g = __ffs(gm) - 1;
+                                gm &= gm - 1;
+                                float a0, a1, a2, a3;
+                                switch (g) {
+                                    case 0: a0 = v[0]; a1 = v[8]; a2 = v[16]; a3 = v[24]; break;
+                                    case 1: a0 = v[1]; a1 = v[9]; a2 = v[17]; a3 = v[25]; break;
+                                    case 2: a0 = v[2]; a1 = v[10]; a2 = v[18]; a3 = v[26]; break;
+                                    case 3: a0 = v[3]; a1 = v[11]; a2 = v[19]; a3 = v[27]; break;
+                                    case 4: a0 = v[4]; a1 = v[12]; a2 = v[20]; a3 = v[28]; break;
+                                    case 5: a0 = v[5]; a1 = v[13]; a2 = v[21]; a3 = v[29]; break;
+                                    case 6: a0 = v[6]; a1 = v[14]; a2 = v[22]; a3 = v[30]; break;
+                                    default: a0 = v[7]; a1 = v[15]; a2 = v[23]; a3 = v[31]; break;
                                 }
+                                auto push = [&](const float val, const int col) {
+                                    const bool hit = val <= thr, room = cnt < cap;
+                                    if (hit && room) sCandG[cnt * BM + r] = make_uint2(__float_as_uint(val), (unsigned)col);
+                                    cnt += (hit && room) ? 1 : 0;
+                                    overflow = overflow || (hit && !room);
+                                };
+                                push(a0, col0 + g); push(a1, col0 + g + 8); push(a2, col0 + g + 16); push(a3, col0 + g + 24);
                             }
                         }
                                     };
