@@ -214,7 +214,10 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // window needs from its half, because a half's own threshold is never tighter).  At D <= 128 the chunk time is the
     // epilogue's, not the MMA's (profiles/r2_ncu_lines_search_d64.txt), and one warp per scheduler hides nothing.
     static_assert(EW == 1 || (EW == 2 && PASSES == 1 && !RESIDENT && !NOAUG && !F16), "second epilogue warpgroup: streamed 1xTF32 search");
-    constexpr int TMEM_COLS = 2 * BN;
+    // accumulator buffers in TMEM: four for the streamed kernels (all 512 columns; one CTA per SM) -- the epilogue's time per
+    // chunk varies with the candidate scans, the MMA's does not, and two buffers let each side wait for the other
+    constexpr int NB = RESIDENT ? 2 : 4;
+    constexpr int TMEM_COLS = NB * BN;
     constexpr int CAP = NOAUG ? 15 : 16;                          // per-row candidate list capacity (SEARCH); 15: fits 227 KB
     static_assert(!RESIDENT || BS == PIECES, "resident codebook needs one slot per piece");
     constexpr int NTHREADS = 64 + 128 * EW;
@@ -234,8 +237,8 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint64_t* b_full = xlo_full + XS;
     uint64_t* b_empty = b_full + BS;
     uint64_t* t_full = b_empty + BS;
-    uint64_t* t_empty = t_full + 2;
-    uint64_t* xlo_free = t_empty + 2;
+    uint64_t* t_empty = t_full + NB;
+    uint64_t* xlo_free = t_empty + NB;
     uint64_t* xr_full = xlo_free + 1;                             // [XS] F16: the raw x tile has been fetched again
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xr_full + XS);
     // per-row index words [128] and (NOAUG) the |e|^2 staging [2][BN] behind the barriers, 16-byte aligned (float4 reads)
@@ -252,7 +255,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_prefetch_desc(&tm_q);
         for (int i = 0; i < XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); mbar_init(&xlo_full[i], 4); }
         for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * EW); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * EW); }
         mbar_init(xlo_free, 1);
         for (int i = 0; i < XS; ++i) mbar_init(&xr_full[i], 1);
         fence_barrier_init();
@@ -321,7 +324,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if ((PASSES == 3 && !RESIDENT) || F16) mbar_wait(&xlo_full[xls], xlph);   // x_lo written / x converted to fp16
                 tcgen05_fence_after();
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
-                    const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                    const uint32_t buf = c_it % NB, tph = (c_it / NB) & 1;
                     mbar_wait(&t_empty[buf], tph ^ 1);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
@@ -607,7 +610,7 @@ vqb_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         }
                                     };
                 for (int chunk = 0; chunk < p.num_chunks; ++chunk) {
-                    const uint32_t buf = c_it & 1, tph = (c_it >> 1) & 1;
+                    const uint32_t buf = c_it % NB, tph = (c_it / NB) & 1;
                     if (NOAUG) {
                         sEn[(chunk & 1) * BN + et] = en_next;
                         const int nk = (chunk + 1) * BN + et;
