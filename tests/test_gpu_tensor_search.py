@@ -22,7 +22,10 @@ def _case(N, K, D, seed, scale=1.0):
                                    (4096, 1024, 64), (2500, 4096, 256), (777, 8192, 64),
                                    (1500, 1000, 256), (300, 130, 256),
                                    # several tiles per CTA on the streamed 3xTF32 kernels (x / x_lo slots alternate)
-                                   (60000, 256, 64), (45000, 200, 32)])
+                                   (60000, 256, 64), (45000, 200, 32),
+                                   # several tiles per CTA on the 1xTF32 kernels with two epilogue warpgroups (D <= 128, K > 1024):
+                                   # the second warpgroup's list is handed over and released once per tile
+                                   (40000, 2048, 64), (40000, 1500, 32), (20000, 2048, 128)])
 def test_tensor_search_equals_exact_simt_search(N, K, D):
     import semi_tts_b200 as V
     x, e = _case(N, K, D, seed=N + K + D)
