@@ -3,12 +3,14 @@
 // distance matrix never leaves TMEM.  Replaces neg_batch_l2 + argmax + F.embedding + straight-through of
 // src/embed.py:208-213, :130, :134, :145.  (The parity-mode forward, where p_code is part of the result, is vqb_fwd_pc.cu.)
 //
-// Anatomy (one persistent CTA per SM, 6 warps, warp-specialised):
+// Anatomy (one persistent CTA per SM, 6 or 10 warps, warp-specialised):
 //   warp 0  TMA producer   x tile [128 rows][D] fp32 (double-buffered when it fits); codebook K-blocks
 //                          [BN codes][32 floats]: resident in shared memory when the codebook is one chunk,
 //                          otherwise streamed through a ring
-//   warp 1  MMA issuer     tcgen05.mma kind::tf32, M=128, N=BN, K=8; accumulators double-buffered in TMEM
+//   warp 1  MMA issuer     tcgen05.mma kind::tf32 / kind::f16, M=128, N=BN; two (resident codebook) or four (streamed)
+//                          accumulator buffers in TMEM
 //   warps 2-5 epilogue     tcgen05.ld 32x32b: thread = row, so the running minimum / candidate list are thread-local
+//   warps 6-9 (EW = 2: streamed 1xTF32 search, D <= 128) a second epilogue warpgroup on the other column half of every chunk
 //
 // Precision.  kind::tf32 reads the top 19 bits of each fp32 operand.  PASSES = 3 ("3xTF32") adds the two
 // cross terms with the operands' low parts: x = x_hi + x_lo (x_hi = hardware truncation of the raw tile, x_lo
