@@ -359,3 +359,27 @@ def test_bench_reference_arm_runs_on_the_cpu_and_keeps_the_contract():
         gpu = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-sweep"],
                              capture_output=True, text=True, timeout=600, env=env)
         assert gpu.returncode != 0 and "no CPU fallback" in gpu.stderr
+
+
+def test_per_step_holders_do_not_travel_with_the_module():
+    """the CTC log-probability holder and the no-grad cache are per-step / per-device state: copy.deepcopy and pickle of
+    the module work with a graph tensor parked in them and produce empty holders; the state dict does not see them; the
+    cached parameter tuple of the no-grad path follows a replaced Parameter."""
+    import copy
+    import pickle
+    g = load_golden("l2_attr_stopgrad")
+    m = build_module(g, "l2", device="cpu")
+    leaf = torch.ones(3, requires_grad=True)
+    m._ctc_out.value = leaf * 2.0                       # a non-leaf tensor: deepcopy of it alone would raise
+    m.ctc_eps = 1e-10
+    keys = list(m.state_dict().keys())
+    m2 = copy.deepcopy(m)
+    assert m2.ctc_logp is None and m2.ctc_eps == 1e-10 and m.ctc_logp is not None
+    m3 = pickle.loads(pickle.dumps(m))
+    assert m3.ctc_logp is None and list(m3.state_dict().keys()) == keys == list(m2.state_dict().keys())
+    assert torch.equal(m3.learnable_table, m.learnable_table)
+    p0 = m._nograd_params()
+    assert p0[0] is m.learnable_table and p0[4] is m.temp and m._nograd_params() is p0
+    m.learnable_table = torch.nn.Parameter(m.learnable_table.detach().clone())
+    p1 = m._nograd_params()
+    assert p1 is not p0 and p1[0] is m.learnable_table
